@@ -1,0 +1,141 @@
+// Shared declarations for libgpmpc.so (sm_100a).  Internal header -- the public C ABI is include/gpmpc.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/gpmpc.h"
+
+namespace gpmpc {
+
+constexpr int kTile = 64;          // padding granule of n (fit GEMM tiles are 64x64)
+constexpr int kPairTile = 32;      // pair-space tile edge of the moment-matching kernels
+constexpr int kMaxD = GPMPC_MAX_D;
+constexpr int kMaxE = GPMPC_MAX_E;
+constexpr int kGroupMax = 4;       // outputs evaluated per pair-kernel pass (sharing one exp)
+
+// number of accumulated statistics per (rollout, output) in q-space: T, N1[D], N2[D]
+__host__ __device__ constexpr int nacc(int D) { return 1 + 2 * D; }
+// tape entries per (rollout, step, output): mean, var, dm/du[D], dm/ds[D], dv/du[D], dv/ds[D]
+__host__ __device__ constexpr int ntape(int D) { return 2 + 4 * D; }
+
+struct DevBuf {                    // grow-only device buffer
+    void *p = nullptr;
+    size_t bytes = 0;
+    cudaError_t reserve(size_t need) {
+        if (need <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e == cudaSuccess) bytes = need;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct LambdaGroup {               // outputs whose propagation length-scales are bit-identical
+    int count = 0;
+    int outputs[kMaxE];
+};
+
+}  // namespace gpmpc
+
+struct gpmpc_ctx {
+    int device = 0, D = 0, E = 0, m = 0;
+    int n = 0, ld = 0;             // training points and padded leading dimension (multiple of 64)
+    cudaStream_t stream = nullptr;
+    std::string err;
+    long long launches = 0;
+
+    // hyper-parameters (host copies).  *_fit were used for Ky^-1, *_prop are used by moment matching.
+    double lam_fit[gpmpc::kMaxE][gpmpc::kMaxD], sf_fit[gpmpc::kMaxE], noise[gpmpc::kMaxE];
+    double lam_prop[gpmpc::kMaxE][gpmpc::kMaxD], sf_prop[gpmpc::kMaxE];
+    std::vector<gpmpc::LambdaGroup> groups;
+    bool fitted = false;
+
+    // device state
+    gpmpc::DevBuf X;               // [ld, D]  (rows >= n are zero)
+    gpmpc::DevBuf Y;               // [E, ld]
+    gpmpc::DevBuf Kinv;            // [E, ld, ld]
+    gpmpc::DevBuf Wt;              // [E, ld, ld]  moment-matching weights (see fit.cu: derive_weights)
+    gpmpc::DevBuf beta;            // [E, ld]
+    gpmpc::DevBuf chol, zt, tt;    // fit workspaces: L [ld,ld], L^-T [ld,ld], panel [ld,64]
+    gpmpc::DevBuf linv;            // [64,64] inverse of the current diagonal block
+    gpmpc::DevBuf info;            // int: index of first bad pivot + 1, 0 = ok
+    gpmpc::DevBuf hyp;             // device copy of propagation hypers: lam[E,D], sf[E]
+
+    // rollout workspaces (grow-only)
+    gpmpc::DevBuf mu, var, tape, cst, part, mpart, stage_in, stage_out, gbuf;
+    int tape_B = 0, tape_H = 0;    // shape of the tape held from the last rollout
+
+    // timing of the last pair-kernel sequence
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_pair_ms = 0.0;
+    long long last_pair_evals = 0;
+    bool time_pairs = false;
+};
+
+namespace gpmpc {
+
+inline int fail(gpmpc_ctx *h, int code, const std::string &msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+#define GP_CUDA(h, call)                                                                       \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return gpmpc::fail((h), GPMPC_ERR_CUDA,                                            \
+                               std::string(#call) + ": " + cudaGetErrorString(e_));            \
+    } while (0)
+
+#define GP_LAUNCH_CHECK(h)                                                                     \
+    do {                                                                                       \
+        (h)->launches++;                                                                       \
+        cudaError_t e_ = cudaGetLastError();                                                   \
+        if (e_ != cudaSuccess)                                                                 \
+            return gpmpc::fail((h), GPMPC_ERR_CUDA,                                            \
+                               std::string("kernel launch: ") + cudaGetErrorString(e_));       \
+    } while (0)
+
+inline bool is_device_ptr(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// copy `bytes` from a host-or-device source into a device destination on the handle's stream
+inline cudaError_t to_device(gpmpc_ctx *h, void *dst, const void *src, size_t bytes) {
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, h->stream);
+}
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ---- fit.cu -------------------------------------------------------------------------------
+int fit_all(gpmpc_ctx *h, const bool *which);           // (re)fit the outputs flagged in which[E]
+int derive_weights(gpmpc_ctx *h, int a);                // Wt[a] from Kinv[a], beta[a], lam_prop[a]
+int gram_into(gpmpc_ctx *h, int a, double *dst, int ldd, bool add_noise);   // Kf / Ky of output a
+void rebuild_groups(gpmpc_ctx *h);
+int upload_prop_hypers(gpmpc_ctx *h);
+
+// ---- gemm.cu ------------------------------------------------------------------------------
+// C[M,N] = alpha * A[M,K] * B[N,K]^T + beta * C   (all row-major, fp64, DMMA m8n8k4)
+//   M, N multiples of 64; K multiple of 16.
+//   tri_lower: compute only tiles whose first column <= first row (+ col_off/row_off aligned at 0)
+//   kmode: 0 = k in [0,K); 1 = k >= tile row0 (A upper triangular); 2 = k >= max(row0, col0)
+int dgemm_nt(gpmpc_ctx *h, int M, int N, int K, double alpha, const double *A, int lda, const double *B,
+             int ldb, double beta, double *C, int ldc, bool tri_lower, int kmode);
+
+// ---- predict.cu ---------------------------------------------------------------------------
+int kernel_matrix_dev(gpmpc_ctx *h, int a, int p, const double *Xs_dev, double *out_dev, int ldo);
+
+// ---- rollout.cu / mm_pairs.cu -------------------------------------------------------------
+struct StepIO;   // defined in rollout.cu
+
+}  // namespace gpmpc

@@ -1,0 +1,363 @@
+// GP fit on the device: Gram matrix, blocked Cholesky, Ky^-1, beta = Ky^-1 y and the precomputed
+// moment-matching weight matrix.  Replaces GaussianProcessRegression.build_Ky_inv_mat
+// (reference src/gpr.py:159-171: Kf, Ky, explicit LU inverse) with
+//     Ky = L L^T  (right-looking blocked Cholesky, DMMA trailing updates)
+//     Z  = L^-1   (blocked forward substitution, DMMA panels), Ky^-1 = Z^T Z (DMMA, symmetric)
+// The explicit inverse is kept because the variance formula contracts a matrix that changes every step
+// against the full Ky^-1 (src/tools/uncertainty_prop.py:399).
+#include "common.cuh"
+
+namespace gpmpc {
+
+constexpr int NB = 64;   // Cholesky block size (== dgemm tile)
+
+// ---------------------------------------------------------------------------------------------
+// Gram matrix.  K[i][j] = sf^2 exp(-1/2 sum_k (x_ik - x_jk)^2 / lam_k) (+ noise on the diagonal).
+// Rows/cols >= n are padded with the identity so that the padded matrix stays positive definite.
+// ---------------------------------------------------------------------------------------------
+struct HyperArg { double inv_lam[kMaxD]; double sf2; double noise; };
+
+__global__ void gram_kernel(const double *__restrict__ X, int n, int np, int D, HyperArg hp,
+                            double *__restrict__ K, int ldk, int add_noise)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= np || j >= np) return;
+    double v;
+    if (i < n && j < n) {
+        double q = 0.0;
+        for (int k = 0; k < D; ++k) {
+            const double d = X[(size_t)i * D + k] - X[(size_t)j * D + k];
+            q = fma(d * d, hp.inv_lam[k], q);
+        }
+        v = hp.sf2 * exp(-0.5 * q);
+        if (add_noise && i == j) v += hp.noise;
+    } else {
+        v = (i == j) ? 1.0 : 0.0;
+    }
+    K[(size_t)i * ldk + j] = v;
+}
+
+static HyperArg make_hyper(const gpmpc_ctx *h, int a, bool prop)
+{
+    HyperArg hp;
+    for (int k = 0; k < kMaxD; ++k) hp.inv_lam[k] = 0.0;
+    for (int k = 0; k < h->D; ++k) hp.inv_lam[k] = 1.0 / (prop ? h->lam_prop[a][k] : h->lam_fit[a][k]);
+    const double sf = prop ? h->sf_prop[a] : h->sf_fit[a];
+    hp.sf2 = sf * sf;
+    hp.noise = h->noise[a];
+    return hp;
+}
+
+int gram_into(gpmpc_ctx *h, int a, double *dst, int ldd, bool add_noise)
+{
+    // exported matrices (n x n, ld = ldd) use the fit-time hyper-parameters, like self.Kf / self.Ky
+    dim3 blk(32, 8), grid((h->n + 31) / 32, (h->n + 7) / 8);
+    gram_kernel<<<grid, blk, 0, h->stream>>>(h->X.as<double>(), h->n, h->n, h->D, make_hyper(h, a, false), dst,
+                                             ldd, add_noise ? 1 : 0);
+    GP_LAUNCH_CHECK(h);
+    return GPMPC_OK;
+}
+
+// Inverse of the lower-triangular 64x64 matrix held in the lower part of S (pitch 65).  The inverse is
+// built column by column (thread j owns column j, forward substitution) and kept in the unused upper part:
+// Xinv[i][j] (i >= j) lives at S[j][i + 1].  Result is written dense (zeros above the diagonal) to Linv.
+__device__ void tri_inverse_packed(double (*S)[NB + 1], int tid, int nthreads, double *__restrict__ Linv)
+{
+    if (tid < NB) {
+        const int j = tid;
+        S[j][j + 1] = 1.0 / S[j][j];
+        for (int i = j + 1; i < NB; ++i) {
+            double s = 0.0;
+            for (int k = j; k < i; ++k) s = fma(S[i][k], S[j][k + 1], s);
+            S[j][i + 1] = -s / S[i][i];
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < NB * NB; e += nthreads) {
+        const int i = e / NB, j = e % NB;
+        Linv[e] = (i >= j) ? S[j][i + 1] : 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Diagonal block: unblocked Cholesky of a 64x64 block in shared memory + inverse of the factor.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+potrf_diag_kernel(double *__restrict__ A, int ld, int k0, double *__restrict__ Linv, int *info)
+{
+    __shared__ double S[NB][NB + 1];
+    __shared__ int bad;
+    const int tid = threadIdx.x;
+    if (tid == 0) bad = 0;
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int r = e / NB, c = e % NB;
+        S[r][c] = (c <= r) ? A[(size_t)(k0 + r) * ld + k0 + c] : 0.0;
+    }
+    __syncthreads();
+    for (int c = 0; c < NB; ++c) {
+        if (tid == 0) {
+            const double d = S[c][c];
+            if (!(d > 0.0)) { if (!bad) bad = k0 + c + 1; S[c][c] = 1.0; }
+            else S[c][c] = sqrt(d);
+        }
+        __syncthreads();
+        const double dinv = 1.0 / S[c][c];
+        if (tid > c && tid < NB) S[tid][c] *= dinv;
+        __syncthreads();
+        // trailing update of the lower triangle: S[r][j] -= S[r][c] S[j][c], c < j <= r
+        for (int e = tid; e < NB * NB; e += 256) {
+            const int r = e / NB, j = e % NB;
+            if (j > c && j <= r) S[r][j] = fma(-S[r][c], S[j][c], S[r][j]);
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int r = e / NB, c = e % NB;
+        A[(size_t)(k0 + r) * ld + k0 + c] = (c <= r) ? S[r][c] : 0.0;      // upper part of the block is zero
+    }
+    if (tid == 0 && bad) atomicCAS(info, 0, bad);
+    __syncthreads();
+    tri_inverse_packed(S, tid, blockDim.x, Linv);
+}
+
+// dst[c][r] = src[r][c] for a 64x64 block
+__global__ void transpose_block_kernel(const double *__restrict__ src, int lds, double *__restrict__ dst, int ldd)
+{
+    __shared__ double T[NB][NB + 1];
+    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) T[e / NB][e % NB] = src[(size_t)(e / NB) * lds + e % NB];
+    __syncthreads();
+    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) dst[(size_t)(e / NB) * ldd + e % NB] = T[e % NB][e / NB];
+}
+
+// copy the lower triangle (tiles computed by the tri_lower GEMM) into the upper triangle
+__global__ void mirror_lower_kernel(double *__restrict__ A, int np, int ld)
+{
+    __shared__ double T[32][33];
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (bj > bi) return;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int r = ty; r < 32; r += blockDim.y) T[r][tx] = A[(size_t)(bi * 32 + r) * ld + bj * 32 + tx];
+    __syncthreads();
+    for (int r = ty; r < 32; r += blockDim.y) {
+        const int i = bj * 32 + r, j = bi * 32 + tx;       // transposed position
+        if (j > i) A[(size_t)i * ld + j] = T[tx][r];
+    }
+}
+
+__global__ void zero_kernel(double *p, size_t count)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = 0.0;
+}
+
+// y = A[0:n,0:n] x   (row per warp, coalesced, warp-shuffle reduction)
+__global__ void gemv_kernel(const double *__restrict__ A, int ld, int n, const double *__restrict__ x,
+                            double *__restrict__ y, int np)
+{
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= np) return;
+    double s = 0.0;
+    if (row < n)
+        for (int j = lane; j < n; j += 32) s = fma(A[(size_t)row * ld + j], x[j], s);
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) y[row] = (row < n) ? s : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Moment-matching weights.  For the variance (src/tools/uncertainty_prop.py:392-399)
+//     T = sum_ij (Ky^-1 - beta beta^T)_ij * exp(-1/4 (x_i-x_j)^T Lam^-1 (x_i-x_j)) * [u,S-dependent part]_ij
+// the first two factors depend only on the fit and on lambda; they are folded once into
+//     Wt_ij = w(i,j) (Ky^-1 - beta beta^T)_ij exp(-1/4 ...),   w = 2 for j > i, 1 for j == i, 0 for j < i
+// so that the per-step kernels sweep only the upper triangle (the [u,S] part is symmetric in i,j).
+// ---------------------------------------------------------------------------------------------
+__global__ void derive_weights_kernel(const double *__restrict__ X, int n, int np, int D, HyperArg hp,
+                                      const double *__restrict__ Kinv, const double *__restrict__ beta,
+                                      double *__restrict__ Wt, int ld)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= np || j >= np) return;
+    double v = 0.0;
+    if (i < n && j < n && j >= i) {
+        double q = 0.0;
+        for (int k = 0; k < D; ++k) {
+            const double d = X[(size_t)i * D + k] - X[(size_t)j * D + k];
+            q = fma(d * d, hp.inv_lam[k], q);
+        }
+        const double w = Kinv[(size_t)i * ld + j] - beta[i] * beta[j];
+        v = (j > i ? 2.0 : 1.0) * w * exp(-0.25 * q);
+    }
+    Wt[(size_t)i * ld + j] = v;
+}
+
+int derive_weights(gpmpc_ctx *h, int a)
+{
+    const size_t mat = (size_t)h->ld * h->ld;
+    dim3 blk(32, 8), grid((h->ld + 31) / 32, (h->ld + 7) / 8);
+    derive_weights_kernel<<<grid, blk, 0, h->stream>>>(h->X.as<double>(), h->n, h->ld, h->D, make_hyper(h, a, true),
+                                                       h->Kinv.as<double>() + a * mat,
+                                                       h->beta.as<double>() + (size_t)a * h->ld,
+                                                       h->Wt.as<double>() + a * mat, h->ld);
+    GP_LAUNCH_CHECK(h);
+    return GPMPC_OK;
+}
+
+void rebuild_groups(gpmpc_ctx *h)
+{
+    h->groups.clear();
+    std::vector<bool> used(h->E, false);
+    for (int a = 0; a < h->E; ++a) {
+        if (used[a]) continue;
+        LambdaGroup g;
+        for (int b = a; b < h->E && g.count < kGroupMax; ++b) {
+            if (used[b]) continue;
+            if (std::memcmp(h->lam_prop[a], h->lam_prop[b], sizeof(double) * h->D) == 0) {
+                g.outputs[g.count++] = b;
+                used[b] = true;
+            }
+        }
+        h->groups.push_back(g);
+    }
+}
+
+int upload_prop_hypers(gpmpc_ctx *h)
+{
+    // layout: lam[E,D] | sf[E] | group lambdas [G,D]
+    const int E = h->E, D = h->D;
+    rebuild_groups(h);
+    std::vector<double> host((size_t)E * D + E + h->groups.size() * D);
+    for (int a = 0; a < E; ++a) {
+        for (int k = 0; k < D; ++k) host[(size_t)a * D + k] = h->lam_prop[a][k];
+        host[(size_t)E * D + a] = h->sf_prop[a];
+    }
+    for (size_t g = 0; g < h->groups.size(); ++g)
+        for (int k = 0; k < D; ++k)
+            host[(size_t)E * D + E + g * D + k] = h->lam_prop[h->groups[g].outputs[0]][k];
+    GP_CUDA(h, h->hyp.reserve(host.size() * sizeof(double)));
+    // pageable source: the copy is staged before the call returns, so the vector may die afterwards
+    GP_CUDA(h, cudaMemcpyAsync(h->hyp.p, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    GP_CUDA(h, cudaStreamSynchronize(h->stream));
+    return GPMPC_OK;
+}
+
+// Ky (padded, in `L`) -> L in place; returns GPMPC_ERR_NOT_PD through info
+static int cholesky_inplace(gpmpc_ctx *h, double *L, int np)
+{
+    const int ld = h->ld;
+    double *linv = h->linv.as<double>();
+    double *panel = h->tt.as<double>();
+    const int nblk = np / NB;
+    for (int k = 0; k < nblk; ++k) {
+        potrf_diag_kernel<<<1, 256, 0, h->stream>>>(L, ld, k * NB, linv, h->info.as<int>());
+        GP_LAUNCH_CHECK(h);
+        const int rem = np - (k + 1) * NB;
+        if (rem <= 0) break;
+        double *Apan = L + (size_t)(k + 1) * NB * ld + (size_t)k * NB;
+        // panel = A[i,k] * Lkk^-T      (then copied back over A[i,k])
+        int rc = dgemm_nt(h, rem, NB, NB, 1.0, Apan, ld, linv, NB, 0.0, panel, NB, false, 0);
+        if (rc) return rc;
+        GP_CUDA(h, cudaMemcpy2DAsync(Apan, (size_t)ld * sizeof(double), panel, NB * sizeof(double),
+                                     NB * sizeof(double), rem, cudaMemcpyDeviceToDevice, h->stream));
+        // trailing update: A[i,j] -= L[i,k] L[j,k]^T, lower tiles only
+        double *Atr = L + (size_t)(k + 1) * NB * ld + (size_t)(k + 1) * NB;
+        rc = dgemm_nt(h, rem, rem, NB, -1.0, Apan, ld, Apan, ld, 1.0, Atr, ld, true, 0);
+        if (rc) return rc;
+    }
+    return GPMPC_OK;
+}
+
+// inverse of one 64x64 lower-triangular diagonal block of L
+__global__ void trtri_diag_kernel(const double *__restrict__ L, int ld, int k0, double *__restrict__ Linv)
+{
+    __shared__ double S[NB][NB + 1];
+    const int tid = threadIdx.x;   // 64 threads
+    for (int e = tid; e < NB * (NB + 1); e += 64) {
+        const int r = e / (NB + 1), c = e % (NB + 1);
+        S[r][c] = (c <= r) ? L[(size_t)(k0 + r) * ld + k0 + c] : 0.0;
+    }
+    __syncthreads();
+    tri_inverse_packed(S, tid, 64, Linv);
+}
+
+// ZT = L^-T (upper triangular, row-major) by blocked forward substitution
+static int invert_factor(gpmpc_ctx *h, const double *L, double *ZT, int np)
+{
+    const int ld = h->ld;
+    double *linv = h->linv.as<double>();
+    double *TT = h->tt.as<double>();
+    const int nblk = np / NB;
+    zero_kernel<<<296, 256, 0, h->stream>>>(ZT, (size_t)np * ld);
+    GP_LAUNCH_CHECK(h);
+    for (int r = 0; r < nblk; ++r) {
+        // inverse of the diagonal block of L
+        trtri_diag_kernel<<<1, 64, 0, h->stream>>>(L, ld, r * NB, linv);
+        GP_LAUNCH_CHECK(h);
+        // ZT[r,r] = (Lrr^-1)^T
+        transpose_block_kernel<<<1, 256, 0, h->stream>>>(linv, NB, ZT + (size_t)r * NB * ld + (size_t)r * NB, ld);
+        GP_LAUNCH_CHECK(h);
+        if (r == 0) continue;
+        const int Mr = r * NB;
+        // TT[c, p] = sum_k ZT[c, k] L[r*NB + p, k],  k < r*NB   (ZT upper triangular: k >= c)
+        int rc = dgemm_nt(h, Mr, NB, Mr, 1.0, ZT, ld, L + (size_t)r * NB * ld, ld, 0.0, TT, NB, false, 1);
+        if (rc) return rc;
+        // ZT[c, r*NB + p] = - sum_s TT[c, s] Lrr^-1[p, s]
+        rc = dgemm_nt(h, Mr, NB, NB, -1.0, TT, NB, linv, NB, 0.0, ZT + (size_t)r * NB, ld, false, 0);
+        if (rc) return rc;
+    }
+    return GPMPC_OK;
+}
+
+int fit_all(gpmpc_ctx *h, const bool *which)
+{
+    const int ld = h->ld, np = h->ld, n = h->n, E = h->E;
+    const size_t mat = (size_t)ld * ld;
+    GP_CUDA(h, h->Kinv.reserve(mat * E * sizeof(double)));
+    GP_CUDA(h, h->Wt.reserve(mat * E * sizeof(double)));
+    GP_CUDA(h, h->beta.reserve((size_t)ld * E * sizeof(double)));
+    GP_CUDA(h, h->chol.reserve(mat * sizeof(double)));
+    GP_CUDA(h, h->zt.reserve(mat * sizeof(double)));
+    GP_CUDA(h, h->tt.reserve((size_t)ld * NB * sizeof(double)));
+    GP_CUDA(h, h->linv.reserve((size_t)NB * NB * sizeof(double)));
+    GP_CUDA(h, h->info.reserve(sizeof(int)));
+
+    for (int a = 0; a < E; ++a) {
+        if (!which[a]) continue;
+        GP_CUDA(h, cudaMemsetAsync(h->info.p, 0, sizeof(int), h->stream));
+        double *L = h->chol.as<double>();
+        dim3 blk(32, 8), grid((np + 31) / 32, (np + 7) / 8);
+        gram_kernel<<<grid, blk, 0, h->stream>>>(h->X.as<double>(), n, np, h->D, make_hyper(h, a, false), L, ld, 1);
+        GP_LAUNCH_CHECK(h);
+        int rc = cholesky_inplace(h, L, np);
+        if (rc) return rc;
+        int info = 0;
+        GP_CUDA(h, cudaMemcpyAsync(&info, h->info.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        GP_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (info != 0) {
+            char msg[160];
+            snprintf(msg, sizeof msg, "gpmpc_fit: Ky of output %d is not positive definite (pivot %d)", a, info - 1);
+            return fail(h, GPMPC_ERR_NOT_PD, msg);
+        }
+        double *ZT = h->zt.as<double>();
+        rc = invert_factor(h, L, ZT, np);
+        if (rc) return rc;
+        double *Kinv = h->Kinv.as<double>() + a * mat;
+        // Ky^-1[i][j] = sum_{k >= max(i,j)} ZT[i][k] ZT[j][k]; lower tiles, then mirrored
+        rc = dgemm_nt(h, np, np, np, 1.0, ZT, ld, ZT, ld, 0.0, Kinv, ld, true, 2);
+        if (rc) return rc;
+        dim3 mblk(32, 8), mgrid(np / 32, np / 32);
+        mirror_lower_kernel<<<mgrid, mblk, 0, h->stream>>>(Kinv, np, ld);
+        GP_LAUNCH_CHECK(h);
+        // beta = Ky^-1 y   (src/tools/uncertainty_prop.py:327)
+        gemv_kernel<<<(np + 7) / 8, 256, 0, h->stream>>>(Kinv, ld, n, h->Y.as<double>() + (size_t)a * ld,
+                                                         h->beta.as<double>() + (size_t)a * ld, np);
+        GP_LAUNCH_CHECK(h);
+        rc = derive_weights(h, a);
+        if (rc) return rc;
+    }
+    h->fitted = true;
+    return GPMPC_OK;
+}
+
+}  // namespace gpmpc

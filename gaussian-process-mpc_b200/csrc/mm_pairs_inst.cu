@@ -1,0 +1,50 @@
+// Explicit instantiations of the batched pair-sum kernel for one input dimension D (compiled once per
+// D = 2..8 with -DGPMPC_INST_D=<D> so that the seven translation units build in parallel).
+#include "mm_pairs.cuh"
+
+#ifndef GPMPC_INST_D
+#error "compile with -DGPMPC_INST_D=<2..8>"
+#endif
+
+namespace gpmpc {
+
+template <int D, int EG, bool GRAD>
+static cudaError_t launch_one(const PairArgs &a, dim3 grid, cudaStream_t st)
+{
+    const size_t smem = 2 * pair_stage_doubles<D, EG>() * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(mm_pairs_batch<D, EG, GRAD>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    mm_pairs_batch<D, EG, GRAD><<<grid, PAIR_THREADS, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int D>
+static cudaError_t launch_d(int EG, bool grad, const PairArgs &a, dim3 grid, cudaStream_t st)
+{
+    switch (EG * 2 + (grad ? 1 : 0)) {
+        case 2: return launch_one<D, 1, false>(a, grid, st);
+        case 3: return launch_one<D, 1, true>(a, grid, st);
+        case 4: return launch_one<D, 2, false>(a, grid, st);
+        case 5: return launch_one<D, 2, true>(a, grid, st);
+        case 6: return launch_one<D, 3, false>(a, grid, st);
+        case 7: return launch_one<D, 3, true>(a, grid, st);
+        case 8: return launch_one<D, 4, false>(a, grid, st);
+        case 9: return launch_one<D, 4, true>(a, grid, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+#define GPMPC_CAT2(a, b) a##b
+#define GPMPC_CAT(a, b) GPMPC_CAT2(a, b)
+cudaError_t GPMPC_CAT(launch_pairs_batch_D, GPMPC_INST_D)(int EG, bool grad, const PairArgs &a, dim3 grid,
+                                                          cudaStream_t st)
+{
+    return launch_d<GPMPC_INST_D>(EG, grad, a, grid, st);
+}
+
+}  // namespace gpmpc

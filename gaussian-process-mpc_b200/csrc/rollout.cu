@@ -1,0 +1,847 @@
+// Horizon rollout, risk-sensitive cost and the exact adjoint (reverse sweep) for B independent control
+// sequences advanced in lock step.  Replaces Dynamics.forward_propagate_torch (src/dynamics.py:126-191),
+// RiskSensitiveMPC.cost_torch (src/mpc.py:156-200) and the autograd replay behind
+// RiskSensitiveMPC.gradient (src/mpc.py:231-255).
+//
+// Per horizon step t (1..H), on the handle's stream:
+//   prep_step      (b, group)   input mean u=[mu_{t-1}, a_{t-1}], variances s=[var_{t-1}, fp32(1e-3)],
+//                               scaled constants for the pair / mean kernels
+//   mean_sums      (b, a, j)    M0 = sum_j beta_j l_j and its first/second moments    (uncertainty_prop.py:324-338)
+//   mm_pairs_batch (b, a, i<=j) T and its first/second moments (mm_pairs.cuh)          (uncertainty_prop.py:372-399)
+//   finalize_step  (b, a)       fixed-order reduction of the partials, mean_t, var_t and the closed-form
+//                               partial derivatives d(mean,var)/d(u,s) written to the tape
+// then one thread per rollout evaluates the cost and runs the reverse sweep over the tape.
+//
+// Internal layouts put the rollout index last (coalesced across the lanes that own rollouts).
+#include "common.cuh"
+#include "mm_pairs.cuh"
+
+namespace gpmpc {
+
+#define DECL_LAUNCH(D) cudaError_t launch_pairs_batch_D##D(int, bool, const PairArgs &, dim3, cudaStream_t);
+DECL_LAUNCH(2) DECL_LAUNCH(3) DECL_LAUNCH(4) DECL_LAUNCH(5) DECL_LAUNCH(6) DECL_LAUNCH(7) DECL_LAUNCH(8)
+#undef DECL_LAUNCH
+
+typedef cudaError_t (*pair_launch_fn)(int, bool, const PairArgs &, dim3, cudaStream_t);
+static pair_launch_fn pair_launcher(int D)
+{
+    switch (D) {
+        case 2: return launch_pairs_batch_D2; case 3: return launch_pairs_batch_D3;
+        case 4: return launch_pairs_batch_D4; case 5: return launch_pairs_batch_D5;
+        case 6: return launch_pairs_batch_D6; case 7: return launch_pairs_batch_D7;
+        case 8: return launch_pairs_batch_D8;
+    }
+    return nullptr;
+}
+
+constexpr int MEAN_JP = 16;          // partitions of the training set in the mean kernel
+constexpr int MEAN_THREADS = 128;
+
+struct StepDims { int B, Bpad, D, E, m, G, n, ld; };
+
+// ---------------------------------------------------------------------------------------------
+// prep_step: one thread per (rollout, lambda-group)
+//   us[(k)*Bpad + b]       u_k            k < D
+//   us[(D+k)*Bpad + b]     s_k
+//   cst[g][4D][Bpad]:      c_k = sqrt(a_k/8), c_k u_k, cm_k = sqrt(b_k/2), cm_k u_k
+//     a_k = 1/(lam_k/2 + s_k)  (uncertainty_prop.py:376),  b_k = 1/(s_k + lam_k)  (:331)
+// mu/var hold step t-1 as [(t-1)*E + a][Bpad]; actions come from Uint [(t-1)*m + k][Bpad].
+// ---------------------------------------------------------------------------------------------
+__global__ void prep_step_kernel(StepDims d, int t, const double *__restrict__ mu, const double *__restrict__ var,
+                                 const double *__restrict__ Uint, const double *__restrict__ lam_group,
+                                 double *__restrict__ us, double *__restrict__ cst, double act_var)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = blockIdx.y;
+    if (b >= d.B) return;
+    for (int k = 0; k < d.D; ++k) {
+        double u, s;
+        if (k < d.E) {
+            u = mu[((size_t)(t - 1) * d.E + k) * d.Bpad + b];
+            s = var[((size_t)(t - 1) * d.E + k) * d.Bpad + b];
+        } else {
+            u = Uint[((size_t)(t - 1) * d.m + (k - d.E)) * d.Bpad + b];
+            s = act_var;
+        }
+        if (g == 0) {
+            us[(size_t)k * d.Bpad + b] = u;
+            us[(size_t)(d.D + k) * d.Bpad + b] = s;
+        }
+        const double lam = lam_group[g * d.D + k];
+        const double a = 1.0 / (0.5 * lam + s);
+        const double bb = 1.0 / (s + lam);
+        const double c = sqrt(0.125 * a);
+        const double cm = sqrt(0.5 * bb);
+        double *cg = cst + (size_t)g * 4 * d.D * d.Bpad;
+        cg[(size_t)k * d.Bpad + b] = c;
+        cg[(size_t)(d.D + k) * d.Bpad + b] = c * u;
+        cg[(size_t)(2 * d.D + k) * d.Bpad + b] = cm;
+        cg[(size_t)(3 * d.D + k) * d.Bpad + b] = cm * u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// mean_sums: lanes <-> rollouts, grid (rollout chunks, MEAN_JP partitions of j, groups).
+//   p_k = cm_k (u_k - x_jk),  l_j = exp(-sum p_k^2),  M0 += beta_j l_j, M1_k += beta_j l_j p_k, M2_k += .. p_k^2
+// ---------------------------------------------------------------------------------------------
+struct MeanArgs {
+    const double *X; const double *beta[kGroupMax]; int out_idx[kGroupMax]; int EG;
+    const double *cst; double *mpart; StepDims d;
+};
+
+template <int D>
+__global__ void __launch_bounds__(MEAN_THREADS) mean_sums_kernel(const MeanArgs a)
+{
+    __shared__ double xs[64 * D];
+    __shared__ double bs[kGroupMax][64];
+    const int tid = threadIdx.x;
+    const int b = blockIdx.x * MEAN_THREADS + tid;
+    const bool active = b < a.d.B;
+    const int jp = blockIdx.y;
+    const int per = (a.d.ld / 64 + MEAN_JP - 1) / MEAN_JP * 64;    // rows per partition (multiple of 64)
+    const int j_begin = jp * per;
+    const int j_end = min(a.d.ld, j_begin + per);
+
+    double cm[D], cmu[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        cm[k] = active ? a.cst[(size_t)(2 * D + k) * a.d.Bpad + b] : 0.0;
+        cmu[k] = active ? a.cst[(size_t)(3 * D + k) * a.d.Bpad + b] : 0.0;
+    }
+    double m0[kGroupMax], m1[kGroupMax][D], m2[kGroupMax][D];
+#pragma unroll
+    for (int g = 0; g < kGroupMax; ++g) {
+        m0[g] = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) m1[g][k] = m2[g][k] = 0.0;
+    }
+    for (int j0 = j_begin; j0 < j_end; j0 += 64) {
+        __syncthreads();
+        for (int e = tid; e < 64 * D; e += MEAN_THREADS) xs[e] = a.X[(size_t)j0 * D + e];
+        for (int e = tid; e < 64 * a.EG; e += MEAN_THREADS) bs[e / 64][e % 64] = a.beta[e / 64][j0 + e % 64];
+        __syncthreads();
+        for (int j = 0; j < 64; ++j) {
+            double p[D], pp[D], S = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) { p[k] = fma(-cm[k], xs[j * D + k], cmu[k]); pp[k] = p[k] * p[k]; S += pp[k]; }
+            const double l = exp_neg(S);
+#pragma unroll
+            for (int g = 0; g < kGroupMax; ++g) {
+                if (g < a.EG) {
+                    const double w = bs[g][j] * l;
+                    m0[g] += w;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) { m1[g][k] = fma(w, p[k], m1[g][k]); m2[g][k] = fma(w, pp[k], m2[g][k]); }
+                }
+            }
+        }
+    }
+    if (active) {
+        constexpr int NA = 1 + 2 * D;
+#pragma unroll
+        for (int g = 0; g < kGroupMax; ++g) {
+            if (g < a.EG) {
+                double *dst = a.mpart + (((size_t)jp * a.d.E + a.out_idx[g]) * NA) * a.d.Bpad + b;
+                dst[0] = m0[g];
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    dst[(size_t)(1 + k) * a.d.Bpad] = m1[g][k];
+                    dst[(size_t)(1 + D + k) * a.d.Bpad] = m2[g][k];
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalize_step: one thread per (rollout, output).  Sums the partials in a fixed order (deterministic),
+// applies the determinant prefactors and writes mean/var of step t plus the tape entry.
+//   tape[((t-1)*E + a) * (2+4D) + e][Bpad]:  e = 0 mean, 1 var, 2.. dm/du, dm/ds, dv/du, dv/ds
+// ---------------------------------------------------------------------------------------------
+__global__ void finalize_step_kernel(StepDims d, int t, int P, const double *__restrict__ part,
+                                     const double *__restrict__ mpart, const double *__restrict__ us,
+                                     const double *__restrict__ hyp, double *__restrict__ mu,
+                                     double *__restrict__ var, double *__restrict__ tape, int want_grad)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int a = blockIdx.y;
+    if (b >= d.B) return;
+    const int D = d.D, NA = 1 + 2 * D;
+    double accN[1 + 2 * kMaxD], accM[1 + 2 * kMaxD];
+    for (int e = 0; e < NA; ++e) {
+        double s = 0.0;
+        for (int p = 0; p < P; ++p) s += part[(((size_t)p * d.E + a) * NA + e) * d.Bpad + b];
+        accN[e] = s;
+        double sm = 0.0;
+        for (int p = 0; p < MEAN_JP; ++p) sm += mpart[(((size_t)p * d.E + a) * NA + e) * d.Bpad + b];
+        accM[e] = sm;
+    }
+    const double *lam = hyp + (size_t)a * D;
+    const double sf = hyp[(size_t)d.E * D + a];
+    double detm = 1.0, detv = 1.0;
+    double u[kMaxD], s[kMaxD];
+    for (int k = 0; k < D; ++k) {
+        u[k] = us[(size_t)k * d.Bpad + b];
+        s[k] = us[(size_t)(D + k) * d.Bpad + b];
+        detm *= 1.0 + s[k] / lam[k];            // |Lam^-1 S + I|      uncertainty_prop.py:335
+        detv *= 1.0 + 2.0 * s[k] / lam[k];      // |2 Lam^-1 S + I|    uncertainty_prop.py:377
+    }
+    const double sf2 = sf * sf;
+    const double cmf = sf2 / sqrt(detm);
+    const double cvf = sf2 * sf2 / sqrt(detv);
+    const double M0 = cmf * accM[0];
+    const double N0 = cvf * accN[0];
+    const double mean = M0;
+    const double v = sf2 - N0 - mean * mean;     // latent variance, uncertainty_prop.py:399
+    mu[((size_t)t * d.E + a) * d.Bpad + b] = mean;
+    var[((size_t)t * d.E + a) * d.Bpad + b] = v;
+    if (!want_grad) return;
+    const int NT = 2 + 4 * D;
+    double *tp = tape + (((size_t)(t - 1) * d.E + a) * NT) * d.Bpad + b;
+    tp[0] = mean;
+    tp[(size_t)d.Bpad] = v;
+    for (int k = 0; k < D; ++k) {
+        const double ak = 1.0 / (0.5 * lam[k] + s[k]);
+        const double bk = 1.0 / (s[k] + lam[k]);
+        const double c = sqrt(0.125 * ak), cm = sqrt(0.5 * bk);
+        const double M1 = cmf * accM[1 + k] / cm;               // sum beta l v_k
+        const double M2 = cmf * accM[1 + D + k] / (cm * cm);    // sum beta l v_k^2
+        const double N1 = cvf * accN[1 + k] / c;                // sum w (v_ik + v_jk)
+        const double N2 = cvf * accN[1 + D + k] / (c * c);      // sum w (v_ik + v_jk)^2
+        const double dmu = -bk * M1;
+        const double dms = 0.5 * bk * bk * M2 - 0.5 * bk * M0;
+        const double dTu = -0.5 * ak * N1;
+        const double dTs = 0.125 * ak * ak * N2 - N0 / (lam[k] + 2.0 * s[k]);
+        tp[(size_t)(2 + k) * d.Bpad] = dmu;
+        tp[(size_t)(2 + D + k) * d.Bpad] = dms;
+        tp[(size_t)(2 + 2 * D + k) * d.Bpad] = -dTu - 2.0 * mean * dmu;
+        tp[(size_t)(2 + 3 * D + k) * d.Bpad] = -dTs - 2.0 * mean * dms;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Layout shuffles between the C-ABI layout ([B, ...] rollout-major) and the internal one ([...][Bpad]).
+// ---------------------------------------------------------------------------------------------
+__global__ void to_internal_kernel(const double *__restrict__ src, int B, int Bpad, int inner, double *__restrict__ dst)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int e = blockIdx.y;
+    if (b < B) dst[(size_t)e * Bpad + b] = src[(size_t)b * inner + e];
+}
+__global__ void to_external_kernel(const double *__restrict__ src, int B, int Bpad, int inner, double *__restrict__ dst)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int e = blockIdx.y;
+    if (b < B) dst[(size_t)b * inner + e] = src[(size_t)e * Bpad + b];
+}
+__global__ void init_state_kernel(const double *__restrict__ x0int, int B, int Bpad, int E, double *__restrict__ mu,
+                                  double *__restrict__ var, double var0)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int a = blockIdx.y;
+    if (b < B) { mu[(size_t)a * Bpad + b] = x0int[(size_t)a * Bpad + b]; var[(size_t)a * Bpad + b] = var0; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small dense LU (partial pivoting) in local memory: determinant and inverse of an E x E matrix.
+// Same algorithm as the LAPACK getrf/getri behind torch.linalg.det / inv (src/mpc.py:179-185).
+// ---------------------------------------------------------------------------------------------
+__device__ double lu_det_inv(int E, const double *Ain, double *inv)
+{
+    double A[kMaxE * kMaxE];
+    int piv[kMaxE];
+    double det = 1.0;
+    for (int i = 0; i < E * E; ++i) A[i] = Ain[i];
+    for (int c = 0; c < E; ++c) {
+        int p = c;
+        for (int r = c + 1; r < E; ++r) if (fabs(A[r * E + c]) > fabs(A[p * E + c])) p = r;
+        piv[c] = p;
+        if (p != c) {
+            for (int k = 0; k < E; ++k) { const double tmp = A[c * E + k]; A[c * E + k] = A[p * E + k]; A[p * E + k] = tmp; }
+            det = -det;
+        }
+        det *= A[c * E + c];
+        const double dinv = 1.0 / A[c * E + c];
+        for (int r = c + 1; r < E; ++r) {
+            const double f = A[r * E + c] * dinv;
+            A[r * E + c] = f;
+            for (int k = c + 1; k < E; ++k) A[r * E + k] -= f * A[c * E + k];
+        }
+    }
+    if (inv) {
+        for (int col = 0; col < E; ++col) {
+            double x[kMaxE];
+            for (int r = 0; r < E; ++r) x[r] = (r == col) ? 1.0 : 0.0;
+            for (int c = 0; c < E; ++c) { const int p = piv[c]; if (p != c) { const double tmp = x[c]; x[c] = x[p]; x[p] = tmp; } }
+            for (int r = 0; r < E; ++r) for (int k = 0; k < r; ++k) x[r] -= A[r * E + k] * x[k];
+            for (int r = E - 1; r >= 0; --r) {
+                for (int k = r + 1; k < E; ++k) x[r] -= A[r * E + k] * x[k];
+                x[r] /= A[r * E + r];
+            }
+            for (int r = 0; r < E; ++r) inv[r * E + col] = x[r];
+        }
+    }
+    return det;
+}
+
+// ---------------------------------------------------------------------------------------------
+// cost_adjoint: one thread per rollout.
+//  mode 0 (cost): cost of src/mpc.py:179-198 and, if grad != NULL, its exact gradient w.r.t. U by a reverse
+//                 sweep over the tape; seeds are the cost partials.
+//  mode 1 (vjp) : seeds are caller-supplied d loss/d mean_t, d loss/d var_t (internal layout), output is
+//                 d loss / d U (and d loss / d x0).
+// ---------------------------------------------------------------------------------------------
+struct CostArgs {
+    StepDims d; int H; int mode; int has_rd; int want_grad;
+    const double *mu, *var, *tape, *Uint;       // internal layouts
+    const double *gamma;                         // [B]
+    const double *last_u;                        // [m][Bpad] internal (iff has_rd)
+    const double *seed_mu, *seed_var;            // mode 1: [(t*E+a)][Bpad], may be NULL
+    double Q[kMaxE * kMaxE], Qi[kMaxE * kMaxE], R[kMaxD * kMaxD], Rd[kMaxD * kMaxD], xref[kMaxE], uref[kMaxD];
+    double *cost;                                // [B] (device, final layout)
+    double *gradint;                             // [(t*m + k)][Bpad]
+    double *gx0int;                              // [a][Bpad] or NULL
+};
+
+__global__ void __launch_bounds__(128) cost_adjoint_kernel(const CostArgs a)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.d.B) return;
+    const int E = a.d.E, D = a.d.D, m = a.d.m, H = a.H, Bp = a.d.Bpad;
+    const int NT = 2 + 4 * D;
+    const double gamma = (a.mode == 0) ? a.gamma[b] : 0.0;
+    double cost = 0.0;
+    double mb[kMaxE], vb[kMaxE];               // adjoints of mean_t / var_t carried backwards
+    for (int k = 0; k < E; ++k) mb[k] = vb[k] = 0.0;
+
+    for (int t = H; t >= 0; --t) {
+        // ---- seeds at time t ----
+        if (a.mode == 0) {
+            double M[kMaxE * kMaxE], Minv[kMaxE * kMaxE], Gm[kMaxE * kMaxE], G[kMaxE * kMaxE], e[kMaxE], sg[kMaxE];
+            for (int k = 0; k < E; ++k) {
+                sg[k] = a.var[((size_t)t * E + k) * Bp + b];
+                e[k] = a.mu[((size_t)t * E + k) * Bp + b] - a.xref[k];
+            }
+            for (int r = 0; r < E; ++r)
+                for (int k = 0; k < E; ++k) {
+                    M[r * E + k] = (r == k ? 1.0 : 0.0) + gamma * a.Q[r * E + k] * sg[k];     // I + gamma Q Sigma
+                    Gm[r * E + k] = a.Qi[r * E + k] + (r == k ? gamma * sg[k] : 0.0);         // Q^-1 + gamma Sigma
+                }
+            const double det = lu_det_inv(E, M, a.want_grad ? Minv : nullptr);
+            lu_det_inv(E, Gm, G);
+            cost += (1.0 / gamma) * log(det);          // log of the determinant (NaN if det < 0), mpc.py:183
+            double Ge[kMaxE], Gte[kMaxE];
+            for (int r = 0; r < E; ++r) {
+                double s1 = 0.0, s2 = 0.0;
+                for (int k = 0; k < E; ++k) { s1 += G[r * E + k] * e[k]; s2 += G[k * E + r] * e[k]; }
+                Ge[r] = s1; Gte[r] = s2;
+            }
+            for (int k = 0; k < E; ++k) cost += e[k] * Ge[k];
+            if (a.want_grad) {
+                for (int k = 0; k < E; ++k) {
+                    double mq = 0.0;
+                    for (int r = 0; r < E; ++r) mq += Minv[k * E + r] * a.Q[r * E + k];
+                    mb[k] += Ge[k] + Gte[k];
+                    vb[k] += mq - gamma * Gte[k] * Ge[k];
+                }
+            }
+        } else {
+            for (int k = 0; k < E; ++k) {
+                if (a.seed_mu) mb[k] += a.seed_mu[((size_t)t * E + k) * Bp + b];
+                if (a.seed_var) vb[k] += a.seed_var[((size_t)t * E + k) * Bp + b];
+            }
+        }
+        if (t == 0) break;
+        // ---- direct action cost of u_{t-1} ----
+        double gact[kMaxD];
+        for (int k = 0; k < m; ++k) gact[k] = 0.0;
+        if (a.mode == 0) {
+            double du[kMaxD];
+            for (int k = 0; k < m; ++k) du[k] = a.Uint[((size_t)(t - 1) * m + k) * Bp + b] - a.uref[k];
+            for (int r = 0; r < m; ++r)
+                for (int k = 0; k < m; ++k) {
+                    cost += du[r] * a.R[r * m + k] * du[k];
+                    gact[r] += (a.R[r * m + k] + a.R[k * m + r]) * du[k];
+                }
+            if (a.has_rd) {
+                // delta_j = u_j - u_{j-1} (u_{-1} = last_u);  u_{t-1} appears in delta_{t-1} and delta_t
+                double d0[kMaxD], d1[kMaxD];
+                for (int k = 0; k < m; ++k) {
+                    const double cur = a.Uint[((size_t)(t - 1) * m + k) * Bp + b];
+                    const double prev = (t - 1 == 0) ? a.last_u[(size_t)k * Bp + b] : a.Uint[((size_t)(t - 2) * m + k) * Bp + b];
+                    d0[k] = cur - prev;
+                    d1[k] = (t < H) ? a.Uint[((size_t)t * m + k) * Bp + b] - cur : 0.0;
+                }
+                for (int r = 0; r < m; ++r)
+                    for (int k = 0; k < m; ++k) {
+                        cost += d0[r] * a.Rd[r * m + k] * d0[k];
+                        gact[r] += (a.Rd[r * m + k] + a.Rd[k * m + r]) * (d0[k] - d1[k]);
+                    }
+            }
+        }
+        if (!a.want_grad) continue;
+        // ---- pull the adjoints of (mean_t, var_t) back through step t ----
+        double ub[kMaxD], sb[kMaxD];
+        for (int k = 0; k < D; ++k) ub[k] = sb[k] = 0.0;
+        for (int o = 0; o < E; ++o) {
+            const double *tp = a.tape + (((size_t)(t - 1) * E + o) * NT) * Bp + b;
+            const double mo = mb[o], vo = vb[o];
+            for (int k = 0; k < D; ++k) {
+                ub[k] += mo * tp[(size_t)(2 + k) * Bp] + vo * tp[(size_t)(2 + 2 * D + k) * Bp];
+                sb[k] += mo * tp[(size_t)(2 + D + k) * Bp] + vo * tp[(size_t)(2 + 3 * D + k) * Bp];
+            }
+        }
+        for (int k = 0; k < E; ++k) { mb[k] = ub[k]; vb[k] = sb[k]; }
+        for (int k = 0; k < m; ++k) a.gradint[((size_t)(t - 1) * m + k) * Bp + b] = ub[E + k] + gact[k];
+    }
+    if (a.mode == 0) a.cost[b] = cost;
+    if (a.gx0int) for (int k = 0; k < E; ++k) a.gx0int[(size_t)k * Bp + b] = mb[k];
+}
+
+// =============================================================================================
+// Host orchestration
+// =============================================================================================
+static int check_ready(gpmpc_ctx *h, int B, int H)
+{
+    if (!h) return GPMPC_ERR_INVALID;
+    if (!h->fitted || h->n <= 0) return fail(h, GPMPC_ERR_NOT_FIT, "no training data: call gpmpc_fit first");
+    if (B <= 0 || H < 0) return fail(h, GPMPC_ERR_INVALID, "B must be > 0 and H >= 0");
+    if (h->m < 0) return fail(h, GPMPC_ERR_INVALID, "D < E");
+    if (!pair_launcher(h->D)) return fail(h, GPMPC_ERR_UNSUPPORTED, "input dimension D outside 2..8");
+    return GPMPC_OK;
+}
+
+static StepDims make_dims(gpmpc_ctx *h, int B)
+{
+    StepDims d;
+    d.B = B; d.Bpad = round_up(B, 32); d.D = h->D; d.E = h->E; d.m = h->m; d.G = (int)h->groups.size();
+    d.n = h->n; d.ld = h->ld;
+    return d;
+}
+
+// number of pair-space partitions: fill the machine with 2 blocks per SM
+static int pair_partitions(gpmpc_ctx *h, int B, long long total_tiles)
+{
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const int chunks = (B + PAIR_THREADS - 1) / PAIR_THREADS;
+    long long P = (2LL * sms + chunks - 1) / chunks;
+    if (P > total_tiles) P = total_tiles;
+    if (P < 1) P = 1;
+    return (int)P;
+}
+
+template <int D> static void launch_mean(const MeanArgs &ma, dim3 grid, cudaStream_t st)
+{
+    mean_sums_kernel<D><<<grid, MEAN_THREADS, 0, st>>>(ma);
+}
+static void launch_mean_d(int D, const MeanArgs &ma, dim3 grid, cudaStream_t st)
+{
+    switch (D) {
+        case 2: launch_mean<2>(ma, grid, st); break; case 3: launch_mean<3>(ma, grid, st); break;
+        case 4: launch_mean<4>(ma, grid, st); break; case 5: launch_mean<5>(ma, grid, st); break;
+        case 6: launch_mean<6>(ma, grid, st); break; case 7: launch_mean<7>(ma, grid, st); break;
+        case 8: launch_mean<8>(ma, grid, st); break;
+    }
+}
+
+// One moment-matching step for all rollouts: us/cst must have been prepared.  Writes mean/var of step t
+// (slot t of mu/var) and, if want_grad, the tape entry t-1.
+static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int P, long long total_tiles, bool want_grad,
+                    double *us, double *cst, double *mu, double *var, double *tape)
+{
+    const size_t mat = (size_t)h->ld * h->ld;
+    const int NA = nacc(d.D);
+    if (h->time_pairs) cudaEventRecord(h->ev0, h->stream);
+    for (int g = 0; g < d.G; ++g) {
+        const LambdaGroup &grp = h->groups[g];
+        PairArgs pa;
+        MeanArgs ma;
+        for (int i = 0; i < kGroupMax; ++i) {
+            const int o = grp.outputs[i < grp.count ? i : 0];
+            pa.Wt[i] = h->Wt.as<double>() + (size_t)o * mat;
+            pa.out_idx[i] = o;
+            ma.beta[i] = h->beta.as<double>() + (size_t)o * h->ld;
+            ma.out_idx[i] = o;
+        }
+        pa.X = h->X.as<double>();
+        pa.cst = cst + (size_t)g * 4 * d.D * d.Bpad;
+        pa.part = h->part.as<double>();
+        pa.ld = h->ld; pa.ntile = h->ld / PT; pa.B = d.B; pa.Bpad = d.Bpad; pa.E = d.E; pa.P = P;
+        pa.total_tiles = total_tiles;
+        dim3 grid(P, (d.B + PAIR_THREADS - 1) / PAIR_THREADS);
+        cudaError_t e = pair_launcher(d.D)(grp.count, want_grad, pa, grid, h->stream);
+        h->launches++;
+        if (e != cudaSuccess) return fail(h, GPMPC_ERR_CUDA, std::string("mm_pairs_batch: ") + cudaGetErrorString(e));
+
+        ma.X = pa.X; ma.EG = grp.count; ma.cst = pa.cst; ma.mpart = h->mpart.as<double>(); ma.d = d;
+        dim3 mgrid((d.B + MEAN_THREADS - 1) / MEAN_THREADS, MEAN_JP);
+        launch_mean_d(d.D, ma, mgrid, h->stream);
+        GP_LAUNCH_CHECK(h);
+    }
+    if (h->time_pairs) cudaEventRecord(h->ev1, h->stream);
+    dim3 fgrid((d.B + 127) / 128, d.E);
+    finalize_step_kernel<<<fgrid, 128, 0, h->stream>>>(d, t, P, h->part.as<double>(), h->mpart.as<double>(), us,
+                                                       h->hyp.as<double>(), mu, var, tape, want_grad ? 1 : 0);
+    GP_LAUNCH_CHECK(h);
+    (void)NA;
+    return GPMPC_OK;
+}
+
+struct RolloutWork {
+    StepDims d; int P; long long total_tiles;
+    double *x0int, *Uint, *us, *cst, *lamg;
+};
+
+static int reserve_rollout(gpmpc_ctx *h, int B, int H, RolloutWork &w)
+{
+    w.d = make_dims(h, B);
+    const StepDims &d = w.d;
+    const long long nt = h->ld / PT;
+    w.total_tiles = nt * (nt + 1) / 2;
+    w.P = pair_partitions(h, B, w.total_tiles);
+    const size_t Bp = d.Bpad;
+    const int Hs = H > 0 ? H : 1;
+    GP_CUDA(h, h->mu.reserve((size_t)(H + 1) * d.E * Bp * sizeof(double)));
+    GP_CUDA(h, h->var.reserve((size_t)(H + 1) * d.E * Bp * sizeof(double)));
+    GP_CUDA(h, h->tape.reserve((size_t)Hs * d.E * ntape(d.D) * Bp * sizeof(double)));
+    GP_CUDA(h, h->part.reserve((size_t)w.P * d.E * nacc(d.D) * Bp * sizeof(double)));
+    GP_CUDA(h, h->mpart.reserve((size_t)MEAN_JP * d.E * nacc(d.D) * Bp * sizeof(double)));
+    // cst: x0int [E][Bp] | Uint [H*m][Bp] | us [2D][Bp] | cst [G][4D][Bp]
+    const size_t cnt = (size_t)d.E * Bp + (size_t)Hs * (d.m > 0 ? d.m : 1) * Bp + 2 * (size_t)d.D * Bp +
+                       (size_t)d.G * 4 * d.D * Bp + 64;
+    GP_CUDA(h, h->cst.reserve(cnt * sizeof(double)));
+    double *p = h->cst.as<double>();
+    w.x0int = p; p += (size_t)d.E * Bp;
+    w.Uint = p; p += (size_t)Hs * (d.m > 0 ? d.m : 1) * Bp;
+    w.us = p; p += 2 * (size_t)d.D * Bp;
+    w.cst = p;
+    w.lamg = h->hyp.as<double>() + (size_t)d.E * d.D + d.E;      // group lambdas [G][D], see upload_prop_hypers
+    return GPMPC_OK;
+}
+
+// stage a host-or-device array into a device buffer (returns the device pointer to use)
+static int stage_in(gpmpc_ctx *h, DevBuf &buf, size_t &off, const double *src, size_t count, const double **dev)
+{
+    if (is_device_ptr(src)) { *dev = src; return GPMPC_OK; }
+    double *dst = reinterpret_cast<double *>(reinterpret_cast<char *>(buf.p) + off);
+    GP_CUDA(h, cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    off += (count * sizeof(double) + 255) / 256 * 256;
+    *dev = dst;
+    return GPMPC_OK;
+}
+
+// forward rollout into h->mu / h->var (+ tape).  x0_dev [B,E], U_dev [B,H,m] are device pointers.
+static int forward(gpmpc_ctx *h, int B, int H, const double *x0_dev, const double *U_dev, bool want_grad, RolloutWork &w)
+{
+    int rc = reserve_rollout(h, B, H, w);
+    if (rc) return rc;
+    const StepDims &d = w.d;
+    dim3 blk(128);
+    to_internal_kernel<<<dim3((B + 127) / 128, d.E), blk, 0, h->stream>>>(x0_dev, B, d.Bpad, d.E, w.x0int);
+    GP_LAUNCH_CHECK(h);
+    if (H > 0 && d.m > 0) {
+        to_internal_kernel<<<dim3((B + 127) / 128, H * d.m), blk, 0, h->stream>>>(U_dev, B, d.Bpad, H * d.m, w.Uint);
+        GP_LAUNCH_CHECK(h);
+    }
+    init_state_kernel<<<dim3((B + 127) / 128, d.E), blk, 0, h->stream>>>(w.x0int, B, d.Bpad, d.E, h->mu.as<double>(),
+                                                                           h->var.as<double>(), 1e-3);
+    GP_LAUNCH_CHECK(h);
+    const double act_var = (double)1e-3f;          // fp32 eye in the action block, src/dynamics.py:162
+    h->last_pair_ms = 0.0; h->last_pair_evals = 0;
+    for (int t = 1; t <= H; ++t) {
+        prep_step_kernel<<<dim3((B + 127) / 128, d.G), blk, 0, h->stream>>>(d, t, h->mu.as<double>(), h->var.as<double>(),
+                                                                             w.Uint, w.lamg, w.us, w.cst, act_var);
+        GP_LAUNCH_CHECK(h);
+        rc = run_step(h, d, t, w.P, w.total_tiles, want_grad, w.us, w.cst, h->mu.as<double>(), h->var.as<double>(),
+                      h->tape.as<double>());
+        if (rc) return rc;
+        if (h->time_pairs) {
+            GP_CUDA(h, cudaEventSynchronize(h->ev1));
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+            h->last_pair_ms += ms;
+            h->last_pair_evals += (long long)B * d.E * ((long long)h->n * (h->n + 1) / 2);
+        }
+    }
+    h->tape_B = want_grad ? B : 0;
+    h->tape_H = want_grad ? H : 0;
+    return GPMPC_OK;
+}
+
+static int export_traj(gpmpc_ctx *h, const StepDims &d, int H, double *means, double *vars)
+{
+    // means / vars: [B, H+1, E] host or device
+    const size_t count = (size_t)d.B * (H + 1) * d.E;
+    for (int which = 0; which < 2; ++which) {
+        double *out = which ? vars : means;
+        if (!out) continue;
+        const double *src = which ? h->var.as<double>() : h->mu.as<double>();
+        double *dev = out;
+        const bool host = !is_device_ptr(out);
+        if (host) { GP_CUDA(h, h->stage_out.reserve(count * sizeof(double))); dev = h->stage_out.as<double>(); }
+        to_external_kernel<<<dim3((d.B + 127) / 128, (H + 1) * d.E), 128, 0, h->stream>>>(src, d.B, d.Bpad, (H + 1) * d.E, dev);
+        GP_LAUNCH_CHECK(h);
+        if (host) {
+            GP_CUDA(h, cudaMemcpyAsync(out, dev, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            GP_CUDA(h, cudaStreamSynchronize(h->stream));
+        }
+    }
+    return GPMPC_OK;
+}
+
+}  // namespace gpmpc
+
+using namespace gpmpc;
+
+extern "C" int gpmpc_rollout(gpmpc_handle h, int B, int H, const double *x0, const double *U, double *means, double *vars)
+{
+    int rc = check_ready(h, B, H);
+    if (rc) return rc;
+    if (!x0 || (H > 0 && h->m > 0 && !U)) return fail(h, GPMPC_ERR_INVALID, "gpmpc_rollout: null input");
+    GP_CUDA(h, cudaSetDevice(h->device));
+    const size_t need = ((size_t)B * h->E + (size_t)B * H * h->m) * sizeof(double) + 1024;
+    GP_CUDA(h, h->stage_in.reserve(need));
+    size_t off = 0;
+    const double *x0d, *Ud = nullptr;
+    if ((rc = stage_in(h, h->stage_in, off, x0, (size_t)B * h->E, &x0d))) return rc;
+    if (H > 0 && h->m > 0 && (rc = stage_in(h, h->stage_in, off, U, (size_t)B * H * h->m, &Ud))) return rc;
+    RolloutWork w;
+    if ((rc = forward(h, B, H, x0d, Ud, true, w))) return rc;
+    return export_traj(h, w.d, H, means, vars);
+}
+
+static int upload_cost_args(gpmpc_ctx *h, CostArgs &ca, const double *Q, const double *R, const double *Rdelta,
+                            const double *xref, const double *uref)
+{
+    const int E = h->E, m = h->m;
+    auto fetch = [&](const double *src, double *dst, size_t cnt) -> cudaError_t {
+        if (!src) { std::memset(dst, 0, cnt * sizeof(double)); return cudaSuccess; }
+        if (is_device_ptr(src)) {
+            cudaError_t e = cudaMemcpyAsync(dst, src, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+            if (e != cudaSuccess) return e;
+            return cudaStreamSynchronize(h->stream);
+        }
+        std::memcpy(dst, src, cnt * sizeof(double));
+        return cudaSuccess;
+    };
+    GP_CUDA(h, fetch(Q, ca.Q, (size_t)E * E));
+    GP_CUDA(h, fetch(R, ca.R, (size_t)m * m));
+    GP_CUDA(h, fetch(Rdelta, ca.Rd, (size_t)m * m));
+    GP_CUDA(h, fetch(xref, ca.xref, E));
+    GP_CUDA(h, fetch(uref, ca.uref, m));
+    // Q^-1 on the host (LU with partial pivoting), src/mpc.py:179
+    {
+        double A[kMaxE * kMaxE];
+        int piv[kMaxE];
+        std::memcpy(A, ca.Q, sizeof(double) * E * E);
+        for (int c = 0; c < E; ++c) {
+            int p = c;
+            for (int r = c + 1; r < E; ++r) if (std::abs(A[r * E + c]) > std::abs(A[p * E + c])) p = r;
+            piv[c] = p;
+            if (p != c) for (int k = 0; k < E; ++k) std::swap(A[c * E + k], A[p * E + k]);
+            const double dinv = 1.0 / A[c * E + c];
+            for (int r = c + 1; r < E; ++r) {
+                const double f = A[r * E + c] * dinv;
+                A[r * E + c] = f;
+                for (int k = c + 1; k < E; ++k) A[r * E + k] -= f * A[c * E + k];
+            }
+        }
+        for (int col = 0; col < E; ++col) {
+            double x[kMaxE];
+            for (int r = 0; r < E; ++r) x[r] = (r == col) ? 1.0 : 0.0;
+            for (int c = 0; c < E; ++c) if (piv[c] != c) std::swap(x[c], x[piv[c]]);
+            for (int r = 0; r < E; ++r) for (int k = 0; k < r; ++k) x[r] -= A[r * E + k] * x[k];
+            for (int r = E - 1; r >= 0; --r) {
+                for (int k = r + 1; k < E; ++k) x[r] -= A[r * E + k] * x[k];
+                x[r] /= A[r * E + r];
+            }
+            for (int r = 0; r < E; ++r) ca.Qi[r * E + col] = x[r];
+        }
+    }
+    return GPMPC_OK;
+}
+
+extern "C" int gpmpc_rollout_cost_grad(gpmpc_handle h, int B, int H, const double *x0, const double *U,
+                                       const double *gamma, const double *Q, const double *R, const double *Rdelta,
+                                       const double *last_u, const double *xref, const double *uref, double *cost,
+                                       double *grad, double *means, double *vars)
+{
+    int rc = check_ready(h, B, H);
+    if (rc) return rc;
+    if (!x0 || !gamma || !Q || !cost || (H > 0 && h->m > 0 && (!U || !R)))
+        return fail(h, GPMPC_ERR_INVALID, "gpmpc_rollout_cost_grad: null input");
+    if (Rdelta && !last_u) return fail(h, GPMPC_ERR_INVALID, "gpmpc_rollout_cost_grad: Rdelta needs last_u");
+    GP_CUDA(h, cudaSetDevice(h->device));
+    const int E = h->E, m = h->m;
+    const size_t need = ((size_t)B * E + (size_t)B * H * m + (size_t)B + (size_t)B * m) * sizeof(double) + 2048;
+    GP_CUDA(h, h->stage_in.reserve(need));
+    size_t off = 0;
+    const double *x0d, *Ud = nullptr, *gd, *lud = nullptr;
+    if ((rc = stage_in(h, h->stage_in, off, x0, (size_t)B * E, &x0d))) return rc;
+    if (H > 0 && m > 0 && (rc = stage_in(h, h->stage_in, off, U, (size_t)B * H * m, &Ud))) return rc;
+    if ((rc = stage_in(h, h->stage_in, off, gamma, (size_t)B, &gd))) return rc;
+    if (Rdelta && (rc = stage_in(h, h->stage_in, off, last_u, (size_t)B * m, &lud))) return rc;
+
+    const bool want_grad = grad != nullptr;
+    RolloutWork w;
+    if ((rc = forward(h, B, H, x0d, Ud, want_grad, w))) return rc;
+    const StepDims &d = w.d;
+
+    CostArgs ca;
+    std::memset(&ca, 0, sizeof ca);
+    if ((rc = upload_cost_args(h, ca, Q, R, Rdelta, xref, uref))) return rc;
+    ca.d = d; ca.H = H; ca.mode = 0; ca.has_rd = Rdelta ? 1 : 0; ca.want_grad = want_grad ? 1 : 0;
+    ca.mu = h->mu.as<double>(); ca.var = h->var.as<double>(); ca.tape = h->tape.as<double>(); ca.Uint = w.Uint;
+    ca.gamma = gd;
+    // gbuf: last_u internal [m][Bp] | grad internal [H*m][Bp] | cost [B] | grad external [B*H*m]
+    const size_t Bp = d.Bpad;
+    const size_t gcount = (size_t)m * Bp + (size_t)H * m * Bp + Bp + (size_t)B * H * m + 64;
+    GP_CUDA(h, h->gbuf.reserve(gcount * sizeof(double)));
+    double *p = h->gbuf.as<double>();
+    double *lu_int = p; p += (size_t)m * Bp;
+    double *grad_int = p; p += (size_t)H * m * Bp;
+    double *cost_dev = p; p += Bp;
+    double *grad_ext = p;
+    if (Rdelta && m > 0) {
+        to_internal_kernel<<<dim3((B + 127) / 128, m), 128, 0, h->stream>>>(lud, B, d.Bpad, m, lu_int);
+        GP_LAUNCH_CHECK(h);
+    }
+    ca.last_u = lu_int;
+    const bool cost_host = !is_device_ptr(cost);
+    ca.cost = cost_host ? cost_dev : cost;
+    ca.gradint = grad_int;
+    ca.gx0int = nullptr;
+    cost_adjoint_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(ca);
+    GP_LAUNCH_CHECK(h);
+    if (want_grad && H > 0 && m > 0) {
+        const bool ghost = !is_device_ptr(grad);
+        double *gdev = ghost ? grad_ext : grad;
+        to_external_kernel<<<dim3((B + 127) / 128, H * m), 128, 0, h->stream>>>(grad_int, B, d.Bpad, H * m, gdev);
+        GP_LAUNCH_CHECK(h);
+        if (ghost) GP_CUDA(h, cudaMemcpyAsync(grad, gdev, (size_t)B * H * m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (cost_host) GP_CUDA(h, cudaMemcpyAsync(cost, cost_dev, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (means || vars) { if ((rc = export_traj(h, d, H, means, vars))) return rc; }
+    if (cost_host || (want_grad && !is_device_ptr(grad))) GP_CUDA(h, cudaStreamSynchronize(h->stream));
+    return GPMPC_OK;
+}
+
+extern "C" int gpmpc_rollout_vjp(gpmpc_handle h, int B, int H, const double *gmeans, const double *gvars, double *gU,
+                                 double *gx0)
+{
+    int rc = check_ready(h, B, H);
+    if (rc) return rc;
+    if (h->tape_B != B || h->tape_H != H)
+        return fail(h, GPMPC_ERR_INVALID, "gpmpc_rollout_vjp: no tape of this shape (call gpmpc_rollout first)");
+    GP_CUDA(h, cudaSetDevice(h->device));
+    const int E = h->E, m = h->m;
+    StepDims d = make_dims(h, B);
+    const size_t Bp = d.Bpad;
+    const size_t tcount = (size_t)(H + 1) * E;
+    GP_CUDA(h, h->stage_in.reserve(2 * (size_t)B * tcount * sizeof(double) + 1024));
+    size_t off = 0;
+    const double *gmd = nullptr, *gvd = nullptr;
+    if (gmeans && (rc = stage_in(h, h->stage_in, off, gmeans, (size_t)B * tcount, &gmd))) return rc;
+    if (gvars && (rc = stage_in(h, h->stage_in, off, gvars, (size_t)B * tcount, &gvd))) return rc;
+    // gbuf: seed_mu [tcount][Bp] | seed_var [tcount][Bp] | grad_int [H*m][Bp] | gx0_int [E][Bp] | ext
+    const size_t gcount = 2 * tcount * Bp + (size_t)H * m * Bp + (size_t)E * Bp + (size_t)B * H * m + (size_t)B * E + 64;
+    GP_CUDA(h, h->gbuf.reserve(gcount * sizeof(double)));
+    double *p = h->gbuf.as<double>();
+    double *smu = p; p += tcount * Bp;
+    double *svar = p; p += tcount * Bp;
+    double *grad_int = p; p += (size_t)H * m * Bp;
+    double *gx0_int = p; p += (size_t)E * Bp;
+    double *ext = p;
+    if (gmd) { to_internal_kernel<<<dim3((B + 127) / 128, (unsigned)tcount), 128, 0, h->stream>>>(gmd, B, d.Bpad, (int)tcount, smu); GP_LAUNCH_CHECK(h); }
+    if (gvd) { to_internal_kernel<<<dim3((B + 127) / 128, (unsigned)tcount), 128, 0, h->stream>>>(gvd, B, d.Bpad, (int)tcount, svar); GP_LAUNCH_CHECK(h); }
+    CostArgs ca;
+    std::memset(&ca, 0, sizeof ca);
+    ca.d = d; ca.H = H; ca.mode = 1; ca.has_rd = 0; ca.want_grad = 1;
+    ca.mu = h->mu.as<double>(); ca.var = h->var.as<double>(); ca.tape = h->tape.as<double>(); ca.Uint = nullptr;
+    ca.seed_mu = gmd ? smu : nullptr; ca.seed_var = gvd ? svar : nullptr;
+    ca.gradint = grad_int; ca.gx0int = gx0_int; ca.cost = nullptr;
+    cost_adjoint_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(ca);
+    GP_LAUNCH_CHECK(h);
+    bool sync = false;
+    if (gU && H > 0 && m > 0) {
+        const bool host = !is_device_ptr(gU);
+        double *dev = host ? ext : gU;
+        to_external_kernel<<<dim3((B + 127) / 128, H * m), 128, 0, h->stream>>>(grad_int, B, d.Bpad, H * m, dev);
+        GP_LAUNCH_CHECK(h);
+        if (host) { GP_CUDA(h, cudaMemcpyAsync(gU, dev, (size_t)B * H * m * sizeof(double), cudaMemcpyDeviceToHost, h->stream)); sync = true; }
+    }
+    if (gx0) {
+        const bool host = !is_device_ptr(gx0);
+        double *dev = host ? ext + (size_t)B * H * m : gx0;
+        to_external_kernel<<<dim3((B + 127) / 128, E), 128, 0, h->stream>>>(gx0_int, B, d.Bpad, E, dev);
+        GP_LAUNCH_CHECK(h);
+        if (host) { GP_CUDA(h, cudaMemcpyAsync(gx0, dev, (size_t)B * E * sizeof(double), cudaMemcpyDeviceToHost, h->stream)); sync = true; }
+    }
+    if (sync) GP_CUDA(h, cudaStreamSynchronize(h->stream));
+    return GPMPC_OK;
+}
+
+// Batched moment matching for diagonal input variances through the same kernels (one "step").
+extern "C" int gpmpc_moment_match_diag_internal(gpmpc_handle h, int B, const double *U_dev, const double *S_dev,
+                                                double *mean_out, double *var_out);
+
+namespace gpmpc {
+// us layout [2D][Bpad] is filled directly from U[B,D], S[B,D]
+__global__ void prep_direct_kernel(StepDims d, const double *__restrict__ U, const double *__restrict__ S,
+                                   const double *__restrict__ lam_group, double *__restrict__ us, double *__restrict__ cst)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = blockIdx.y;
+    if (b >= d.B) return;
+    for (int k = 0; k < d.D; ++k) {
+        const double u = U[(size_t)b * d.D + k], s = S[(size_t)b * d.D + k];
+        if (g == 0) { us[(size_t)k * d.Bpad + b] = u; us[(size_t)(d.D + k) * d.Bpad + b] = s; }
+        const double lam = lam_group[g * d.D + k];
+        const double a = 1.0 / (0.5 * lam + s), bb = 1.0 / (s + lam);
+        const double c = sqrt(0.125 * a), cm = sqrt(0.5 * bb);
+        double *cg = cst + (size_t)g * 4 * d.D * d.Bpad;
+        cg[(size_t)k * d.Bpad + b] = c;
+        cg[(size_t)(d.D + k) * d.Bpad + b] = c * u;
+        cg[(size_t)(2 * d.D + k) * d.Bpad + b] = cm;
+        cg[(size_t)(3 * d.D + k) * d.Bpad + b] = cm * u;
+    }
+}
+}  // namespace gpmpc
+
+extern "C" int gpmpc_moment_match_diag_internal(gpmpc_handle h, int B, const double *U_dev, const double *S_dev,
+                                                double *mean_out, double *var_out)
+{
+    int rc = check_ready(h, B, 1);
+    if (rc) return rc;
+    RolloutWork w;
+    if ((rc = reserve_rollout(h, B, 1, w))) return rc;
+    const StepDims &d = w.d;
+    prep_direct_kernel<<<dim3((B + 127) / 128, d.G), 128, 0, h->stream>>>(d, U_dev, S_dev, w.lamg, w.us, w.cst);
+    GP_LAUNCH_CHECK(h);
+    h->last_pair_ms = 0.0; h->last_pair_evals = 0;
+    // results land in slot t = 1 of mu / var
+    if ((rc = run_step(h, d, 1, w.P, w.total_tiles, false, w.us, w.cst, h->mu.as<double>(), h->var.as<double>(),
+                       h->tape.as<double>()))) return rc;
+    if (h->time_pairs) {
+        GP_CUDA(h, cudaEventSynchronize(h->ev1));
+        float ms = 0.f; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+        h->last_pair_ms = ms; h->last_pair_evals = (long long)B * d.E * ((long long)h->n * (h->n + 1) / 2);
+    }
+    h->tape_B = 0; h->tape_H = 0;
+    for (int which = 0; which < 2; ++which) {
+        double *out = which ? var_out : mean_out;
+        if (!out) continue;
+        const double *src = (which ? h->var.as<double>() : h->mu.as<double>()) + (size_t)d.E * d.Bpad;
+        const bool host = !is_device_ptr(out);
+        double *dev = out;
+        if (host) { GP_CUDA(h, h->stage_out.reserve((size_t)B * d.E * sizeof(double))); dev = h->stage_out.as<double>(); }
+        to_external_kernel<<<dim3((B + 127) / 128, d.E), 128, 0, h->stream>>>(src, B, d.Bpad, d.E, dev);
+        GP_LAUNCH_CHECK(h);
+        if (host) {
+            GP_CUDA(h, cudaMemcpyAsync(out, dev, (size_t)B * d.E * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            GP_CUDA(h, cudaStreamSynchronize(h->stream));
+        }
+    }
+    return GPMPC_OK;
+}

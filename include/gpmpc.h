@@ -1,0 +1,148 @@
+/*
+ * gpmpc.h -- C ABI of libgpmpc.so, the B200 (sm_100a) implementation of the GP-MPC rollout hot path.
+ *
+ * The reference (Thiagodcv/gaussian-process-mpc) has no FFI; its hot path sits behind Python classes.
+ * Each entry point below names the reference interface it replaces (file:line relative to the
+ * reference root).  The Python classes in gaussian-process-mpc_b200/ bind these with ctypes; see
+ * INTEGRATION.md for the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 (GPMPC_OK) or a negative error code and never throws;
+ *     gpmpc_last_error(h) gives the message of the last failure on that handle;
+ *   - all arrays are fp64, row-major, dense; every data pointer may be a HOST or a DEVICE pointer
+ *     (detected per pointer with cudaPointerGetAttributes); host buffers are staged through the
+ *     handle's stream;
+ *   - a handle owns one GP bundle (E outputs sharing the training inputs X) on one CUDA device; calls on
+ *     a handle are serialised on its stream; results written to device buffers are ordered on that
+ *     stream, results written to host buffers are complete on return;
+ *   - non-finite results (e.g. the NaN cost of log(det) < 0, src/mpc.py:183) are data, not errors.
+ *
+ * Symbols: n training points, D = E + m input dimension, E outputs (state_dim), m actions,
+ *          B independent rollouts, H horizon.
+ */
+#ifndef GPMPC_H
+#define GPMPC_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gpmpc_ctx *gpmpc_handle;
+
+#define GPMPC_OK               0
+#define GPMPC_ERR_INVALID     -1   /* bad argument / shape                                   */
+#define GPMPC_ERR_CUDA        -2   /* CUDA runtime failure                                   */
+#define GPMPC_ERR_NOT_FIT     -3   /* no training data / gpmpc_fit not called                */
+#define GPMPC_ERR_UNSUPPORTED -4   /* D, E outside the compiled range                        */
+#define GPMPC_ERR_NOT_PD      -5   /* Cholesky met a non-positive pivot (Ky not positive definite) */
+
+#define GPMPC_MAX_D 8              /* compiled input dimensions: 1..8                         */
+#define GPMPC_MAX_E 8              /* compiled output counts:    1..8 (E < D unless m == 0)   */
+
+/* gpmpc_get_matrix selectors */
+#define GPMPC_MAT_KF     0         /* [n,n]  sigma_f^2 exp(-1/2 d^2)          src/gpr.py:169  */
+#define GPMPC_MAT_KY     1         /* [n,n]  Kf + noise_var I                 src/gpr.py:170  */
+#define GPMPC_MAT_KY_INV 2         /* [n,n]  Ky^-1                            src/gpr.py:171  */
+#define GPMPC_MAT_BETA   3         /* [n]    Ky^-1 y          src/tools/uncertainty_prop.py:327 */
+
+int gpmpc_version(void);
+
+/* Handle lifetime.  Replaces Dynamics.__init__ / GaussianProcessRegression.__init__
+ * (src/dynamics.py:10-37, src/gpr.py:11-49): one handle per bundle of E GPs with D inputs.        */
+int gpmpc_create(int device, int D, int E, gpmpc_handle *out);
+int gpmpc_destroy(gpmpc_handle h);
+const char *gpmpc_last_error(gpmpc_handle h);   /* h may be NULL: message of the last failed create */
+int gpmpc_set_stream(gpmpc_handle h, void *cuda_stream);   /* cudaStream_t; NULL = legacy default  */
+int gpmpc_synchronize(gpmpc_handle h);
+int gpmpc_num_train(gpmpc_handle h);
+
+/* Fit: Gram matrix, blocked Cholesky, Ky^-1, beta and the moment-matching weight matrices.
+ * Replaces GaussianProcessRegression.build_Ky_inv_mat for all E outputs (src/gpr.py:159-171) as driven by
+ * Dynamics.append_train_data (src/dynamics.py:39-60).
+ *   X[n,D], Y[n,E], lambdas[E,D] (SQUARED length-scales), sigma_f[E], noise_var[E] (= sigma_n^2 as the
+ *   caller wants it added to the diagonal; the reference adds an fp32-rounded value, src/gpr.py:170).   */
+int gpmpc_fit(gpmpc_handle h, int n, const double *X, const double *Y, const double *lambdas,
+              const double *sigma_f, const double *noise_var);
+
+/* Refit one output only (hyper-parameters of output `a` changed; X unchanged).  Replaces a single
+ * GaussianProcessRegression.build_Ky_inv_mat call (src/gpr.py:159-171).  y may be NULL (keep targets). */
+int gpmpc_refit_output(gpmpc_handle h, int a, const double *y, const double *lambdas_a, double sigma_f_a,
+                       double noise_var_a);
+
+/* Change the length-scales / amplitudes used by the MOMENT-MATCHING formulas without refitting Ky^-1.
+ * The reference reads log_lambdas / sigma_f at rollout time (src/dynamics.py:171,173) but Ky_inv from the
+ * last build (src/dynamics.py:170), so setters without a rebuild affect only the propagation.           */
+int gpmpc_set_propagation_hypers(gpmpc_handle h, const double *lambdas, const double *sigma_f);
+
+/* Copy a fitted matrix of output a into out (leading dimension n for matrices).                      */
+int gpmpc_get_matrix(gpmpc_handle h, int which, int a, double *out);
+
+/* K(X*, X_train) for output a: out[p,n].  Replaces compute_pred_train_covariance (src/gpr.py:253-283). */
+int gpmpc_kernel_matrix(gpmpc_handle h, int a, int p, const double *Xs, double *out);
+
+/* Posterior at p test inputs for output a: mean[p]; cov[p,p] if cov != NULL (+ noise_var I if
+ * add_noise).  Replaces predict_latent_vars with f_nom = None (src/gpr.py:285-332).                  */
+int gpmpc_predict(gpmpc_handle h, int a, int p, const double *Xs, double *mean, double *cov, int add_noise);
+
+/* Exact moments of all E GP outputs for B Gaussian inputs N(U_b, S_b).  S is [B,D] (diagonal variances,
+ * s_is_full = 0) or [B,D,D] (full covariance, s_is_full = 1).  mean[B,E], var[B,E] (latent variance, no
+ * noise term).  Replaces mean_prop_torch + variance_prop_torch called on a fitted bundle
+ * (src/tools/uncertainty_prop.py:296-338,341-399 as used at src/dynamics.py:175-181).                 */
+int gpmpc_moment_match(gpmpc_handle h, int B, const double *U, const double *S, int s_is_full,
+                       double *mean, double *var);
+
+/* Stateless form of the same two functions for caller-supplied matrices (no handle state is used except
+ * the device/stream): Kinv[n,n], lambdas[D], u[D], S[D,D] full, X[n,D], y[n].
+ * Outputs: mean[1], var[1] (may be NULL), beta[n] (may be NULL), l[n] (may be NULL).
+ * If y == NULL the call has variance_prop_torch's signature: beta[n] and mean[1] are INPUTS and only var
+ * is written.  Replaces mean_prop_torch / variance_prop_torch as free functions
+ * (src/tools/uncertainty_prop.py:296-338,341-399).                                                  */
+int gpmpc_moment_match_raw(gpmpc_handle h, int n, int D, const double *Kinv, const double *lambdas,
+                           const double *u, const double *S, const double *X, const double *y,
+                           double sigma_f, double *mean, double *var, double *beta, double *l);
+
+/* Cross-covariance of outputs a and b for one Gaussian input, caller-supplied vectors:
+ * cov = beta1^T Qt beta2 - mean1 mean2 (src/tools/uncertainty_prop.py:187-236 / 402-465).
+ * bugcompat != 0 reproduces the transposed cross term of the torch function (:446).                  */
+int gpmpc_covariance_raw(gpmpc_handle h, int n, int D, const double *lambdas1, const double *lambdas2,
+                         const double *u, const double *S, const double *X, double mean1, double mean2,
+                         const double *beta1, const double *beta2, double sigma_f1, double sigma_f2,
+                         int bugcompat, double *cov);
+
+/* Variance-only moment-matched rollout of B control sequences over H steps.
+ *   x0[B,E], U[B,H,m]  ->  means[B,H+1,E], vars[B,H+1,E]
+ * Step-0 variance is 1e-3 (exact fp64) and the action variance is fp32(1e-3) as in
+ * src/dynamics.py:148,162.  The per-step partial derivatives are kept in the handle for gpmpc_rollout_vjp.
+ * Replaces Dynamics.forward_propagate_torch (src/dynamics.py:126-191).                                */
+int gpmpc_rollout(gpmpc_handle h, int B, int H, const double *x0, const double *U, double *means,
+                  double *vars);
+
+/* Vector-Jacobian product of the last gpmpc_rollout: given d loss / d means and d loss / d vars
+ * ([B,H+1,E] each, either may be NULL) return d loss / d U [B,H,m] and, if gx0 != NULL, d loss / d x0 [B,E].
+ * Replaces the autograd replay through forward_propagate_torch (src/mpc.py:251).                      */
+int gpmpc_rollout_vjp(gpmpc_handle h, int B, int H, const double *gmeans, const double *gvars, double *gU,
+                      double *gx0);
+
+/* Fused objective + gradient for B independent control sequences: rollout, risk-sensitive cost
+ * (src/mpc.py:156-200) and its exact gradient w.r.t. U (src/mpc.py:231-255).
+ *   x0[B,E], U[B,H,m], gamma[B], Q[E,E], R[m,m], Rdelta[m,m] or NULL, last_u[B,m] (used iff Rdelta),
+ *   xref[E], uref[m]  ->  cost[B], grad[B,H,m] (NULL = cost only), means/vars [B,H+1,E] (may be NULL).
+ * Replaces RiskSensitiveMPC.objective + gradient (src/mpc.py:202-255).                                */
+int gpmpc_rollout_cost_grad(gpmpc_handle h, int B, int H, const double *x0, const double *U,
+                            const double *gamma, const double *Q, const double *R, const double *Rdelta,
+                            const double *last_u, const double *xref, const double *uref, double *cost,
+                            double *grad, double *means, double *vars);
+
+/* Introspection for benchmarks: kernels launched by this handle since creation, and the device time
+ * (ms, CUDA events on the handle's stream) of the last pair-sum kernel sequence.                      */
+long long gpmpc_launch_count(gpmpc_handle h);
+int gpmpc_last_pair_kernel_ms(gpmpc_handle h, double *ms, long long *pair_evals);
+
+/* Measured ceilings for the roofline: sustained fp64 FMA rate (TFLOP/s, 2 flop per FMA) and the rate of
+ * the library's own exp() (Gexp/s) on this device.                                                    */
+int gpmpc_measure_fp64_peak(gpmpc_handle h, double *fma_tflops, double *exp_gops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPMPC_H */

@@ -1,0 +1,367 @@
+"""Parity of the CUDA path (through the C ABI / the reference-shaped Python classes) against
+  (a) golden vectors produced by the unmodified reference (tests/golden/*.npz) and
+  (b) the CPU oracle (oracle/) on seeded inputs.
+All tests need a CUDA device: run with `-m gpu` on the B200 box.
+
+Tolerances (fp64 end to end): the north star asks for relative 1e-6 on posterior mean / variance, cost and
+gradient.  Variances are small differences of O(sigma_f^2) terms, so their tolerance is relative to
+max(|ref|, 1e-3 sigma_f^2) as SURVEY 7 ("hard parts") explains.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-6
+
+
+def close(a, b, rtol=RTOL, floor=1e-12):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    nan_a, nan_b = np.isnan(a), np.isnan(b)
+    assert np.array_equal(nan_a, nan_b), "NaN masks differ"
+    err = np.abs(a - b)[~nan_a]
+    ref = np.maximum(np.abs(b)[~nan_a], floor)
+    worst = float(np.max(err / ref)) if err.size else 0.0
+    assert worst <= rtol, f"max relative error {worst:.3e} > {rtol:.1e}"
+
+
+def norm_close(a, b, rtol=RTOL):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape
+    scale = max(np.max(np.abs(b)), 1e-300)
+    worst = float(np.max(np.abs(a - b)) / scale)
+    assert worst <= rtol, f"max error relative to max|ref| {worst:.3e} > {rtol:.1e}"
+
+
+@pytest.fixture(scope="module")
+def gp():
+    import gpmpc_b200
+    assert torch.cuda.is_available()
+    return gpmpc_b200
+
+
+def T(a):
+    return torch.tensor(np.asarray(a, dtype=np.float64), device="cuda:0")
+
+
+# ------------------------------------------------------------------------------------------------
+# GPR: Gram, inverse, posterior  (reference src/test/test_gpr.py:781-943)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["a", "b", "c"])
+def test_gpr_matrices_and_posterior(gp, name):
+    g = golden("gpr")
+    X = np.atleast_2d(g[f"gpr_{name}_X"]); y = g[f"gpr_{name}_y"]
+    lam = [float(v) for v in g[f"gpr_{name}_lam"]]
+    gpr = gp.GaussianProcessRegression(X.shape[1])
+    gpr.set_lambdas(lam); gpr.set_sigma_f(float(g[f"gpr_{name}_sf"])); gpr.set_sigma_n(float(g[f"gpr_{name}_sn"]))
+    # the setters must round through fp32 exactly like the reference's (src/gpr.py:59,72,85)
+    assert np.array_equal(gpr.get_lambdas(), g[f"gpr_{name}_lam_eff"])
+    assert gpr.get_sigma_f() == float(g[f"gpr_{name}_sf_eff"])
+    if name == "c":
+        gpr.append_train_data(X[0], float(y[0]))
+    else:
+        gpr.append_train_data(X, y)
+    norm_close(gpr.Kf.cpu().numpy(), g[f"gpr_{name}_Kf"], 1e-12)
+    norm_close(gpr.Ky.cpu().numpy(), g[f"gpr_{name}_Ky"], 1e-12)
+    norm_close(gpr.Ky_inv.cpu().numpy(), g[f"gpr_{name}_Kyinv"], 1e-9)
+    Xp = g[f"gpr_{name}_Xp"]
+    mean, cov = gpr.predict_latent_vars(Xp, covar=True, targets=False)
+    norm_close(mean, g[f"gpr_{name}_mean"], 1e-9)
+    norm_close(cov, g[f"gpr_{name}_cov"], 1e-8)
+    _, cov_t = gpr.predict_latent_vars(Xp, covar=True, targets=True)
+    norm_close(cov_t, g[f"gpr_{name}_cov_targets"], 1e-8)
+    norm_close(gpr.compute_pred_train_covariance(Xp).cpu().numpy(), g[f"gpr_{name}_Kpt"], 1e-12)
+    norm_close(gpr.compute_pred_train_covariance(Xp[0]).cpu().numpy(), g[f"gpr_{name}_k1"], 1e-7)  # fp32 in the ref
+
+
+def test_fit_large_vs_lapack(gp):
+    """Blocked Cholesky + DMMA inverse at n = 1500 (not a multiple of the tile) against LAPACK."""
+    rng = np.random.default_rng(0)
+    n, D = 1500, 5
+    X = rng.uniform(-1, 1, (n, D)); y = np.sin(X.sum(1))
+    gpr = gp.GaussianProcessRegression(D)
+    gpr.set_lambdas(np.full(D, 2.0)); gpr.set_sigma_n(np.float64(0.1))
+    gpr.append_train_data(X, y)
+    Ky = gpr.Ky.cpu().numpy()
+    Kinv = gpr.Ky_inv.cpu().numpy()
+    assert np.max(np.abs(Kinv - Kinv.T)) == 0.0
+    resid = np.max(np.abs(Kinv @ Ky - np.eye(n)))
+    assert resid < 1e-9, resid
+    norm_close(Kinv, np.linalg.inv(Ky), 1e-9)
+
+
+# ------------------------------------------------------------------------------------------------
+# Moment matching free functions, FULL input covariance  (src/test/tools/test_uncertainty_prop.py:183-385)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["a", "b", "c"])
+def test_uncertainty_prop_free_functions(gp, name):
+    from gpmpc_b200.tools.uncertainty_prop import mean_prop_torch, variance_prop_torch, covariance_prop_torch
+    g = golden("moment_matching")
+    X, y, u, S, sf = (g[f"mm_{name}_{k}"] for k in ("X", "y", "u", "S", "sf"))
+    sf = float(sf)
+    res = {}
+    for tag in ("1", "2"):
+        lam = g[f"mm_{name}_lam{tag}"]; Kinv = g[f"mm_{name}_Kinv{tag}"]
+        mu, d = mean_prop_torch(T(Kinv), T(lam), T(u), T(S), T(X), T(y), sf)
+        var = variance_prop_torch(T(Kinv), T(lam), T(u), T(S), T(X), mu, d["beta"], sf)
+        close(mu.item(), g[f"mm_{name}_mean{tag}"], 1e-9)
+        norm_close(d["beta"].cpu().numpy(), g[f"mm_{name}_beta{tag}"], 1e-10)
+        assert abs(var.item() - float(g[f"mm_{name}_var{tag}"])) <= RTOL * max(abs(float(g[f"mm_{name}_var{tag}"])), 1e-3 * sf ** 2)
+        if tag == "1":
+            norm_close(d["l"].cpu().numpy(), g[f"mm_{name}_l1"], 1e-10)
+        res[tag] = (mu, d["beta"])
+    lam1, lam2 = g[f"mm_{name}_lam1"], g[f"mm_{name}_lam2"]
+    c_bug = covariance_prop_torch(T(lam1), T(lam2), T(u), T(S), T(X), res["1"][0], res["2"][0], res["1"][1], res["2"][1],
+                                  sf, sf, bugcompat=True)
+    close(c_bug.item(), g[f"mm_{name}_cov12_torch"], 1e-8)
+    if name == "a":
+        c_ok = covariance_prop_torch(T(lam1), T(lam2), T(u), T(S), T(X), res["1"][0], res["2"][0], res["1"][1],
+                                     res["2"][1], sf, sf)
+        close(c_ok.item(), g["mm_a_cov12_numpy"], 1e-7)
+
+
+def _fit_dynamics(gp, g, name):
+    S, A, nxt = g[f"{name}_S"], g[f"{name}_A"], g[f"{name}_next"]
+    E, m = S.shape[1], A.shape[1]
+    dyn = gp.Dynamics(E, m)
+    for a in range(E):
+        # float64 ndarray / np.float64 inputs keep full precision in the setters, as in the reference
+        dyn.gpr_err[a].set_lambdas(np.asarray(g[f"{name}_lam"][a], dtype=np.float64))
+        dyn.gpr_err[a].set_sigma_f(np.float64(g[f"{name}_sf"][a]))
+        dyn.gpr_err[a].set_sigma_n(np.float64(g[f"{name}_sn"][a]))
+    dyn.append_train_data(S, A, nxt)
+    return dyn
+
+
+# ------------------------------------------------------------------------------------------------
+# Batched moment matching on a fitted bundle: diagonal (hot kernels) and full S (generic kernels)
+# ------------------------------------------------------------------------------------------------
+def test_bundle_moment_match_vs_oracle(gp):
+    from oracle import oracle as orc
+    g = golden("rollout")
+    name = "r3"                      # per-output ARD length-scales -> one lambda group per output
+    dyn = _fit_dynamics(gp, g, name)
+    S, A, nxt = g[f"{name}_S"], g[f"{name}_A"], g[f"{name}_next"]
+    X = np.concatenate([S, A], 1)
+    E, D = nxt.shape[1], X.shape[1]
+    lam, sf, sn = g[f"{name}_lam"], g[f"{name}_sf"], g[f"{name}_sn"]
+    fits = [orc.fit(X, nxt[:, a], lam[a], sf[a], float(np.float32(sn[a] ** 2)) ** 0.5) for a in range(E)]
+    rng = np.random.default_rng(1)
+    B = 37
+    U = rng.uniform(-0.5, 0.5, (B, D)); Sd = rng.uniform(1e-3, 5e-2, (B, D))
+    mean, var = dyn._bundle.moment_match(U, Sd, out_device=False)
+    for b in range(0, B, 6):
+        for a in range(E):
+            mo, vo, _ = orc.c_moment_match_diag(X, fits[a]["Ky_inv"], fits[a]["beta"], lam[a], sf[a], U[b], Sd[b])
+            close(mean[b, a], mo, 1e-8)
+            assert abs(var[b, a] - vo) <= RTOL * max(abs(vo), 1e-3 * sf[a] ** 2)
+    # full covariance through the same handle
+    Am = rng.normal(size=(3, D, D)) * 0.15
+    Sf = Am @ np.transpose(Am, (0, 2, 1)) + 0.01 * np.eye(D)
+    mean_f, var_f = dyn._bundle.moment_match(U[:3], Sf, out_device=False)
+    for b in range(3):
+        for a in range(E):
+            mo, beta, _ = orc.mean_prop(fits[a]["Ky_inv"], lam[a], U[b], Sf[b], X, nxt[:, a], sf[a])
+            vo = orc.variance_prop(fits[a]["Ky_inv"], lam[a], U[b], Sf[b], X, mo, beta, sf[a])
+            close(mean_f[b, a], mo, 1e-8)
+            assert abs(var_f[b, a] - vo) <= RTOL * max(abs(vo), 1e-3 * sf[a] ** 2)
+
+
+# ------------------------------------------------------------------------------------------------
+# Rollout + cost + gradient against the reference's own numbers (objective / autograd gradient)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["r1", "r2", "r3", "r4", "r5"])
+def test_rollout_cost_gradient_vs_reference(gp, name):
+    g = golden("rollout")
+    S, A = g[f"{name}_S"], g[f"{name}_A"]
+    E, m = S.shape[1], A.shape[1]
+    U = g[f"{name}_U"]; H = U.shape[0]
+    Rd = g[f"{name}_Rd"]; Rd = None if Rd.size == 0 else Rd
+    mpc = gp.RiskSensitiveMPC(float(g[f"{name}_gamma"]), H, E, m, g[f"{name}_Q"], g[f"{name}_R"], Rd)
+    for a in range(E):
+        mpc.dynamics.gpr_err[a].set_lambdas(np.asarray(g[f"{name}_lam"][a], dtype=np.float64))
+        mpc.dynamics.gpr_err[a].set_sigma_f(np.float64(g[f"{name}_sf"][a]))
+        mpc.dynamics.gpr_err[a].set_sigma_n(np.float64(g[f"{name}_sn"][a]))
+    mpc.dynamics.append_train_data(S, A, g[f"{name}_next"])
+    mpc.set_xref(g[f"{name}_xref"]); mpc.set_uref(g[f"{name}_uref"])
+    mpc.last_traj = g[f"{name}_last"]
+    mpc.curr_state = T(g[f"{name}_x0"])
+    c = mpc.objective(U.reshape(-1).copy())
+    grad = np.asarray(mpc.gradient(U.reshape(-1).copy()))
+    close(c, float(g[f"{name}_cost"]), RTOL)
+    assert grad.shape == (H, m)
+    norm_close(grad, g[f"{name}_grad"], RTOL)
+    # forward_propagate_torch: values, list structure and autograd through the device adjoint
+    u_t = T(U).requires_grad_(True)
+    means, covs = mpc.dynamics.forward_propagate_torch(H, T(g[f"{name}_x0"]), u_t)
+    assert len(means) == H + 1 and len(covs) == H + 1 and covs[1].shape == (E, E)
+    norm_close(torch.stack(means).detach().cpu().numpy(), g[f"{name}_means"], 1e-8)
+    ref_covs = g[f"{name}_covs"]
+    got_covs = torch.stack(covs).detach().cpu().numpy()
+    assert np.max(np.abs(got_covs - ref_covs)) <= RTOL * max(np.max(np.abs(ref_covs)), 1e-3)
+    cost_t = mpc.cost_torch(means, u_t, covs, mpc.x_ref, mpc.u_ref)
+    close(cost_t.item(), float(g[f"{name}_cost"]), RTOL)
+    cost_t.backward()
+    norm_close(u_t.grad.cpu().numpy(), g[f"{name}_grad"], RTOL)
+    # NumPy-interface rollout
+    m_np, c_np = mpc.dynamics.forward_propagate(H, g[f"{name}_x0"], U)
+    norm_close(m_np, g[f"{name}_means"], 1e-8)
+
+
+def test_shipped_experiment_config1(gp):
+    """BASELINE config 1 inputs (shipped data, n=400, sigma_n=1e-5, cond(Ky) ~ 2.6e6): values, gradient, NaN mask.
+    With this conditioning LU-inverse vs Cholesky-inverse differences are amplified, hence 1e-5."""
+    g = golden("shipped")
+    H = 6
+    mpc = gp.RiskSensitiveMPC(-1, H, 2, 2, 2 * np.identity(2), np.zeros((2, 2)), None)
+    for i in range(2):
+        mpc.dynamics.gpr_err[i].set_sigma_n(1e-5)
+        mpc.dynamics.gpr_err[i].set_lambdas([0.5, 0.5, 0.5, 0.5])
+        mpc.dynamics.gpr_err[i].set_sigma_f(1.)
+    mpc.dynamics.append_train_data(g["ship_S"], g["ship_A"], g["ship_next"])
+    assert np.array_equal(mpc.dynamics.gpr_err[0].get_lambdas(), g["ship_lam"][0])
+    mpc.set_xref(np.array([0., 0.])); mpc.set_uref(np.array([0., 0.]))
+    mpc.curr_state = T(g["ship_x0"])
+    for i in range(4):
+        U = g[f"ship_U{i}"]
+        c = mpc.objective(U.reshape(-1).copy())
+        ref = float(g[f"ship_cost{i}"])
+        assert np.isnan(c) == np.isnan(ref)
+        if not np.isnan(ref):
+            close(c, ref, 1e-5)
+            norm_close(np.asarray(mpc.gradient(U.reshape(-1).copy())), g[f"ship_grad{i}"], 1e-5)
+
+
+def test_cost_known_answers(gp):
+    """Deterministic KATs of the reference: src/test/test_mpc.py:15-57 and :245-274."""
+    mpc = gp.RiskSensitiveMPC(1, 1, 2, 2, np.array([[2, 0], [0, 2]]), np.array([[1, 1], [1, 1]]))
+    x = np.array([[1., 1.], [3., 3.]]); u = np.array([[2., 2.]])
+    sig = np.array([[[1., 2.], [3., 4.]], [[5., 6.], [7., 8.]]])
+    assert abs(mpc.cost(x, u, sig, np.array([.5, .5]), np.array([.6, .6])) - 13.532174074852094) < 1e-9
+    assert abs(mpc.cost_torch(T(x), T(u), T(sig), T([.5, .5]), T([.6, .6])).item() - 13.532174074852094) < 1e-9
+    H = 5
+    mpc = gp.RiskSensitiveMPC(-1, H, 1, 1, 2 * np.identity(1), np.array([[0]]), np.array([[0]]))
+    xt = T([5, 4, 3, 2, 1, 0]).reshape(H + 1, 1)
+    st = T([1 / 6, 1 / 7, 1 / 8, 1 / 9, 1 / 10, 1 / 11]).reshape(H + 1, 1, 1)
+    z = torch.zeros(1, device="cuda:0", dtype=torch.float64)
+    c = mpc.cost_torch(xt, torch.zeros((H, 1), device="cuda:0", dtype=torch.float64), st, z, z)
+    assert abs(c.item() - 158.2904623779527) < 1e-7
+
+
+# ------------------------------------------------------------------------------------------------
+# Batched path vs the C oracle at sizes the oracle finishes in seconds; properties at larger sizes
+# ------------------------------------------------------------------------------------------------
+def _synth(n, E, m, seed):
+    rng = np.random.default_rng(seed)
+    D = E + m
+    S = rng.uniform(-1, 1, (n, E)); A = rng.uniform(-1, 1, (n, m))
+    W = rng.normal(0, 0.3, (D, E))
+    nxt = 0.9 * S + 0.2 * np.tanh(np.concatenate([S, A], 1) @ W)
+    return S, A, nxt, rng
+
+
+def _synth_dynamics(gp, n, E, m, seed, lam=2.0, sn=0.1):
+    S, A, nxt, rng = _synth(n, E, m, seed)
+    dyn = gp.Dynamics(E, m)
+    for a in range(E):
+        dyn.gpr_err[a].set_lambdas(np.full(E + m, lam)); dyn.gpr_err[a].set_sigma_n(np.float64(sn))
+    dyn.append_train_data(S, A, nxt)
+    return dyn, S, A, nxt, rng
+
+
+def test_batched_rollouts_vs_c_oracle(gp):
+    from oracle import oracle as orc
+    n, E, m, H, B = 700, 4, 1, 6, 70           # n not a multiple of 64, B not a multiple of 32
+    dyn, S, A, nxt, rng = _synth_dynamics(gp, n, E, m, seed=2)
+    X = np.concatenate([S, A], 1)
+    lam = np.full((E, E + m), 2.0); sf = np.ones(E)
+    fits = [orc.fit(X, nxt[:, a], lam[a], 1.0, float(np.float32(0.1 ** 2)) ** 0.5) for a in range(E)]
+    x0 = rng.uniform(-0.5, 0.5, (B, E)); U = rng.uniform(-0.3, 0.3, (B, H, m))
+    gamma = np.where(np.arange(B) % 2 == 0, -1.0, 0.5)
+    Q = 2 * np.eye(E); R = 0.01 * np.eye(m)
+    br = gp.BatchedRollouts(dyn, Q, R)
+    cost, grad = br.cost_and_grad(x0, U, gamma, host_out=True)
+    for b in (0, 1, 33, 69):
+        c, gr, _, _ = orc.c_rollout_cost_grad(X, [f["Ky_inv"] for f in fits], [f["beta"] for f in fits], lam, sf,
+                                              x0[b], U[b], gamma[b], Q, R)
+        close(cost[b], c, RTOL)
+        norm_close(grad[b], gr, RTOL)
+    # property: a rollout's result does not depend on its batch neighbours or its position in the batch
+    perm = rng.permutation(B)
+    cost_p, grad_p = br.cost_and_grad(x0[perm], U[perm], gamma[perm], host_out=True)
+    close(cost_p, cost[perm], 1e-12)
+    norm_close(grad_p, grad[perm], 1e-11)
+    c1, g1 = br.cost_and_grad(x0[5:6], U[5:6], gamma[5:6], host_out=True)
+    close(c1, cost[5:6], 1e-12)
+
+
+def test_gradient_vs_finite_differences_mid_size(gp):
+    """n = 2048: too slow for the Python reference, fine for central differences of the device objective."""
+    n, E, m, H = 2048, 4, 1, 5
+    dyn, S, A, nxt, rng = _synth_dynamics(gp, n, E, m, seed=3)
+    br = gp.BatchedRollouts(dyn, 2 * np.eye(E), 0.01 * np.eye(m))
+    x0 = rng.uniform(-0.5, 0.5, E); U = rng.uniform(-0.3, 0.3, (1, H, m))
+    cost, grad = br.cost_and_grad(x0, U, -1.0, host_out=True)
+    h = 1e-5
+    Up = np.repeat(U, 2 * H * m, axis=0)
+    for k in range(H * m):
+        Up[2 * k].reshape(-1)[k] += h
+        Up[2 * k + 1].reshape(-1)[k] -= h
+    cp, _ = br.cost_and_grad(x0, Up, -1.0, host_out=True)
+    fd = (cp[0::2] - cp[1::2]) / (2 * h)
+    norm_close(grad.reshape(-1), fd, 1e-6)
+
+
+def test_determinism(gp):
+    dyn, S, A, nxt, rng = _synth_dynamics(gp, 512, 4, 1, seed=4)
+    br = gp.BatchedRollouts(dyn, 2 * np.eye(4), 0.01 * np.eye(1))
+    x0 = rng.uniform(-0.5, 0.5, 4); U = rng.uniform(-0.3, 0.3, (40, 4, 1))
+    a = br.cost_and_grad(x0, U, -1.0, host_out=True)
+    b = br.cost_and_grad(x0, U, -1.0, host_out=True)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_device_buffers_and_host_buffers_agree(gp):
+    dyn, S, A, nxt, rng = _synth_dynamics(gp, 300, 2, 2, seed=5)
+    br = gp.BatchedRollouts(dyn, 2 * np.eye(2), 0.01 * np.eye(2), R_delta=0.2 * np.eye(2))
+    x0 = rng.uniform(-0.5, 0.5, (9, 2)); U = rng.uniform(-0.3, 0.3, (9, 3, 2)); lu = rng.uniform(-0.1, 0.1, (9, 2))
+    ch, gh = br.cost_and_grad(x0, U, np.full(9, -1.0), last_u=lu, host_out=True)
+    cd, gd = br.cost_and_grad(T(x0), T(U), T(np.full(9, -1.0)), last_u=T(lu), host_out=False)
+    assert np.array_equal(ch, cd.cpu().numpy()) and np.array_equal(gh, gd.cpu().numpy())
+
+
+def test_hyper_setters_without_rebuild_affect_only_propagation(gp):
+    """src/dynamics.py:170-173: Ky_inv comes from the last build, lambdas/sigma_f are read at rollout time."""
+    from oracle import oracle as orc
+    n, E, m = 200, 2, 1
+    dyn, S, A, nxt, rng = _synth_dynamics(gp, n, E, m, seed=6)
+    X = np.concatenate([S, A], 1)
+    fits = [orc.fit(X, nxt[:, a], np.full(3, 2.0), 1.0, float(np.float32(0.1 ** 2)) ** 0.5) for a in range(E)]
+    new_lam = np.array([1.5, 2.5, 1.0])
+    dyn.gpr_err[1].set_lambdas(new_lam)           # no rebuild
+    x0 = np.array([0.1, -0.2]); U = np.array([[0.05], [-0.1]])
+    means, covs = dyn.forward_propagate(2, x0, U)
+    lam = np.stack([np.full(3, 2.0), new_lam])
+    mo, vo = orc.rollout(X, [f["Ky_inv"] for f in fits], nxt, lam, np.ones(2), x0, U)
+    norm_close(means, mo, 1e-8)
+    # rebuild of that member only
+    dyn.gpr_err[1].build_Ky_inv_mat()
+    fits[1] = orc.fit(X, nxt[:, 1], new_lam, 1.0, float(np.float32(0.1 ** 2)) ** 0.5)
+    means, covs = dyn.forward_propagate(2, x0, U)
+    mo, vo = orc.rollout(X, [f["Ky_inv"] for f in fits], nxt, lam, np.ones(2), x0, U)
+    norm_close(means, mo, 1e-8)
+
+
+def test_errors_are_reported(gp):
+    dyn = gp.Dynamics(2, 1)
+    with pytest.raises(RuntimeError):
+        dyn.forward_propagate(1, np.zeros(2), np.zeros((1, 1)))
+    gpr = gp.GaussianProcessRegression(2)
+    gpr.set_sigma_n(np.float64(1e-30))
+    X = np.zeros((3, 2))                       # three identical points and no noise: Ky is singular
+    with pytest.raises(gp.GpmpcError):
+        gpr.append_train_data(X, np.zeros(3))
