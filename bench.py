@@ -1,0 +1,324 @@
+"""Benchmark of the GP-MPC rollout hot path (BASELINE.json metric: moment-matched rollout cost+gradient
+evaluations per second, n=4096 training points, H=30).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2]): synthetic contracting dynamics, n=4096, E=4, m=1
+(D=5), H=30, B=1024 multi-start control sequences from one initial state, gamma=-1, lambda=2, sigma_f=1,
+sigma_n=0.1, Q=2I, R=0.01I.  One "step" = one cost+gradient evaluation of the whole batch (B rollouts x H
+horizon steps x E outputs).  With N GPUs the B rollouts are split into contiguous shards (GP replicated) and
+one NCCL all-gather returns cost and gradient: total work is fixed, so scaling is "strong".
+
+`--impl reference` times the reference's CPU algorithm (oracle/ref_port.py: the reference's own torch
+operation sequence incl. the n^3 mm+trace and autograd; the Python reference itself cannot travel to the GPU
+box) on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "gp_mpc_rollout_cost_grad_evals_per_sec"
+UNIT = "evals/s"
+# FP64-pipe instructions per pair for D=5 with 4 outputs sharing one exp ("pair kernel"):
+# 14 (q, q^2, sum) + 17 (exp) + 4 * 12 (w, T, N1[5], N2[5])
+OPS_PER_PAIR_GROUP4 = 14 + 17 + 4 * 12
+
+
+def synth(n, E, m, seed=0):
+    rng = np.random.default_rng(seed)
+    D = E + m
+    S = rng.uniform(-1, 1, (n, E)); A = rng.uniform(-1, 1, (n, m))
+    W = rng.normal(0, 0.3, (D, E))
+    nxt = 0.9 * S + 0.2 * np.tanh(np.concatenate([S, A], 1) @ W)
+    return S, A, nxt, rng
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = []
+        for i, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
+            if any(r[3 + i].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]),
+                "power_w_max": max(float(r[2]) for r in self.rows), "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_reference_sample(n, E, m, H_full, H_sample, seed, threads):
+    """Time the reference algorithm (torch port) on a bounded sample: full n, H_sample horizon steps, one
+    control sequence; cost is linear in H, so evals/s = 1 / (t * H_full / H_sample)."""
+    import torch
+    from oracle.ref_port import RefPortProblem
+    torch.set_num_threads(threads)
+    S, A, nxt, rng = synth(n, E, m, seed)
+    X = np.concatenate([S, A], 1)
+    t0 = time.perf_counter()
+    prob = RefPortProblem(X, nxt, np.full((E, E + m), 2.0), np.ones(E), np.full(E, 0.1), -1.0, 2 * np.eye(E),
+                          0.01 * np.eye(m))
+    t_fit = time.perf_counter() - t0
+    x0 = rng.uniform(-0.5, 0.5, E); U = rng.uniform(-0.3, 0.3, (H_sample, m))
+
+    def one():
+        t = time.perf_counter()
+        prob.cost_and_grad(x0, U)
+        return time.perf_counter() - t
+    return prob, one, t_fit
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, E, m, H = args.n, 4, 1, args.H
+    threads = os.cpu_count() or 1
+    Hs = 1
+    _, one, t_fit = cpu_reference_sample(n, E, m, H, Hs, 0, threads)
+    for _ in range(args.warmup):
+        one()
+    ts = [one() for _ in range(args.steps)]
+    t = float(np.mean(ts))
+    value = 1.0 / (t * H / Hs)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"config3: n={n} E=4 m=1 H={H} gamma=-1 multi-start rollouts", "n": n, "H": H,
+                   "B": args.B},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"torch-CPU port of the reference op sequence (oracle/ref_port.py): objective+autograd "
+                                   f"gradient of ONE control sequence at full n={n} for H={Hs} horizon step(s), "
+                                   f"extrapolated linearly to H={H}; fit ({t_fit:.1f} s) excluded"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import gpmpc_b200 as gp
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    n, E, m, H, B = args.n, 4, 1, args.H, args.B
+    D = E + m
+    S, A, nxt, rng = synth(n, E, m, 0)
+    dyn = gp.Dynamics(E, m)
+    for a in range(E):
+        dyn.gpr_err[a].set_lambdas(np.full(D, 2.0)); dyn.gpr_err[a].set_sigma_n(np.float64(0.1))
+    t0 = time.perf_counter()
+    dyn.append_train_data(S, A, nxt)
+    dyn._bundle.synchronize()
+    t_fit = time.perf_counter() - t0
+    Q = 2 * np.eye(E); R = 0.01 * np.eye(m)
+    br = gp.BatchedRollouts(dyn, Q, R)
+    bundle = dyn._bundle
+    dev = torch.device("cuda", local)
+
+    x0 = rng.uniform(-0.5, 0.5, E)
+    U_all = rng.uniform(-0.3, 0.3, (B, H, m))
+    lo, hi = gp.shard_range(B, world, rank)
+    Bl = hi - lo
+    per = (B + world - 1) // world
+    # host (pinned) and device copies of this rank's shard
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()   # noqa: E731
+    x0_h = pin(np.broadcast_to(x0, (Bl, E)).copy()); U_h = pin(U_all[lo:hi]); g_h = pin(np.full(Bl, -1.0))
+    x0_d, U_d, g_d = x0_h.to(dev), U_h.to(dev), g_h.to(dev)
+    cost_h = torch.empty(Bl, dtype=torch.float64).pin_memory()
+    grad_h = torch.empty((Bl, H, m), dtype=torch.float64).pin_memory()
+    packed = torch.zeros((per, 1 + H * m), dtype=torch.float64, device=dev)
+    gathered = torch.empty((world * per, 1 + H * m), dtype=torch.float64, device=dev)
+    full_h = torch.empty((world * per, 1 + H * m), dtype=torch.float64).pin_memory()
+
+    def step_device():
+        cost, grad, _, _ = bundle.cost_grad(x0_d, U_d, g_d, Q, R, want_grad=True, host_out=False)
+        if world > 1:
+            packed[:Bl, 0] = cost
+            packed[:Bl, 1:] = grad.reshape(Bl, H * m)
+            dist.all_gather_into_tensor(gathered, packed)
+        return cost, grad
+
+    def step_e2e():
+        # public API with HOST buffers: H2D of the inputs and D2H of cost/grad happen inside the C-ABI call
+        cost, grad, _, _ = bundle.cost_grad(x0_h.numpy(), U_h.numpy(), g_h.numpy(), Q, R, want_grad=True, host_out=True)
+        if world > 1:
+            packed[:Bl, 0] = torch.from_numpy(cost).to(dev, non_blocking=True)
+            packed[:Bl, 1:] = torch.from_numpy(grad.reshape(Bl, H * m)).to(dev, non_blocking=True)
+            dist.all_gather_into_tensor(gathered, packed)
+            full_h.copy_(gathered, non_blocking=True)
+            torch.cuda.synchronize()
+        return cost, grad
+
+    def timed(fn, K, sample_clocks=False):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = None
+        if sample_clocks and rank == 0:
+            sampler = ClockSampler(local); sampler.start()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        l0 = bundle.launch_count()
+        e0.record()
+        for _ in range(K):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        launches = bundle.launch_count() - l0
+        if sampler is not None:
+            sampler.stop_flag.set(); sampler.join(2)
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, (sampler.summary() if sampler is not None else None)
+
+    for _ in range(args.warmup):
+        step_device()
+    ms, launches, clocks = timed(step_device, args.steps, sample_clocks=True)
+    value = B * args.steps / (ms * 1e-3)
+
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+    e2e_value = B * args.steps / (ms_e2e * 1e-3)
+
+    # dominant kernel: the pair-sum kernel, timed with CUDA events on its own stream inside the library
+    bundle.pair_kernel_timing()              # arms the timers
+    step_device(); torch.cuda.synchronize()
+    pair_ms, pair_evals = bundle.pair_kernel_timing()     # summed over the H launches of one evaluation
+    fma_tflops, exp_gops = bundle.measure_fp64_peak()
+    pairs = pair_evals / E                                 # (rollout, pair) evaluations, 4 outputs each
+    achieved_tflops = pairs * OPS_PER_PAIR_GROUP4 * 2.0 / (pair_ms * 1e-3) / 1e12
+    bytes_algo = H * E * (n * (n + 1) / 2) * 8.0           # Wt upper triangle once per step and output
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    roofline = {
+        "bound": "fp64_pipe", "kernel": "mm_pairs_batch<5,4,grad>", "achieved": achieved_tflops, "peak": fma_tflops,
+        "unit": "TFLOP/s", "frac": achieved_tflops / fma_tflops if fma_tflops else None, "traffic": None,
+        "note": "FP64-pipe instructions (x2 flop) per launch / CUDA-event duration of the pair kernel; peak = DFMA rate "
+                "measured live by gpmpc_measure_fp64_peak (MEASURED_PEAKS.json has no fp64 figure); this kernel is "
+                "neither HBM- nor tensor-bound (see DESIGN.md)",
+        "pair_kernel_ms_per_eval": pair_ms, "pair_kernel_share_of_step": pair_ms / (ms / args.steps),
+        "launches_per_eval": H, "fp64_exp_gops_measured": exp_gops,
+        "hbm": {"achieved": bytes_algo / (pair_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": bytes_algo / (pair_ms * 1e-3) / 1e9 / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
+    }
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"config3: n={n} E=4 m=1 H={H} gamma=-1, B={B} multi-start control sequences",
+                   "n": n, "H": H, "B": B, "sharding": f"rollouts/{world}", "l2": "per-step Wt working set "
+                   f"{E * n * n * 8 / 2 / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2)", "fit_s": t_fit},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(B * (E + H * m + 1) * 8), "d2h_bytes_per_step": int(B * (1 + H * m) * 8)},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        _, one, tf = cpu_reference_sample(n, E, m, H, 1, 0, threads)
+        one()
+        t = min(one(), one())
+        line["cpu_baseline"] = {
+            "value": 1.0 / (t * H), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"oracle/ref_port.py (reference op sequence, torch CPU fp64): objective+gradient of ONE control "
+                      f"sequence at n={n}, H=1 ({t:.2f} s), extrapolated linearly to H={H}"}
+        try:
+            from oracle import oracle as orc
+            orc.c_set_threads(threads)
+            X = np.concatenate([S, A], 1)
+            sub = 1024                                      # O(n^2) C restatement on an n=1024 sub-sample
+            lam = np.full((E, D), 2.0)
+            fits = [orc.fit(X[:sub], nxt[:sub, a], lam[a], 1.0, 0.1) for a in range(E)]
+            t1 = time.perf_counter()
+            orc.c_rollout_cost_grad(X[:sub], [f["Ky_inv"] for f in fits], [f["beta"] for f in fits], lam, np.ones(E),
+                                    x0, U_all[0, :2], -1.0, Q, R)
+            tc = (time.perf_counter() - t1) * (n / sub) ** 2 * (H / 2)
+            line["cpu_baseline_c_oracle"] = {"value": 1.0 / tc, "unit": UNIT, "cores": threads, "kind": "port",
+                                             "sample": f"oracle/gpmpc_oracle.c (O(n^2) pair sums, OpenMP): n={sub}, H=2 "
+                                                       f"scaled by (n/{sub})^2 * H/2"}
+        except Exception as ex:                             # the C oracle is optional here
+            line["cpu_baseline_c_oracle"] = {"error": str(ex)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=4096)
+    ap.add_argument("--H", type=int, default=30)
+    ap.add_argument("--B", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -91,7 +91,7 @@ class Dynamics(object):
 
     def _fit_all(self):
         if self._bundle is None:
-            self._bundle = GPBundle(self.state_dim + self.action_dim, self.state_dim, 0)
+            self._bundle = GPBundle(self.state_dim + self.action_dim, self.state_dim, self.device.index or 0)
         lam, sf, nv = self._collect_hypers()
         self._bundle.fit(self._X, self._Y, lam, sf, nv)
         self._prop_key = tuple(g._hyper_key() for g in self.gpr_err)

@@ -23,6 +23,12 @@ from . import _lib
 from .backend import GPBundle, F64
 
 
+def current_device():
+    if torch.cuda.is_available():
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
 def noise_variance(sigma_n: float) -> float:
     """sigma_n^2 as the reference adds it to the diagonal: through an fp32 eye (`src/gpr.py:170`)."""
     return float(np.float32(float(sigma_n) ** 2))
@@ -32,7 +38,8 @@ class GaussianProcessRegression(object):
     """Exact GP regression with the squared-exponential ARD kernel (lambdas are squared length-scales)."""
 
     def __init__(self, x_dim, nominal_model=None, _owner=None, _index=0):
-        self.device = torch.device("cuda:0" if torch.cuda.is_available() else "cpu")
+        # the reference hard-codes cuda:0 (`src/gpr.py:22`); one process per GPU uses its current device
+        self.device = current_device()
         self.x_dim = x_dim
         self.num_train = 0
         self._X = None                       # (n, x_dim) device tensor (standalone mode)
@@ -122,7 +129,7 @@ class GaussianProcessRegression(object):
             self._owner._refit_member(self._index, lam, sf, nv)
             return
         if self._bundle is None:
-            self._bundle = GPBundle(self.x_dim, 1, 0)
+            self._bundle = GPBundle(self.x_dim, 1, self.device.index or 0)
         self._bundle.fit(self._X, self._y, lam[None, :], [sf], [nv])
 
     # ---- materialised matrices ------------------------------------------------------------------

@@ -34,7 +34,7 @@ class RiskSensitiveMPC:
         self.R_delta = R_delta
         self.dynamics = Dynamics(self.state_dim, self.input_dim, nominal_models=None)
 
-        self.device = torch.device("cuda:0" if torch.cuda.is_available() else "cpu")
+        self.device = self.dynamics.device
         self.Q_tor = torch.tensor(self.Q, device=self.device).type(F64)
         self.R_tor = torch.tensor(self.R, device=self.device).type(F64)
         self.R_delta_tor = None if R_delta is None else torch.tensor(self.R_delta, device=self.device).type(F64)

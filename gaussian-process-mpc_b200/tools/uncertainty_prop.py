@@ -20,7 +20,9 @@ from .._lib import check
 
 
 def _dev(t):
-    return t.device if isinstance(t, torch.Tensor) and t.is_cuda else torch.device("cuda:0")
+    if isinstance(t, torch.Tensor) and t.is_cuda:
+        return t.device
+    return torch.device("cuda", torch.cuda.current_device())
 
 
 def _scalar(x):

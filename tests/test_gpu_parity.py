@@ -58,9 +58,13 @@ def test_gpr_matrices_and_posterior(gp, name):
     lam = [float(v) for v in g[f"gpr_{name}_lam"]]
     gpr = gp.GaussianProcessRegression(X.shape[1])
     gpr.set_lambdas(lam); gpr.set_sigma_f(float(g[f"gpr_{name}_sf"])); gpr.set_sigma_n(float(g[f"gpr_{name}_sn"]))
-    # the setters must round through fp32 exactly like the reference's (src/gpr.py:59,72,85)
-    assert np.array_equal(gpr.get_lambdas(), g[f"gpr_{name}_lam_eff"])
-    assert gpr.get_sigma_f() == float(g[f"gpr_{name}_sf_eff"])
+    # the setters round Python floats through fp32 like the reference's (src/gpr.py:59,72,85); the golden values
+    # were produced on the CPU, the GPU's fp32 log may differ by an ulp
+    np.testing.assert_allclose(gpr.get_lambdas(), g[f"gpr_{name}_lam_eff"], rtol=3e-7)
+    np.testing.assert_allclose(gpr.get_sigma_f(), float(g[f"gpr_{name}_sf_eff"]), rtol=3e-7)
+    # for the matrix comparison use the reference's effective values exactly (float64 inputs are not rounded)
+    gpr.set_lambdas(np.asarray(g[f"gpr_{name}_lam_eff"], dtype=np.float64))
+    gpr.set_sigma_f(np.float64(g[f"gpr_{name}_sf_eff"])); gpr.set_sigma_n(np.float64(g[f"gpr_{name}_sn_eff"]))
     if name == "c":
         gpr.append_train_data(X[0], float(y[0]))
     else:
@@ -219,11 +223,17 @@ def test_shipped_experiment_config1(gp):
     H = 6
     mpc = gp.RiskSensitiveMPC(-1, H, 2, 2, 2 * np.identity(2), np.zeros((2, 2)), None)
     for i in range(2):
+        # as in src/experiments/pretrain_uncertainty.py:98-101 (Python floats -> fp32 rounding) ...
         mpc.dynamics.gpr_err[i].set_sigma_n(1e-5)
         mpc.dynamics.gpr_err[i].set_lambdas([0.5, 0.5, 0.5, 0.5])
         mpc.dynamics.gpr_err[i].set_sigma_f(1.)
+        np.testing.assert_allclose(mpc.dynamics.gpr_err[i].get_lambdas(), g["ship_lam"][i], rtol=3e-7)
+        np.testing.assert_allclose(mpc.dynamics.gpr_err[i].get_sigma_n(), g["ship_sn"][i], rtol=3e-6)  # fp32 ulp of log(1e-5)
+        # ... then pin the exact effective values the CPU reference used (GPU fp32 log may differ by an ulp)
+        mpc.dynamics.gpr_err[i].set_sigma_n(np.float64(g["ship_sn"][i]))
+        mpc.dynamics.gpr_err[i].set_lambdas(np.asarray(g["ship_lam"][i], dtype=np.float64))
+        mpc.dynamics.gpr_err[i].set_sigma_f(np.float64(g["ship_sf"][i]))
     mpc.dynamics.append_train_data(g["ship_S"], g["ship_A"], g["ship_next"])
-    assert np.array_equal(mpc.dynamics.gpr_err[0].get_lambdas(), g["ship_lam"][0])
     mpc.set_xref(np.array([0., 0.])); mpc.set_uref(np.array([0., 0.]))
     mpc.curr_state = T(g["ship_x0"])
     for i in range(4):
@@ -299,21 +309,31 @@ def test_batched_rollouts_vs_c_oracle(gp):
     close(c1, cost[5:6], 1e-12)
 
 
-def test_gradient_vs_finite_differences_mid_size(gp):
-    """n = 2048: too slow for the Python reference, fine for central differences of the device objective."""
-    n, E, m, H = 2048, 4, 1, 5
+def test_mid_size_vs_c_oracle_and_finite_differences(gp):
+    """n = 2048: too slow for the Python reference; the C oracle (pinned to the reference's autograd at small n)
+    checks cost and gradient, central differences of the device objective cross-check the adjoint."""
+    from oracle import oracle as orc
+    n, E, m, H = 2048, 4, 1, 3
     dyn, S, A, nxt, rng = _synth_dynamics(gp, n, E, m, seed=3)
-    br = gp.BatchedRollouts(dyn, 2 * np.eye(E), 0.01 * np.eye(m))
+    Q = 2 * np.eye(E); R = 0.01 * np.eye(m)
+    br = gp.BatchedRollouts(dyn, Q, R)
     x0 = rng.uniform(-0.5, 0.5, E); U = rng.uniform(-0.3, 0.3, (1, H, m))
     cost, grad = br.cost_and_grad(x0, U, -1.0, host_out=True)
-    h = 1e-5
+    X = np.concatenate([S, A], 1)
+    lam = np.full((E, E + m), 2.0)
+    fits = [orc.fit(X, nxt[:, a], lam[a], 1.0, float(np.float32(0.1 ** 2)) ** 0.5) for a in range(E)]
+    c, gr, _, _ = orc.c_rollout_cost_grad(X, [f["Ky_inv"] for f in fits], [f["beta"] for f in fits], lam, np.ones(E),
+                                          x0, U[0], -1.0, Q, R)
+    close(cost[0], c, RTOL)
+    norm_close(grad[0], gr, RTOL)
+    h = 1e-4
     Up = np.repeat(U, 2 * H * m, axis=0)
     for k in range(H * m):
         Up[2 * k].reshape(-1)[k] += h
         Up[2 * k + 1].reshape(-1)[k] -= h
     cp, _ = br.cost_and_grad(x0, Up, -1.0, host_out=True)
     fd = (cp[0::2] - cp[1::2]) / (2 * h)
-    norm_close(grad.reshape(-1), fd, 1e-6)
+    norm_close(grad.reshape(-1), fd, 2e-4)      # limited by finite-difference noise, not by the adjoint
 
 
 def test_determinism(gp):
