@@ -33,8 +33,8 @@ if ROOT not in sys.path:
 METRIC = "gp_mpc_rollout_cost_grad_evals_per_sec"
 UNIT = "evals/s"
 # FP64-pipe instructions per pair for D=5 with 4 outputs sharing one exp ("pair kernel"):
-# 14 (q, q^2, sum) + 17 (exp) + 4 * 12 (w, T, N1[5], N2[5])
-OPS_PER_PAIR_GROUP4 = 14 + 17 + 4 * 12
+# 14 (q, q^2, sum) + 11 (table exp) + 4 * 12 (w, T, N1[5], N2[5])
+OPS_PER_PAIR_GROUP4 = 14 + 11 + 4 * 12
 
 
 def synth(n, E, m, seed=0):

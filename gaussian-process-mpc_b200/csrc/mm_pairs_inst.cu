@@ -11,7 +11,7 @@ namespace gpmpc {
 template <int D, int EG, bool GRAD>
 static cudaError_t launch_one(const PairArgs &a, dim3 grid, cudaStream_t st)
 {
-    const size_t smem = 2 * pair_stage_doubles<D, EG>() * sizeof(double);
+    const size_t smem = pair_smem_bytes<D, EG>();
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(mm_pairs_batch<D, EG, GRAD>,

@@ -94,7 +94,9 @@ __global__ void __launch_bounds__(MEAN_THREADS) mean_sums_kernel(const MeanArgs 
 {
     __shared__ double xs[64 * D];
     __shared__ double bs[kGroupMax][64];
+    __shared__ double etab[16];
     const int tid = threadIdx.x;
+    if (tid < 16) etab[tid] = kExp2Tab[tid];
     const int b = blockIdx.x * MEAN_THREADS + tid;
     const bool active = b < a.d.B;
     const int jp = blockIdx.y;
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(MEAN_THREADS) mean_sums_kernel(const MeanArgs 
             double p[D], pp[D], S = 0.0;
 #pragma unroll
             for (int k = 0; k < D; ++k) { p[k] = fma(-cm[k], xs[j * D + k], cmu[k]); pp[k] = p[k] * p[k]; S += pp[k]; }
-            const double l = exp_neg(S);
+            const double l = exp_neg(S, etab);
 #pragma unroll
             for (int g = 0; g < kGroupMax; ++g) {
                 if (g < a.EG) {
@@ -419,16 +421,22 @@ static StepDims make_dims(gpmpc_ctx *h, int B)
     return d;
 }
 
-// number of pair-space partitions: fill the machine with 2 blocks per SM
-static int pair_partitions(gpmpc_ctx *h, int B, long long total_tiles)
+// Launch geometry of the pair kernel: one wave of 2 CTAs per SM (register limited), split over the rollout
+// chunks; each chunk's tile list is cut into ~kItemsPerCta work items per CTA that are handed out dynamically.
+constexpr int kItemsPerCta = 16;
+static void pair_geometry(gpmpc_ctx *h, int B, long long total_tiles, int &ctas_per_chunk, int &n_items)
 {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     const int chunks = (B + PAIR_THREADS - 1) / PAIR_THREADS;
-    long long P = (2LL * sms + chunks - 1) / chunks;
-    if (P > total_tiles) P = total_tiles;
-    if (P < 1) P = 1;
-    return (int)P;
+    long long c = (2LL * sms) / chunks;          // floor: never spill into a second wave
+    if (c < 1) c = 1;
+    if (c > total_tiles) c = total_tiles;
+    // few rollout chunks -> many CTAs per chunk already; keep the partial-sum buffer (and the finalize loop) short
+    long long it = c * (chunks >= 4 ? kItemsPerCta : 2);
+    if (it > total_tiles) it = total_tiles;
+    ctas_per_chunk = (int)c;
+    n_items = (int)it;
 }
 
 template <int D> static void launch_mean(const MeanArgs &ma, dim3 grid, cudaStream_t st)
@@ -447,7 +455,7 @@ static void launch_mean_d(int D, const MeanArgs &ma, dim3 grid, cudaStream_t st)
 
 // One moment-matching step for all rollouts: us/cst must have been prepared.  Writes mean/var of step t
 // (slot t of mu/var) and, if want_grad, the tape entry t-1.
-static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int P, long long total_tiles, bool want_grad,
+static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int ctas, int P, long long total_tiles, bool want_grad,
                     double *us, double *cst, double *mu, double *var, double *tape)
 {
     const size_t mat = (size_t)h->ld * h->ld;
@@ -467,9 +475,12 @@ static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int P, long long tot
         pa.X = h->X.as<double>();
         pa.cst = cst + (size_t)g * 4 * d.D * d.Bpad;
         pa.part = h->part.as<double>();
-        pa.ld = h->ld; pa.ntile = h->ld / PT; pa.B = d.B; pa.Bpad = d.Bpad; pa.E = d.E; pa.P = P;
-        pa.total_tiles = total_tiles;
-        dim3 grid(P, (d.B + PAIR_THREADS - 1) / PAIR_THREADS);
+        pa.ld = h->ld; pa.ntile = h->ld / PT; pa.B = d.B; pa.Bpad = d.Bpad; pa.E = d.E; pa.n_items = P;
+        pa.total_tiles = (int)total_tiles; pa.chunks = (d.B + PAIR_THREADS - 1) / PAIR_THREADS;
+        const int chunks = (d.B + PAIR_THREADS - 1) / PAIR_THREADS;
+        pa.counters = h->tickets.as<int>();
+        GP_CUDA(h, cudaMemsetAsync(pa.counters, 0, chunks * sizeof(int), h->stream));
+        dim3 grid(ctas * chunks);
         cudaError_t e = pair_launcher(d.D)(grp.count, want_grad, pa, grid, h->stream);
         h->launches++;
         if (e != cudaSuccess) return fail(h, GPMPC_ERR_CUDA, std::string("mm_pairs_batch: ") + cudaGetErrorString(e));
@@ -489,7 +500,7 @@ static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int P, long long tot
 }
 
 struct RolloutWork {
-    StepDims d; int P; long long total_tiles;
+    StepDims d; int P; int ctas; long long total_tiles;
     double *x0int, *Uint, *us, *cst, *lamg;
 };
 
@@ -499,7 +510,8 @@ static int reserve_rollout(gpmpc_ctx *h, int B, int H, RolloutWork &w)
     const StepDims &d = w.d;
     const long long nt = h->ld / PT;
     w.total_tiles = nt * (nt + 1) / 2;
-    w.P = pair_partitions(h, B, w.total_tiles);
+    pair_geometry(h, B, w.total_tiles, w.ctas, w.P);
+    GP_CUDA(h, h->tickets.reserve(((B + PAIR_THREADS - 1) / PAIR_THREADS) * sizeof(int)));
     const size_t Bp = d.Bpad;
     const int Hs = H > 0 ? H : 1;
     GP_CUDA(h, h->mu.reserve((size_t)(H + 1) * d.E * Bp * sizeof(double)));
@@ -553,8 +565,8 @@ static int forward(gpmpc_ctx *h, int B, int H, const double *x0_dev, const doubl
         prep_step_kernel<<<dim3((B + 127) / 128, d.G), blk, 0, h->stream>>>(d, t, h->mu.as<double>(), h->var.as<double>(),
                                                                              w.Uint, w.lamg, w.us, w.cst, act_var);
         GP_LAUNCH_CHECK(h);
-        rc = run_step(h, d, t, w.P, w.total_tiles, want_grad, w.us, w.cst, h->mu.as<double>(), h->var.as<double>(),
-                      h->tape.as<double>());
+        rc = run_step(h, d, t, w.ctas, w.P, w.total_tiles, want_grad, w.us, w.cst, h->mu.as<double>(),
+                      h->var.as<double>(), h->tape.as<double>());
         if (rc) return rc;
         if (h->time_pairs) {
             GP_CUDA(h, cudaEventSynchronize(h->ev1));
@@ -821,8 +833,8 @@ extern "C" int gpmpc_moment_match_diag_internal(gpmpc_handle h, int B, const dou
     GP_LAUNCH_CHECK(h);
     h->last_pair_ms = 0.0; h->last_pair_evals = 0;
     // results land in slot t = 1 of mu / var
-    if ((rc = run_step(h, d, 1, w.P, w.total_tiles, false, w.us, w.cst, h->mu.as<double>(), h->var.as<double>(),
-                       h->tape.as<double>()))) return rc;
+    if ((rc = run_step(h, d, 1, w.ctas, w.P, w.total_tiles, false, w.us, w.cst, h->mu.as<double>(),
+                       h->var.as<double>(), h->tape.as<double>()))) return rc;
     if (h->time_pairs) {
         GP_CUDA(h, cudaEventSynchronize(h->ev1));
         float ms = 0.f; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
