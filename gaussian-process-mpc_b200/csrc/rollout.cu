@@ -160,23 +160,36 @@ __global__ void __launch_bounds__(MEAN_THREADS) mean_sums_kernel(const MeanArgs 
 // applies the determinant prefactors and writes mean/var of step t plus the tape entry.
 //   tape[((t-1)*E + a) * (2+4D) + e][Bpad]:  e = 0 mean, 1 var, 2.. dm/du, dm/ds, dv/du, dv/ds
 // ---------------------------------------------------------------------------------------------
-__global__ void finalize_step_kernel(StepDims d, int t, int P, const double *__restrict__ part,
-                                     const double *__restrict__ mpart, const double *__restrict__ us,
-                                     const double *__restrict__ hyp, double *__restrict__ mu,
-                                     double *__restrict__ var, double *__restrict__ tape, int want_grad)
+constexpr int FIN_WARPS = 4;
+__global__ void __launch_bounds__(32 * FIN_WARPS)
+finalize_step_kernel(StepDims d, int t, int P, const double *__restrict__ part,
+                     const double *__restrict__ mpart, const double *__restrict__ us,
+                     const double *__restrict__ hyp, double *__restrict__ mu,
+                     double *__restrict__ var, double *__restrict__ tape, int want_grad)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    // block = 32 rollouts (lanes) x FIN_WARPS slices of the partial-sum list; fixed summation order
+    __shared__ double red[FIN_WARPS][2 * (1 + 2 * kMaxD)][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int b = blockIdx.x * 32 + lane;
     const int a = blockIdx.y;
-    if (b >= d.B) return;
     const int D = d.D, NA = 1 + 2 * D;
+    const bool live = b < d.B;
+    for (int e = 0; e < NA; ++e) {
+        double s = 0.0, sm = 0.0;
+        if (live) {
+            for (int p = wid; p < P; p += FIN_WARPS) s += part[(((size_t)p * d.E + a) * NA + e) * d.Bpad + b];
+            for (int p = wid; p < MEAN_JP; p += FIN_WARPS) sm += mpart[(((size_t)p * d.E + a) * NA + e) * d.Bpad + b];
+        }
+        red[wid][e][lane] = s;
+        red[wid][NA + e][lane] = sm;
+    }
+    __syncthreads();
+    if (wid != 0 || !live) return;
     double accN[1 + 2 * kMaxD], accM[1 + 2 * kMaxD];
     for (int e = 0; e < NA; ++e) {
-        double s = 0.0;
-        for (int p = 0; p < P; ++p) s += part[(((size_t)p * d.E + a) * NA + e) * d.Bpad + b];
-        accN[e] = s;
-        double sm = 0.0;
-        for (int p = 0; p < MEAN_JP; ++p) sm += mpart[(((size_t)p * d.E + a) * NA + e) * d.Bpad + b];
-        accM[e] = sm;
+        double s = 0.0, sm = 0.0;
+        for (int w = 0; w < FIN_WARPS; ++w) { s += red[w][e][lane]; sm += red[w][NA + e][lane]; }
+        accN[e] = s; accM[e] = sm;
     }
     const double *lam = hyp + (size_t)a * D;
     const double sf = hyp[(size_t)d.E * D + a];
@@ -491,8 +504,8 @@ static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int ctas, int P, lon
         GP_LAUNCH_CHECK(h);
     }
     if (h->time_pairs) cudaEventRecord(h->ev1, h->stream);
-    dim3 fgrid((d.B + 127) / 128, d.E);
-    finalize_step_kernel<<<fgrid, 128, 0, h->stream>>>(d, t, P, h->part.as<double>(), h->mpart.as<double>(), us,
+    dim3 fgrid((d.B + 31) / 32, d.E);
+    finalize_step_kernel<<<fgrid, 32 * FIN_WARPS, 0, h->stream>>>(d, t, P, h->part.as<double>(), h->mpart.as<double>(), us,
                                                        h->hyp.as<double>(), mu, var, tape, want_grad ? 1 : 0);
     GP_LAUNCH_CHECK(h);
     (void)NA;
