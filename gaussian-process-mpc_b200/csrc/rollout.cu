@@ -15,10 +15,12 @@
 // Internal layouts put the rollout index last (coalesced across the lanes that own rollouts).
 #include "common.cuh"
 #include "mm_pairs.cuh"
+#include "mm_pairs_single.cuh"
 
 namespace gpmpc {
 
-#define DECL_LAUNCH(D) cudaError_t launch_pairs_batch_D##D(int, bool, const PairArgs &, dim3, cudaStream_t);
+#define DECL_LAUNCH(D) cudaError_t launch_pairs_batch_D##D(int, bool, const PairArgs &, dim3, cudaStream_t); \
+                       cudaError_t launch_pairs_single_D##D(int, bool, const PairArgs &, dim3, cudaStream_t);
 DECL_LAUNCH(2) DECL_LAUNCH(3) DECL_LAUNCH(4) DECL_LAUNCH(5) DECL_LAUNCH(6) DECL_LAUNCH(7) DECL_LAUNCH(8)
 #undef DECL_LAUNCH
 
@@ -34,6 +36,19 @@ static pair_launch_fn pair_launcher(int D)
     return nullptr;
 }
 
+static pair_launch_fn single_launcher(int D)
+{
+    switch (D) {
+        case 2: return launch_pairs_single_D2; case 3: return launch_pairs_single_D3;
+        case 4: return launch_pairs_single_D4; case 5: return launch_pairs_single_D5;
+        case 6: return launch_pairs_single_D6; case 7: return launch_pairs_single_D7;
+        case 8: return launch_pairs_single_D8;
+    }
+    return nullptr;
+}
+
+// below this many rollouts the lanes<->pairs kernel (one rollout per CTA column) replaces the lanes<->rollouts one
+constexpr int kSingleMaxB = 64;
 constexpr int MEAN_JP = 16;          // partitions of the training set in the mean kernel
 constexpr int MEAN_THREADS = 128;
 
@@ -155,48 +170,85 @@ __global__ void __launch_bounds__(MEAN_THREADS) mean_sums_kernel(const MeanArgs 
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// finalize_step: one thread per (rollout, output).  Sums the partials in a fixed order (deterministic),
-// applies the determinant prefactors and writes mean/var of step t plus the tape entry.
-//   tape[((t-1)*E + a) * (2+4D) + e][Bpad]:  e = 0 mean, 1 var, 2.. dm/du, dm/ds, dv/du, dv/ds
-// ---------------------------------------------------------------------------------------------
-constexpr int FIN_WARPS = 4;
-__global__ void __launch_bounds__(32 * FIN_WARPS)
-finalize_step_kernel(StepDims d, int t, int P, const double *__restrict__ part,
-                     const double *__restrict__ mpart, const double *__restrict__ us,
-                     const double *__restrict__ hyp, double *__restrict__ mu,
-                     double *__restrict__ var, double *__restrict__ tape, int want_grad)
+// Few rollouts: lanes <-> training points.  grid (MEAN_JP, B); fixed-order block reduction.
+template <int D>
+__global__ void __launch_bounds__(256) mean_single_kernel(const MeanArgs a)
 {
-    // block = 32 rollouts (lanes) x FIN_WARPS slices of the partial-sum list; fixed summation order
-    __shared__ double red[FIN_WARPS][2 * (1 + 2 * kMaxD)][32];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int b = blockIdx.x * 32 + lane;
-    const int a = blockIdx.y;
-    const int D = d.D, NA = 1 + 2 * D;
-    const bool live = b < d.B;
-    for (int e = 0; e < NA; ++e) {
-        double s = 0.0, sm = 0.0;
-        if (live) {
-            for (int p = wid; p < P; p += FIN_WARPS) s += part[(((size_t)p * d.E + a) * NA + e) * d.Bpad + b];
-            for (int p = wid; p < MEAN_JP; p += FIN_WARPS) sm += mpart[(((size_t)p * d.E + a) * NA + e) * d.Bpad + b];
+    constexpr int NA = 1 + 2 * D;
+    __shared__ double etab[16];
+    __shared__ double cs[2 * D];
+    __shared__ double red[8][kGroupMax * NA];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int jp = blockIdx.x, b = blockIdx.y;
+    if (tid < 16) etab[tid] = kExp2Tab[tid];
+    if (tid < 2 * D) cs[tid] = a.cst[(size_t)(2 * D + tid) * a.d.Bpad + b];      // cm_k, cm_k u_k
+    __syncthreads();
+    const int per = (a.d.ld / 64 + MEAN_JP - 1) / MEAN_JP * 64;
+    const int j_begin = jp * per;
+    const int j_end = min(a.d.ld, j_begin + per);
+    double m0[kGroupMax], m1[kGroupMax][D], m2[kGroupMax][D];
+#pragma unroll
+    for (int g = 0; g < kGroupMax; ++g) {
+        m0[g] = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) m1[g][k] = m2[g][k] = 0.0;
+    }
+    for (int j = j_begin + tid; j < j_end; j += 256) {
+        double p[D], pp[D], S = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) { p[k] = fma(-cs[k], a.X[(size_t)j * D + k], cs[D + k]); pp[k] = p[k] * p[k]; S += pp[k]; }
+        const double l = exp_neg(S, etab);
+#pragma unroll
+        for (int g = 0; g < kGroupMax; ++g) {
+            if (g < a.EG) {
+                const double w = a.beta[g][j] * l;
+                m0[g] += w;
+#pragma unroll
+                for (int k = 0; k < D; ++k) { m1[g][k] = fma(w, p[k], m1[g][k]); m2[g][k] = fma(w, pp[k], m2[g][k]); }
+            }
         }
-        red[wid][e][lane] = s;
-        red[wid][NA + e][lane] = sm;
+    }
+    auto warp_sum = [](double v) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    };
+#pragma unroll
+    for (int g = 0; g < kGroupMax; ++g) {
+        const double v0 = warp_sum(m0[g]);
+        if (lane == 0) red[wid][g * NA] = v0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const double v1 = warp_sum(m1[g][k]), v2 = warp_sum(m2[g][k]);
+            if (lane == 0) { red[wid][g * NA + 1 + k] = v1; red[wid][g * NA + 1 + D + k] = v2; }
+        }
     }
     __syncthreads();
-    if (wid != 0 || !live) return;
-    double accN[1 + 2 * kMaxD], accM[1 + 2 * kMaxD];
-    for (int e = 0; e < NA; ++e) {
-        double s = 0.0, sm = 0.0;
-        for (int w = 0; w < FIN_WARPS; ++w) { s += red[w][e][lane]; sm += red[w][NA + e][lane]; }
-        accN[e] = s; accM[e] = sm;
+    if (tid < a.EG * NA) {
+        double sacc = 0.0;
+        for (int w = 0; w < 8; ++w) sacc += red[w][tid];
+        const int g = tid / NA, e = tid % NA;
+        a.mpart[(((size_t)jp * a.d.E + a.out_idx[g]) * NA + e) * a.d.Bpad + b] = sacc;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalize_step: sums the partials of (rollout, output) in a fixed order (deterministic), applies the
+// determinant prefactors and writes mean/var of step t plus the tape entry.
+//   tape[((t-1)*E + a) * (2+4D) + e][Bpad]:  e = 0 mean, 1 var, 2.. dm/du, dm/ds, dv/du, dv/ds
+// ---------------------------------------------------------------------------------------------
+// Shared tail of the finalize kernels: prefactors, mean/var of step t and the tape entry of (b, a).
+__device__ void finalize_math(const StepDims &d, int t, int a, int b, const double *accN, const double *accM,
+                              const double *__restrict__ us, const double *__restrict__ hyp,
+                              double *__restrict__ mu, double *__restrict__ var, double *__restrict__ tape,
+                              int want_grad)
+{
+    const int D = d.D;
     const double *lam = hyp + (size_t)a * D;
     const double sf = hyp[(size_t)d.E * D + a];
     double detm = 1.0, detv = 1.0;
-    double u[kMaxD], s[kMaxD];
+    double s[kMaxD];
     for (int k = 0; k < D; ++k) {
-        u[k] = us[(size_t)k * d.Bpad + b];
         s[k] = us[(size_t)(D + k) * d.Bpad + b];
         detm *= 1.0 + s[k] / lam[k];            // |Lam^-1 S + I|      uncertainty_prop.py:335
         detv *= 1.0 + 2.0 * s[k] / lam[k];      // |2 Lam^-1 S + I|    uncertainty_prop.py:377
@@ -232,6 +284,61 @@ finalize_step_kernel(StepDims d, int t, int P, const double *__restrict__ part,
         tp[(size_t)(2 + 2 * D + k) * d.Bpad] = -dTu - 2.0 * mean * dmu;
         tp[(size_t)(2 + 3 * D + k) * d.Bpad] = -dTs - 2.0 * mean * dms;
     }
+}
+
+constexpr int FIN_WARPS = 4;
+__global__ void __launch_bounds__(32 * FIN_WARPS)
+finalize_step_kernel(StepDims d, int t, int P, const double *__restrict__ part,
+                     const double *__restrict__ mpart, const double *__restrict__ us,
+                     const double *__restrict__ hyp, double *__restrict__ mu,
+                     double *__restrict__ var, double *__restrict__ tape, int want_grad)
+{
+    // block = 32 rollouts (lanes) x FIN_WARPS slices of the partial-sum list; fixed summation order
+    __shared__ double red[FIN_WARPS][2 * (1 + 2 * kMaxD)][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int b = blockIdx.x * 32 + lane;
+    const int a = blockIdx.y;
+    const int D = d.D, NA = 1 + 2 * D;
+    const bool live = b < d.B;
+    for (int e = 0; e < NA; ++e) {
+        double s = 0.0, sm = 0.0;
+        if (live) {
+            for (int p = wid; p < P; p += FIN_WARPS) s += part[(((size_t)p * d.E + a) * NA + e) * d.Bpad + b];
+            for (int p = wid; p < MEAN_JP; p += FIN_WARPS) sm += mpart[(((size_t)p * d.E + a) * NA + e) * d.Bpad + b];
+        }
+        red[wid][e][lane] = s;
+        red[wid][NA + e][lane] = sm;
+    }
+    __syncthreads();
+    if (wid != 0 || !live) return;
+    double accN[1 + 2 * kMaxD], accM[1 + 2 * kMaxD];
+    for (int e = 0; e < NA; ++e) {
+        double s = 0.0, sm = 0.0;
+        for (int w = 0; w < FIN_WARPS; ++w) { s += red[w][e][lane]; sm += red[w][NA + e][lane]; }
+        accN[e] = s; accM[e] = sm;
+    }
+    finalize_math(d, t, a, b, accN, accM, us, hyp, mu, var, tape, want_grad);
+}
+
+// Few rollouts: one block per (rollout, output); warp e sums statistic e over the partial list (lanes stride the
+// list, xor-tree combine: fixed order), thread 0 finishes.
+__global__ void __launch_bounds__(32 * (1 + 2 * kMaxD))
+finalize_small_kernel(StepDims d, int t, int P, const double *__restrict__ part,
+                      const double *__restrict__ mpart, const double *__restrict__ us,
+                      const double *__restrict__ hyp, double *__restrict__ mu,
+                      double *__restrict__ var, double *__restrict__ tape, int want_grad)
+{
+    __shared__ double accN[1 + 2 * kMaxD], accM[1 + 2 * kMaxD];
+    const int lane = threadIdx.x & 31, e = threadIdx.x >> 5;
+    const int b = blockIdx.x, a = blockIdx.y;
+    const int NA = 1 + 2 * d.D;
+    double s = 0.0, sm = 0.0;
+    for (int p = lane; p < P; p += 32) s += part[(((size_t)p * d.E + a) * NA + e) * d.Bpad + b];
+    for (int p = lane; p < MEAN_JP; p += 32) sm += mpart[(((size_t)p * d.E + a) * NA + e) * d.Bpad + b];
+    for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); sm += __shfl_xor_sync(0xffffffffu, sm, o); }
+    if (lane == 0) { accN[e] = s; accM[e] = sm; }
+    __syncthreads();
+    if (threadIdx.x == 0) finalize_math(d, t, a, b, accN, accM, us, hyp, mu, var, tape, want_grad);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -318,6 +425,72 @@ struct CostArgs {
     double *gx0int;                              // [a][Bpad] or NULL
 };
 
+// State cost of time t and its partials (src/mpc.py:179-185):
+//   c_t = 1/gamma log det(I + gamma Q Sigma_t) + e^T (Q^-1 + gamma Sigma_t)^-1 e,  e = mu_t - x_ref
+// d c_t / d mu = (G + G^T) e,  d c_t / d sigma_k^2 = (M^-1 Q)_kk - gamma (G^T e)_k (G e)_k
+__device__ double state_cost_terms(const CostArgs &a, int b, int t, double gamma, double *dmu, double *dvar)
+{
+    const int E = a.d.E, Bp = a.d.Bpad;
+    double M[kMaxE * kMaxE], Minv[kMaxE * kMaxE], Gm[kMaxE * kMaxE], G[kMaxE * kMaxE], e[kMaxE], sg[kMaxE];
+    for (int k = 0; k < E; ++k) {
+        sg[k] = a.var[((size_t)t * E + k) * Bp + b];
+        e[k] = a.mu[((size_t)t * E + k) * Bp + b] - a.xref[k];
+    }
+    for (int r = 0; r < E; ++r)
+        for (int k = 0; k < E; ++k) {
+            M[r * E + k] = (r == k ? 1.0 : 0.0) + gamma * a.Q[r * E + k] * sg[k];     // I + gamma Q Sigma
+            Gm[r * E + k] = a.Qi[r * E + k] + (r == k ? gamma * sg[k] : 0.0);         // Q^-1 + gamma Sigma
+        }
+    const double det = lu_det_inv(E, M, a.want_grad ? Minv : nullptr);
+    lu_det_inv(E, Gm, G);
+    double cost = (1.0 / gamma) * log(det);            // log of the determinant (NaN if det < 0), mpc.py:183
+    double Ge[kMaxE], Gte[kMaxE];
+    for (int r = 0; r < E; ++r) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int k = 0; k < E; ++k) { s1 += G[r * E + k] * e[k]; s2 += G[k * E + r] * e[k]; }
+        Ge[r] = s1; Gte[r] = s2;
+    }
+    for (int k = 0; k < E; ++k) cost += e[k] * Ge[k];
+    if (a.want_grad) {
+        for (int k = 0; k < E; ++k) {
+            double mq = 0.0;
+            for (int r = 0; r < E; ++r) mq += Minv[k * E + r] * a.Q[r * E + k];
+            dmu[k] = Ge[k] + Gte[k];
+            dvar[k] = mq - gamma * Gte[k] * Ge[k];
+        }
+    }
+    return cost;
+}
+
+// Direct cost of action j (src/mpc.py:188-198): (u_j-u_ref)^T R (u_j-u_ref) + delta_j^T Rd delta_j, and the
+// gradient w.r.t. u_j (u_j also appears in delta_{j+1}).
+__device__ double action_cost_terms(const CostArgs &a, int b, int j, double *gact)
+{
+    const int m = a.d.m, Bp = a.d.Bpad, H = a.H;
+    double cost = 0.0, du[kMaxD];
+    for (int k = 0; k < m; ++k) { gact[k] = 0.0; du[k] = a.Uint[((size_t)j * m + k) * Bp + b] - a.uref[k]; }
+    for (int r = 0; r < m; ++r)
+        for (int k = 0; k < m; ++k) {
+            cost += du[r] * a.R[r * m + k] * du[k];
+            gact[r] += (a.R[r * m + k] + a.R[k * m + r]) * du[k];
+        }
+    if (a.has_rd) {
+        double d0[kMaxD], d1[kMaxD];
+        for (int k = 0; k < m; ++k) {
+            const double cur = a.Uint[((size_t)j * m + k) * Bp + b];
+            const double prev = (j == 0) ? a.last_u[(size_t)k * Bp + b] : a.Uint[((size_t)(j - 1) * m + k) * Bp + b];
+            d0[k] = cur - prev;
+            d1[k] = (j + 1 < H) ? a.Uint[((size_t)(j + 1) * m + k) * Bp + b] - cur : 0.0;
+        }
+        for (int r = 0; r < m; ++r)
+            for (int k = 0; k < m; ++k) {
+                cost += d0[r] * a.Rd[r * m + k] * d0[k];
+                gact[r] += (a.Rd[r * m + k] + a.Rd[k * m + r]) * (d0[k] - d1[k]);
+            }
+    }
+    return cost;
+}
+
 __global__ void __launch_bounds__(128) cost_adjoint_kernel(const CostArgs a)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -332,34 +505,9 @@ __global__ void __launch_bounds__(128) cost_adjoint_kernel(const CostArgs a)
     for (int t = H; t >= 0; --t) {
         // ---- seeds at time t ----
         if (a.mode == 0) {
-            double M[kMaxE * kMaxE], Minv[kMaxE * kMaxE], Gm[kMaxE * kMaxE], G[kMaxE * kMaxE], e[kMaxE], sg[kMaxE];
-            for (int k = 0; k < E; ++k) {
-                sg[k] = a.var[((size_t)t * E + k) * Bp + b];
-                e[k] = a.mu[((size_t)t * E + k) * Bp + b] - a.xref[k];
-            }
-            for (int r = 0; r < E; ++r)
-                for (int k = 0; k < E; ++k) {
-                    M[r * E + k] = (r == k ? 1.0 : 0.0) + gamma * a.Q[r * E + k] * sg[k];     // I + gamma Q Sigma
-                    Gm[r * E + k] = a.Qi[r * E + k] + (r == k ? gamma * sg[k] : 0.0);         // Q^-1 + gamma Sigma
-                }
-            const double det = lu_det_inv(E, M, a.want_grad ? Minv : nullptr);
-            lu_det_inv(E, Gm, G);
-            cost += (1.0 / gamma) * log(det);          // log of the determinant (NaN if det < 0), mpc.py:183
-            double Ge[kMaxE], Gte[kMaxE];
-            for (int r = 0; r < E; ++r) {
-                double s1 = 0.0, s2 = 0.0;
-                for (int k = 0; k < E; ++k) { s1 += G[r * E + k] * e[k]; s2 += G[k * E + r] * e[k]; }
-                Ge[r] = s1; Gte[r] = s2;
-            }
-            for (int k = 0; k < E; ++k) cost += e[k] * Ge[k];
-            if (a.want_grad) {
-                for (int k = 0; k < E; ++k) {
-                    double mq = 0.0;
-                    for (int r = 0; r < E; ++r) mq += Minv[k * E + r] * a.Q[r * E + k];
-                    mb[k] += Ge[k] + Gte[k];
-                    vb[k] += mq - gamma * Gte[k] * Ge[k];
-                }
-            }
+            double dmu[kMaxE], dvar[kMaxE];
+            cost += state_cost_terms(a, b, t, gamma, dmu, dvar);
+            if (a.want_grad) for (int k = 0; k < E; ++k) { mb[k] += dmu[k]; vb[k] += dvar[k]; }
         } else {
             for (int k = 0; k < E; ++k) {
                 if (a.seed_mu) mb[k] += a.seed_mu[((size_t)t * E + k) * Bp + b];
@@ -370,30 +518,7 @@ __global__ void __launch_bounds__(128) cost_adjoint_kernel(const CostArgs a)
         // ---- direct action cost of u_{t-1} ----
         double gact[kMaxD];
         for (int k = 0; k < m; ++k) gact[k] = 0.0;
-        if (a.mode == 0) {
-            double du[kMaxD];
-            for (int k = 0; k < m; ++k) du[k] = a.Uint[((size_t)(t - 1) * m + k) * Bp + b] - a.uref[k];
-            for (int r = 0; r < m; ++r)
-                for (int k = 0; k < m; ++k) {
-                    cost += du[r] * a.R[r * m + k] * du[k];
-                    gact[r] += (a.R[r * m + k] + a.R[k * m + r]) * du[k];
-                }
-            if (a.has_rd) {
-                // delta_j = u_j - u_{j-1} (u_{-1} = last_u);  u_{t-1} appears in delta_{t-1} and delta_t
-                double d0[kMaxD], d1[kMaxD];
-                for (int k = 0; k < m; ++k) {
-                    const double cur = a.Uint[((size_t)(t - 1) * m + k) * Bp + b];
-                    const double prev = (t - 1 == 0) ? a.last_u[(size_t)k * Bp + b] : a.Uint[((size_t)(t - 2) * m + k) * Bp + b];
-                    d0[k] = cur - prev;
-                    d1[k] = (t < H) ? a.Uint[((size_t)t * m + k) * Bp + b] - cur : 0.0;
-                }
-                for (int r = 0; r < m; ++r)
-                    for (int k = 0; k < m; ++k) {
-                        cost += d0[r] * a.Rd[r * m + k] * d0[k];
-                        gact[r] += (a.Rd[r * m + k] + a.Rd[k * m + r]) * (d0[k] - d1[k]);
-                    }
-            }
-        }
+        if (a.mode == 0) cost += action_cost_terms(a, b, t - 1, gact);
         if (!a.want_grad) continue;
         // ---- pull the adjoints of (mean_t, var_t) back through step t ----
         double ub[kMaxD], sb[kMaxD];
@@ -413,9 +538,88 @@ __global__ void __launch_bounds__(128) cost_adjoint_kernel(const CostArgs a)
     if (a.gx0int) for (int k = 0; k < E; ++k) a.gx0int[(size_t)k * Bp + b] = mb[k];
 }
 
+// Few rollouts: one block per rollout.  Phase 1 evaluates the H+1 state-cost terms (and their partials) and the H
+// action terms in parallel over t; phase 2 is the sequential reverse sweep, with lane k of warp 0 owning input
+// dimension k (its 4E tape loads per step are independent, so the sweep costs ~one memory latency per step).
+__global__ void __launch_bounds__(128) cost_adjoint_small_kernel(const CostArgs a)
+{
+    extern __shared__ double sm[];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int E = a.d.E, D = a.d.D, m = a.d.m, H = a.H, Bp = a.d.Bpad;
+    const int NT = 2 + 4 * D;
+    double *seed_mu = sm;                          // [(H+1) * E]
+    double *seed_var = seed_mu + (size_t)(H + 1) * E;
+    double *gact = seed_var + (size_t)(H + 1) * E; // [H * m]
+    double *cpart = gact + (size_t)H * (m > 0 ? m : 1);   // [2H + 1]
+    double *carry = cpart + 2 * H + 1;             // [2E]: mb, vb
+    const double gamma = (a.mode == 0) ? a.gamma[b] : 0.0;
+    for (int t = tid; t <= H; t += blockDim.x) {
+        double dmu[kMaxE], dvar[kMaxE];
+        for (int k = 0; k < E; ++k) dmu[k] = dvar[k] = 0.0;
+        double c = 0.0;
+        if (a.mode == 0) c = state_cost_terms(a, b, t, gamma, dmu, dvar);
+        else
+            for (int k = 0; k < E; ++k) {
+                if (a.seed_mu) dmu[k] = a.seed_mu[((size_t)t * E + k) * Bp + b];
+                if (a.seed_var) dvar[k] = a.seed_var[((size_t)t * E + k) * Bp + b];
+            }
+        cpart[t] = c;
+        for (int k = 0; k < E; ++k) { seed_mu[t * E + k] = dmu[k]; seed_var[t * E + k] = dvar[k]; }
+    }
+    for (int j = tid; j < H; j += blockDim.x) {
+        double g[kMaxD];
+        for (int k = 0; k < m; ++k) g[k] = 0.0;
+        double c = 0.0;
+        if (a.mode == 0) c = action_cost_terms(a, b, j, g);
+        cpart[H + 1 + j] = c;
+        for (int k = 0; k < m; ++k) gact[j * m + k] = g[k];
+    }
+    if (tid < 2 * E) carry[tid] = 0.0;
+    __syncthreads();
+    if (tid >= 32) return;
+    if (tid == 0 && a.mode == 0) {
+        // same order as the one-thread kernel: t = H..0, each state term followed by the action term of t-1
+        double c = 0.0;
+        for (int t = H; t >= 0; --t) { c += cpart[t]; if (t > 0) c += cpart[H + t]; }
+        a.cost[b] = c;
+    }
+    if (!a.want_grad) return;
+    const int k = tid;                             // lane k < D owns input dimension k
+    for (int t = H; t >= 1; --t) {
+        if (k < E) { carry[k] += seed_mu[t * E + k]; carry[E + k] += seed_var[t * E + k]; }
+        __syncwarp();
+        double ub = 0.0, sb = 0.0;
+        if (k < D) {
+            for (int o = 0; o < E; ++o) {
+                const double *tp = a.tape + (((size_t)(t - 1) * E + o) * NT) * Bp + b;
+                const double mo = carry[o], vo = carry[E + o];
+                ub += mo * tp[(size_t)(2 + k) * Bp] + vo * tp[(size_t)(2 + 2 * D + k) * Bp];
+                sb += mo * tp[(size_t)(2 + D + k) * Bp] + vo * tp[(size_t)(2 + 3 * D + k) * Bp];
+            }
+        }
+        __syncwarp();
+        if (k < E) { carry[k] = ub; carry[E + k] = sb; }
+        else if (k < D) a.gradint[((size_t)(t - 1) * m + (k - E)) * Bp + b] = ub + gact[(t - 1) * m + (k - E)];
+        __syncwarp();
+    }
+    if (a.gx0int && k < E) a.gx0int[(size_t)k * Bp + b] = carry[k] + seed_mu[k];
+}
+
 // =============================================================================================
 // Host orchestration
 // =============================================================================================
+static void launch_cost_adjoint(gpmpc_ctx *h, const CostArgs &ca, int B, int H)
+{
+    if (B < kSingleMaxB) {
+        const size_t smem = ((size_t)2 * (H + 1) * ca.d.E + (size_t)H * (ca.d.m > 0 ? ca.d.m : 1) + 2 * H + 1 + 2 * ca.d.E) * sizeof(double);
+        if (smem <= 40 * 1024) {
+            cost_adjoint_small_kernel<<<B, 128, smem, h->stream>>>(ca);
+            return;
+        }
+    }
+    cost_adjoint_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(ca);
+}
+
 static int check_ready(gpmpc_ctx *h, int B, int H)
 {
     if (!h) return GPMPC_ERR_INVALID;
@@ -441,6 +645,13 @@ static void pair_geometry(gpmpc_ctx *h, int B, long long total_tiles, int &ctas_
 {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    if (B < kSingleMaxB) {                       // mm_pairs_single: two CTAs per SM and rollout, static tile ranges
+        long long c = 2LL * sms;
+        if (c > total_tiles) c = total_tiles;
+        ctas_per_chunk = (int)c;
+        n_items = (int)c;
+        return;
+    }
     const int chunks = (B + PAIR_THREADS - 1) / PAIR_THREADS;
     long long c = (2LL * sms) / chunks;          // floor: never spill into a second wave
     if (c < 1) c = 1;
@@ -454,7 +665,8 @@ static void pair_geometry(gpmpc_ctx *h, int B, long long total_tiles, int &ctas_
 
 template <int D> static void launch_mean(const MeanArgs &ma, dim3 grid, cudaStream_t st)
 {
-    mean_sums_kernel<D><<<grid, MEAN_THREADS, 0, st>>>(ma);
+    if (ma.d.B < kSingleMaxB) mean_single_kernel<D><<<dim3(MEAN_JP, ma.d.B), 256, 0, st>>>(ma);
+    else mean_sums_kernel<D><<<grid, MEAN_THREADS, 0, st>>>(ma);
 }
 static void launch_mean_d(int D, const MeanArgs &ma, dim3 grid, cudaStream_t st)
 {
@@ -473,6 +685,12 @@ static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int ctas, int P, lon
 {
     const size_t mat = (size_t)h->ld * h->ld;
     const int NA = nacc(d.D);
+    if (d.B < kSingleMaxB) {
+        GP_CUDA(h, h->zall.reserve((size_t)d.G * d.B * h->ld * d.D * sizeof(double)));
+        zprep_kernel<<<dim3((h->ld * d.D + 255) / 256, d.B, d.G), 256, 0, h->stream>>>(h->X.as<double>(), h->ld, d.D, d.B,
+                                                                                      d.Bpad, d.G, cst, h->zall.as<double>());
+        GP_LAUNCH_CHECK(h);
+    }
     if (h->time_pairs) cudaEventRecord(h->ev0, h->stream);
     for (int g = 0; g < d.G; ++g) {
         const LambdaGroup &grp = h->groups[g];
@@ -492,9 +710,14 @@ static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int ctas, int P, lon
         pa.total_tiles = (int)total_tiles; pa.chunks = (d.B + PAIR_THREADS - 1) / PAIR_THREADS;
         const int chunks = (d.B + PAIR_THREADS - 1) / PAIR_THREADS;
         pa.counters = h->tickets.as<int>();
-        GP_CUDA(h, cudaMemsetAsync(pa.counters, 0, chunks * sizeof(int), h->stream));
-        dim3 grid(ctas * chunks);
-        cudaError_t e = pair_launcher(d.D)(grp.count, want_grad, pa, grid, h->stream);
+        cudaError_t e;
+        if (d.B < kSingleMaxB) {
+            pa.zall = h->zall.as<double>() + (size_t)g * d.B * h->ld * d.D;
+            e = single_launcher(d.D)(grp.count, want_grad, pa, dim3(ctas, d.B), h->stream);
+        } else {
+            GP_CUDA(h, cudaMemsetAsync(pa.counters, 0, chunks * sizeof(int), h->stream));
+            e = pair_launcher(d.D)(grp.count, want_grad, pa, dim3(ctas * chunks), h->stream);
+        }
         h->launches++;
         if (e != cudaSuccess) return fail(h, GPMPC_ERR_CUDA, std::string("mm_pairs_batch: ") + cudaGetErrorString(e));
 
@@ -504,9 +727,16 @@ static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int ctas, int P, lon
         GP_LAUNCH_CHECK(h);
     }
     if (h->time_pairs) cudaEventRecord(h->ev1, h->stream);
-    dim3 fgrid((d.B + 31) / 32, d.E);
-    finalize_step_kernel<<<fgrid, 32 * FIN_WARPS, 0, h->stream>>>(d, t, P, h->part.as<double>(), h->mpart.as<double>(), us,
-                                                       h->hyp.as<double>(), mu, var, tape, want_grad ? 1 : 0);
+    if (d.B < kSingleMaxB) {
+        finalize_small_kernel<<<dim3(d.B, d.E), 32 * nacc(d.D), 0, h->stream>>>(d, t, P, h->part.as<double>(),
+                                                                                h->mpart.as<double>(), us, h->hyp.as<double>(),
+                                                                                mu, var, tape, want_grad ? 1 : 0);
+    } else {
+        dim3 fgrid((d.B + 31) / 32, d.E);
+        finalize_step_kernel<<<fgrid, 32 * FIN_WARPS, 0, h->stream>>>(d, t, P, h->part.as<double>(), h->mpart.as<double>(),
+                                                                      us, h->hyp.as<double>(), mu, var, tape,
+                                                                      want_grad ? 1 : 0);
+    }
     GP_LAUNCH_CHECK(h);
     (void)NA;
     return GPMPC_OK;
@@ -737,7 +967,7 @@ extern "C" int gpmpc_rollout_cost_grad(gpmpc_handle h, int B, int H, const doubl
     ca.cost = cost_host ? cost_dev : cost;
     ca.gradint = grad_int;
     ca.gx0int = nullptr;
-    cost_adjoint_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(ca);
+    launch_cost_adjoint(h, ca, B, H);
     GP_LAUNCH_CHECK(h);
     if (want_grad && H > 0 && m > 0) {
         const bool ghost = !is_device_ptr(grad);
@@ -786,7 +1016,7 @@ extern "C" int gpmpc_rollout_vjp(gpmpc_handle h, int B, int H, const double *gme
     ca.mu = h->mu.as<double>(); ca.var = h->var.as<double>(); ca.tape = h->tape.as<double>(); ca.Uint = nullptr;
     ca.seed_mu = gmd ? smu : nullptr; ca.seed_var = gvd ? svar : nullptr;
     ca.gradint = grad_int; ca.gx0int = gx0_int; ca.cost = nullptr;
-    cost_adjoint_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(ca);
+    launch_cost_adjoint(h, ca, B, H);
     GP_LAUNCH_CHECK(h);
     bool sync = false;
     if (gU && H > 0 && m > 0) {

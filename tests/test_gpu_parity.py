@@ -306,7 +306,7 @@ def test_batched_rollouts_vs_c_oracle(gp):
     close(cost_p, cost[perm], 1e-12)
     norm_close(grad_p, grad[perm], 1e-11)
     c1, g1 = br.cost_and_grad(x0[5:6], U[5:6], gamma[5:6], host_out=True)
-    close(c1, cost[5:6], 1e-12)
+    close(c1, cost[5:6], 1e-9)      # B < 64 runs the lanes<->pairs kernel: different (fixed) summation order
 
 
 def test_mid_size_vs_c_oracle_and_finite_differences(gp):
