@@ -1,5 +1,6 @@
 // Shared declarations for libgpmpc.so (sm_100a).  Internal header -- the public C ABI is include/gpmpc.h.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
@@ -66,6 +67,7 @@ struct gpmpc_ctx {
     gpmpc::DevBuf linv;            // [64,64] inverse of the current diagonal block
     gpmpc::DevBuf info;            // int: index of first bad pivot + 1, 0 = ok
     gpmpc::DevBuf hyp;             // device copy of propagation hypers: lam[E,D], sf[E]
+    CUtensorMap wt_map[gpmpc::kMaxE];   // TMA descriptors of the Wt matrices (2-D, box 32x32), see fit.cu
 
     // rollout workspaces (grow-only)
     gpmpc::DevBuf mu, var, tape, cst, part, mpart, stage_in, stage_out, gbuf, tickets, zall;
@@ -123,6 +125,7 @@ int derive_weights(gpmpc_ctx *h, int a);                // Wt[a] from Kinv[a], b
 int gram_into(gpmpc_ctx *h, int a, double *dst, int ldd, bool add_noise);   // Kf / Ky of output a
 void rebuild_groups(gpmpc_ctx *h);
 int upload_prop_hypers(gpmpc_ctx *h);
+int encode_wt_maps(gpmpc_ctx *h);                       // (re)build the TMA descriptors after Wt was (re)allocated
 
 // ---- gemm.cu ------------------------------------------------------------------------------
 // C[M,N] = alpha * A[M,K] * B[N,K]^T + beta * C   (all row-major, fp64, DMMA m8n8k4)

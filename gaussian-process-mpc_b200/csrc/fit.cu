@@ -309,6 +309,37 @@ static int invert_factor(gpmpc_ctx *h, const double *L, double *ZT, int np)
     return GPMPC_OK;
 }
 
+// TMA descriptors for the per-step pair kernel: Wt[a] as a 2-D fp64 tensor {ld, ld}, 32x32 boxes, no swizzle.
+// cuTensorMapEncodeTiled is a driver entry point; it is resolved through the runtime so that libgpmpc.so
+// does not link libcuda directly.
+int encode_wt_maps(gpmpc_ctx *h)
+{
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        GP_CUDA(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess)
+            return fail(h, GPMPC_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        encode = reinterpret_cast<encode_fn>(fn);
+    }
+    const size_t mat = (size_t)h->ld * h->ld;
+    for (int a = 0; a < h->E; ++a) {
+        const cuuint64_t dims[2] = {(cuuint64_t)h->ld, (cuuint64_t)h->ld};
+        const cuuint64_t strides[1] = {(cuuint64_t)h->ld * sizeof(double)};
+        const cuuint32_t box[2] = {(cuuint32_t)kPairTile, (cuuint32_t)kPairTile};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&h->wt_map[a], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, h->Wt.as<double>() + a * mat, dims, strides,
+                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(h, GPMPC_ERR_CUDA, "cuTensorMapEncodeTiled failed for a Wt matrix");
+    }
+    return GPMPC_OK;
+}
+
 int fit_all(gpmpc_ctx *h, const bool *which)
 {
     const int ld = h->ld, np = h->ld, n = h->n, E = h->E;
@@ -321,6 +352,10 @@ int fit_all(gpmpc_ctx *h, const bool *which)
     GP_CUDA(h, h->tt.reserve((size_t)ld * NB * sizeof(double)));
     GP_CUDA(h, h->linv.reserve((size_t)NB * NB * sizeof(double)));
     GP_CUDA(h, h->info.reserve(sizeof(int)));
+    {
+        int rc_maps = encode_wt_maps(h);
+        if (rc_maps) return rc_maps;
+    }
 
     for (int a = 0; a < E; ++a) {
         if (!which[a]) continue;

@@ -17,6 +17,7 @@
 // loop has no cross-lane traffic at all.  Shared memory is filled by cp.async double buffering of 32x32
 // Wt tiles.  The kernel is bound by the FP64 pipe (one exp + ~14 + 12*EG DFMA-class ops per pair).
 #pragma once
+#include <cuda.h>
 #include "common.cuh"
 
 namespace gpmpc {
@@ -39,6 +40,9 @@ namespace gpmpc {
 #endif
 #ifndef GPMPC_ACC_ORDER
 #define GPMPC_ACC_ORDER 0        // accumulation loop nest: 0 output-major, 1 dimension-major, 2 e-scaled features
+#endif
+#ifndef GPMPC_USE_TMA
+#define GPMPC_USE_TMA 1          // 1: Wt tiles by TMA (cp.async.bulk.tensor.2d + mbarrier), 0: cp.async (LDGSTS)
 #endif
 #ifndef GPMPC_MINBLOCKS
 #define GPMPC_MINBLOCKS 2        // CTAs per SM promised to ptxas
@@ -158,6 +162,42 @@ __device__ __forceinline__ void cpa16(void *smem, const void *gmem)
 __device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// ---- TMA / mbarrier primitives (sm_90+ PTX; SASS: UTMALDG / UBLKCP / SYNCS) ----
+struct alignas(64) PairTma { CUtensorMap map[kGroupMax]; };   // one 2-D map per Wt matrix: dims {ld, ld}, box {32, 32}
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(void *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "GPMPC_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra GPMPC_DONE_%=;\n"
+        "bra GPMPC_WAIT_%=;\n"
+        "GPMPC_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, void *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, unsigned bytes, void *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 struct PairArgs {
     const double *Wt[kGroupMax];   // weight matrices of the group's outputs (ld x ld, upper-tri weights)
     int out_idx[kGroupMax];        // global output index of each member
@@ -187,9 +227,10 @@ __host__ __device__ constexpr size_t pair_smem_bytes()
 }
 
 template <int D, int EG, bool GRAD>
-__global__ void __launch_bounds__(PAIR_THREADS, GPMPC_MINBLOCKS) mm_pairs_batch(const PairArgs a)
+__global__ void __launch_bounds__(PAIR_THREADS, GPMPC_MINBLOCKS)
+mm_pairs_batch(const PairArgs a, const __grid_constant__ PairTma tm)
 {
-    extern __shared__ __align__(16) double smem[];
+    extern __shared__ __align__(128) double smem[];
     constexpr size_t STAGE = pair_stage_doubles<D, EG>();
     const int tid = threadIdx.x;
     // consecutive CTAs serve different rollout chunks, so that the early-launched (favoured) and late-launched
@@ -225,6 +266,30 @@ __global__ void __launch_bounds__(PAIR_THREADS, GPMPC_MINBLOCKS) mm_pairs_batch(
 #define GP_CU(k) cu[k]
 #endif
 
+#if GPMPC_USE_TMA
+    // full[stage] completes when the TMA engine has written the stage's bytes; one thread arms and issues.
+    __shared__ __align__(8) unsigned long long full[2];
+    if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
+    __syncthreads();
+    unsigned uses0 = 0, uses1 = 0;               // completed uses of each stage -> wait parity
+    constexpr unsigned STAGE_BYTES = (unsigned)(STAGE * sizeof(double));
+    auto issue = [&](int stage, int ti, int tj) {
+        if (tid == 0) {
+            double *base = smem + (size_t)stage * STAGE;
+            void *bar = &full[stage];
+            mbar_expect_tx(bar, STAGE_BYTES);
+#pragma unroll
+            for (int g = 0; g < EG; ++g) tma_load_2d(base + (size_t)g * PT * PT, &tm.map[g], tj * PT, ti * PT, bar);
+            double *xi = base + (size_t)EG * PT * PT;
+            bulk_load_1d(xi, a.X + (size_t)ti * PT * D, PT * D * sizeof(double), bar);
+            bulk_load_1d(xi + PT * D, a.X + (size_t)tj * PT * D, PT * D * sizeof(double), bar);
+        }
+    };
+    auto wait_stage = [&](int stage) {
+        if (stage == 0) { mbar_wait(&full[0], uses0 & 1); ++uses0; }
+        else { mbar_wait(&full[1], uses1 & 1); ++uses1; }
+    };
+#else
     auto issue = [&](int stage, int ti, int tj) {
         double *base = smem + (size_t)stage * STAGE;
 #pragma unroll
@@ -246,6 +311,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, GPMPC_MINBLOCKS) mm_pairs_batch(
         }
         cpa_commit();
     };
+#endif
 
     // Work items = fixed contiguous ranges of the upper-triangular tile list.  CTAs draw items from a ticket
     // counter (the two CTAs of an SM do not progress at the same rate: the warp scheduler favours one of
@@ -287,9 +353,14 @@ __global__ void __launch_bounds__(PAIR_THREADS, GPMPC_MINBLOCKS) mm_pairs_batch(
         for (int t = t_begin; t < t_end; ++t) {
             int In = I, Jn = J + 1;
             if (Jn == a.ntile) { ++In; Jn = In; }
+#if GPMPC_USE_TMA
+            if (t + 1 < t_end) issue(stage ^ 1, In, Jn);
+            wait_stage(stage);
+#else
             if (t + 1 < t_end) { issue(stage ^ 1, In, Jn); cpa_wait<1>(); }
             else cpa_wait<0>();
             __syncthreads();
+#endif
 
             const double *Ws = smem + (size_t)stage * STAGE;
             const double *xi = Ws + (size_t)EG * PT * PT;

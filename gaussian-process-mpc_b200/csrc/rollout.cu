@@ -19,13 +19,14 @@
 
 namespace gpmpc {
 
-#define DECL_LAUNCH(D) cudaError_t launch_pairs_batch_D##D(int, bool, const PairArgs &, dim3, cudaStream_t); \
+#define DECL_LAUNCH(D) cudaError_t launch_pairs_batch_D##D(int, bool, const PairArgs &, const PairTma &, dim3, cudaStream_t); \
                        cudaError_t launch_pairs_single_D##D(int, bool, const PairArgs &, dim3, cudaStream_t);
 DECL_LAUNCH(2) DECL_LAUNCH(3) DECL_LAUNCH(4) DECL_LAUNCH(5) DECL_LAUNCH(6) DECL_LAUNCH(7) DECL_LAUNCH(8)
 #undef DECL_LAUNCH
 
 typedef cudaError_t (*pair_launch_fn)(int, bool, const PairArgs &, dim3, cudaStream_t);
-static pair_launch_fn pair_launcher(int D)
+typedef cudaError_t (*pair_tma_launch_fn)(int, bool, const PairArgs &, const PairTma &, dim3, cudaStream_t);
+static pair_tma_launch_fn pair_launcher(int D)
 {
     switch (D) {
         case 2: return launch_pairs_batch_D2; case 3: return launch_pairs_batch_D3;
@@ -716,7 +717,9 @@ static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int ctas, int P, lon
             e = single_launcher(d.D)(grp.count, want_grad, pa, dim3(ctas, d.B), h->stream);
         } else {
             GP_CUDA(h, cudaMemsetAsync(pa.counters, 0, chunks * sizeof(int), h->stream));
-            e = pair_launcher(d.D)(grp.count, want_grad, pa, dim3(ctas * chunks), h->stream);
+            PairTma tm;
+            for (int i = 0; i < kGroupMax; ++i) tm.map[i] = h->wt_map[grp.outputs[i < grp.count ? i : 0]];
+            e = pair_launcher(d.D)(grp.count, want_grad, pa, tm, dim3(ctas * chunks), h->stream);
         }
         h->launches++;
         if (e != cudaSuccess) return fail(h, GPMPC_ERR_CUDA, std::string("mm_pairs_batch: ") + cudaGetErrorString(e));
