@@ -124,6 +124,16 @@ class GPBundle:
               "gpmpc_predict")
         return mean, cov
 
+    def marginal_likelihood(self, a, resid=None, want_grad=True):
+        """ml (float) and d ml / d [log lambdas, log sigma_f, log sigma_n] (numpy [D+2])."""
+        self._sync_stream()
+        r = None if resid is None else as_f64(resid).reshape(-1)
+        ml = np.empty(1)
+        grad = np.empty(self.D + 2) if want_grad else None
+        check(self.h, self.lib.gpmpc_marginal_likelihood(self.h, int(a), _ptr(r), _ptr(ml), _ptr(grad)),
+              "gpmpc_marginal_likelihood")
+        return float(ml[0]), grad
+
     def moment_match(self, U, S, out_device=True):
         """U [B,D]; S [B,D] (diagonal) or [B,D,D] (full).  Returns mean [B,E], var [B,E]."""
         self._sync_stream()

@@ -92,3 +92,129 @@ class BatchedRollouts:
             rows.append(gathered[r, :rhi - rlo])
         full = torch.cat(rows, dim=0)
         return full[:, 0].contiguous(), full[:, 1:].reshape(B, H, m).contiguous()
+
+
+class BatchedSolver:
+    """Lock-step solver for MANY independent MPC problems (multi-start control sequences, gamma sweeps, many
+    initial states): SURVEY 8f row N1.  The reference solves one NLP at a time through cyipopt
+    (`src/mpc.py:269-330`), which keeps a GPU at B = 1; here every iteration is ONE batched device evaluation
+    of cost and gradient for all still-active problems.
+
+    Method: projected L-BFGS with Armijo backtracking on the box lb <= u <= ub (per-problem histories, all
+    vectorised over the batch).  Non-finite costs (the NaN of log(det) < 0) are treated like IPOPT
+    treats evaluation errors: the trial step is rejected and shortened.
+    """
+
+    def __init__(self, rollouts: BatchedRollouts, horizon, input_dim, lb=None, ub=None, memory=8, max_iter=100,
+                 gtol=1e-4, ftol=1e-10, max_backtracks=12):
+        self.rollouts = rollouts
+        self.H, self.m = int(horizon), int(input_dim)
+        n = self.H * self.m
+        self.lb = np.full(n, -np.inf) if lb is None else np.tile(np.asarray(lb, dtype=np.float64), self.H)
+        self.ub = np.full(n, np.inf) if ub is None else np.tile(np.asarray(ub, dtype=np.float64), self.H)
+        self.memory, self.max_iter, self.gtol, self.ftol = memory, max_iter, gtol, ftol
+        self.max_backtracks = max_backtracks
+        self.n_evals = 0
+
+    def _eval(self, x0, X, gamma, last_u):
+        B = X.shape[0]
+        cost, grad = self.rollouts.cost_and_grad(x0, X.reshape(B, self.H, self.m), gamma, last_u, host_out=True)
+        self.n_evals += 1
+        return np.asarray(cost, dtype=np.float64), np.asarray(grad, dtype=np.float64).reshape(B, -1)
+
+    def _direction(self, G, S, Y, rho, count):
+        """Two-loop recursion for every problem at once.  S, Y: [B, mem, n]; count: history length per problem."""
+        B, mem, _ = S.shape
+        q = G.copy()
+        alpha = np.zeros((B, mem))
+        for i in range(mem - 1, -1, -1):
+            use = (i < count)
+            a = rho[:, i] * np.einsum("bn,bn->b", S[:, i], q) * use
+            alpha[:, i] = a
+            q -= a[:, None] * Y[:, i]
+        last = np.clip(count - 1, 0, mem - 1)
+        idx = np.arange(B)
+        yy = np.einsum("bn,bn->b", Y[idx, last], Y[idx, last])
+        sy = np.einsum("bn,bn->b", S[idx, last], Y[idx, last])
+        scale = np.where((count > 0) & (yy > 0), sy / np.where(yy > 0, yy, 1.0), 1.0)
+        r = q * scale[:, None]
+        for i in range(mem):
+            use = (i < count)
+            beta = rho[:, i] * np.einsum("bn,bn->b", Y[:, i], r) * use
+            r += (alpha[:, i] - beta)[:, None] * S[:, i]
+        return -r
+
+    def solve(self, x0, gamma, U0=None, last_u=None):
+        """x0 [B,E] (or [E]), gamma [B] (or scalar).  Returns dict(U [B,H,m], cost [B], iters, evals, converged [B])."""
+        x0 = np.asarray(x0, dtype=np.float64)
+        if x0.ndim == 1:
+            B = int(np.size(gamma)) if np.ndim(gamma) else (1 if U0 is None else U0.shape[0])
+            x0 = np.broadcast_to(x0, (B, x0.shape[0])).copy()
+        B = x0.shape[0]
+        gamma = np.broadcast_to(np.asarray(gamma, dtype=np.float64), (B,)).copy()
+        n = self.H * self.m
+        X = np.zeros((B, n)) if U0 is None else np.asarray(U0, dtype=np.float64).reshape(B, n).copy()
+        X = np.clip(X, self.lb, self.ub)
+        F, G = self._eval(x0, X, gamma, last_u)
+        mem = self.memory
+        S = np.zeros((B, mem, n)); Y = np.zeros((B, mem, n)); rho = np.zeros((B, mem))
+        count = np.zeros(B, dtype=np.int64)
+        active = np.isfinite(F)
+        converged = np.zeros(B, dtype=bool)
+        it = 0
+        for it in range(1, self.max_iter + 1):
+            # projected-gradient optimality measure
+            pg = X - np.clip(X - G, self.lb, self.ub)
+            done = np.max(np.abs(pg), axis=1) < self.gtol
+            converged |= done & active
+            active &= ~done
+            if not active.any():
+                break
+            # active set: variables sitting on a bound with the gradient pushing outwards are frozen
+            at_bound = ((X <= self.lb) & (G > 0)) | ((X >= self.ub) & (G < 0))
+            Gf = np.where(at_bound, 0.0, G)
+            Dir = self._direction(Gf, S, Y, rho, count)
+            Dir[at_bound] = 0.0
+            # fall back to (projected) steepest descent where the quasi-Newton direction is not a descent direction
+            slope = np.einsum("bn,bn->b", Dir, Gf)
+            bad = ~(slope < 0)
+            Dir[bad] = -Gf[bad]
+            step = np.ones(B)
+            Xn, Fn, Gn = X.copy(), F.copy(), G.copy()
+            pending = active.copy()
+            retried = np.zeros(B, dtype=bool)
+            for _ in range(2 * self.max_backtracks):
+                T = np.clip(X + step[:, None] * Dir, self.lb, self.ub)
+                Ft, Gt = self._eval(x0, np.where(pending[:, None], T, X), gamma, last_u)
+                dec = np.einsum("bn,bn->b", G, T - X)
+                ok = pending & np.isfinite(Ft) & (Ft <= F + 1e-4 * dec) & (dec < 0)
+                Xn[ok], Fn[ok], Gn[ok] = T[ok], Ft[ok], Gt[ok]
+                pending &= ~ok
+                if not pending.any():
+                    break
+                step[pending] *= 0.5
+                # a quasi-Newton direction that keeps failing is replaced once by the projected gradient
+                retry = pending & (step < 0.5 ** self.max_backtracks) & ~retried
+                if retry.any():
+                    Dir[retry] = -Gf[retry]
+                    step[retry] = 1.0
+                    count[retry] = 0
+                    retried |= retry
+            stalled = pending                     # no acceptable step found: stop these problems
+            s = Xn - X; y = Gn - G
+            sy = np.einsum("bn,bn->b", s, y)
+            upd = active & ~stalled & (sy > 1e-12)
+            if upd.any():
+                slot = np.minimum(count, mem - 1)
+                full = upd & (count >= mem)
+                if full.any():                    # drop the oldest pair
+                    S[full, :-1] = S[full, 1:]; Y[full, :-1] = Y[full, 1:]; rho[full, :-1] = rho[full, 1:]
+                idx = np.where(upd)[0]
+                S[idx, slot[idx]] = s[idx]; Y[idx, slot[idx]] = y[idx]; rho[idx, slot[idx]] = 1.0 / sy[idx]
+                count[idx] = np.minimum(count[idx] + 1, mem)
+            small = np.abs(F - Fn) <= self.ftol * np.maximum(1.0, np.abs(F))
+            X, F, G = Xn, Fn, Gn
+            converged |= active & small & ~stalled
+            active &= ~(stalled | small)
+        return {"U": X.reshape(B, self.H, self.m), "cost": F, "iters": it, "evals": self.n_evals,
+                "converged": converged}

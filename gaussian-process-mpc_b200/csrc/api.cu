@@ -773,6 +773,109 @@ extern "C" int gpmpc_covariance_raw(gpmpc_handle h, int n, int D, const double *
 }
 
 // ---------------------------------------------------------------------------------------------
+// Marginal likelihood and its gradient (src/gpr.py:240-251; the reference differentiates it with autograd)
+// ---------------------------------------------------------------------------------------------
+namespace gpmpc {
+struct MlArg { double inv_lam[kMaxD]; double sf2; int D; };
+// rows[(k)*n + i] = sum_j B_ij Kf_ij d_ijk^2 / lam_k (k < D),  rows[D*n + i] = sum_j B_ij Kf_ij,
+// rows[(D+1)*n + i] = B_ii,   B = alpha alpha^T - Ky^-1
+__global__ void __launch_bounds__(256) ml_grad_rows_kernel(const double *__restrict__ X, int n, MlArg ma,
+                                                            const double *__restrict__ Kinv, int ldk,
+                                                            const double *__restrict__ alpha, double *__restrict__ rows)
+{
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const int D = ma.D;
+    double xi[kMaxD], acc[kMaxD + 1];
+    for (int k = 0; k < D; ++k) { xi[k] = X[(size_t)i * D + k]; acc[k] = 0.0; }
+    acc[D] = 0.0;
+    const double ai = alpha[i];
+    for (int j = lane; j < n; j += 32) {
+        double dk[kMaxD], q = 0.0;
+        for (int k = 0; k < D; ++k) {
+            const double d = xi[k] - X[(size_t)j * D + k];
+            dk[k] = d * d * ma.inv_lam[k];
+            q += dk[k];
+        }
+        const double bk = (ai * alpha[j] - Kinv[(size_t)i * ldk + j]) * ma.sf2 * exp(-0.5 * q);
+        for (int k = 0; k < D; ++k) acc[k] = fma(bk, dk[k], acc[k]);
+        acc[D] += bk;
+    }
+    for (int k = 0; k <= D; ++k) {
+        double v = acc[k];
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) rows[(size_t)k * n + i] = v;
+    }
+    if (lane == 0) rows[(size_t)(D + 1) * n + i] = ai * ai - Kinv[(size_t)i * ldk + i];
+}
+__global__ void dot_rows_kernel(const double *__restrict__ a, const double *__restrict__ b, int n, double *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] * b[i];
+}
+}  // namespace gpmpc
+
+extern "C" int gpmpc_marginal_likelihood(gpmpc_handle h, int a, const double *resid, double *ml, double *grad)
+{
+    if (!h) return GPMPC_ERR_INVALID;
+    if (!h->fitted) return fail(h, GPMPC_ERR_NOT_FIT, "gpmpc_marginal_likelihood: not fitted");
+    if (a < 0 || a >= h->E || !ml) return fail(h, GPMPC_ERR_INVALID, "gpmpc_marginal_likelihood: bad argument");
+    GP_CUDA(h, cudaSetDevice(h->device));
+    const int n = h->n, D = h->D, ld = h->ld;
+    const size_t mat = (size_t)ld * ld;
+    // workspace: r [n] | alpha [n] | prod [n] | rows [(D+2) n] | scal [D+4]
+    const size_t cnt = (size_t)(D + 5) * n + D + 8;
+    GP_CUDA(h, h->gbuf.reserve(cnt * sizeof(double)));
+    double *w = h->gbuf.as<double>();
+    double *r = w; w += n;
+    double *alpha = w; w += n;
+    double *prod = w; w += n;
+    double *rows = w; w += (size_t)(D + 2) * n;
+    double *scal = w;
+    const double *Kinv = h->Kinv.as<double>() + a * mat;
+    const double *rd, *ad;
+    if (resid) {
+        GP_CUDA(h, cudaMemcpyAsync(r, resid, (size_t)n * sizeof(double), cudaMemcpyDefault, h->stream));
+        gpmpc_rowdot_kernel<<<(n + 7) / 8, 256, 0, h->stream>>>(Kinv, ld, n, r, alpha, n);
+        GP_LAUNCH_CHECK(h);
+        rd = r; ad = alpha;
+    } else {
+        rd = h->Y.as<double>() + (size_t)a * ld;
+        ad = h->beta.as<double>() + (size_t)a * ld;
+    }
+    dot_rows_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(rd, ad, n, prod);
+    GP_LAUNCH_CHECK(h);
+    sum_kernel<<<1, 1024, 0, h->stream>>>(prod, n, scal);
+    GP_LAUNCH_CHECK(h);
+    if (grad) {
+        MlArg ma;
+        ma.D = D; ma.sf2 = h->sf_fit[a] * h->sf_fit[a];
+        for (int k = 0; k < kMaxD; ++k) ma.inv_lam[k] = k < D ? 1.0 / h->lam_fit[a][k] : 0.0;
+        ml_grad_rows_kernel<<<(n + 7) / 8, 256, 0, h->stream>>>(h->X.as<double>(), n, ma, Kinv, ld, ad, rows);
+        GP_LAUNCH_CHECK(h);
+        for (int k = 0; k < D + 2; ++k) {
+            sum_kernel<<<1, 1024, 0, h->stream>>>(rows + (size_t)k * n, n, scal + 1 + k);
+            GP_LAUNCH_CHECK(h);
+        }
+    }
+    double hs[kMaxD + 4];
+    GP_CUDA(h, cudaMemcpyAsync(hs, scal, (size_t)(grad ? D + 3 : 1) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    GP_CUDA(h, cudaStreamSynchronize(h->stream));
+    const double value = -0.5 * hs[0] - 0.5 * h->logdet[a] - 0.5 * n * 1.8378770664093453;   // log(2 pi)
+    GP_CUDA(h, cudaMemcpyAsync(ml, &value, sizeof(double), cudaMemcpyDefault, h->stream));
+    double g[kMaxD + 2];
+    if (grad) {
+        for (int k = 0; k < D; ++k) g[k] = 0.25 * hs[1 + k];          // 1/2 tr(B dK/dlog lam_k), dK = Kf d_k^2 / (2 lam_k)
+        g[D] = hs[1 + D];                                             // 1/2 tr(B 2 Kf)
+        g[D + 1] = h->noise[a] * hs[2 + D];                           // 1/2 tr(B 2 sigma_n^2 I)
+        GP_CUDA(h, cudaMemcpyAsync(grad, g, (size_t)(D + 2) * sizeof(double), cudaMemcpyDefault, h->stream));
+    }
+    GP_CUDA(h, cudaStreamSynchronize(h->stream));
+    return GPMPC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Measured ceilings of the FP64 pipe (roofline denominators for the pair kernels)
 // ---------------------------------------------------------------------------------------------
 namespace gpmpc {

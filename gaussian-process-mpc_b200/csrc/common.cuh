@@ -56,6 +56,7 @@ struct gpmpc_ctx {
     double lam_prop[gpmpc::kMaxE][gpmpc::kMaxD], sf_prop[gpmpc::kMaxE];
     std::vector<gpmpc::LambdaGroup> groups;
     bool fitted = false;
+    double logdet[gpmpc::kMaxE];   // log det Ky per output (2 sum log diag L), set by the fit
 
     // device state
     gpmpc::DevBuf X;               // [ld, D]  (rows >= n are zero)

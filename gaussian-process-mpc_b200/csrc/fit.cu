@@ -281,6 +281,21 @@ __global__ void trtri_diag_kernel(const double *__restrict__ L, int ld, int k0, 
     tri_inverse_packed(S, tid, 64, Linv);
 }
 
+// out[0] = 2 * sum_{i<n} log L[i][i]  (single block, fixed reduction order)
+__global__ void __launch_bounds__(1024) logdet_kernel(const double *__restrict__ L, int ld, int n, double *__restrict__ out)
+{
+    __shared__ double sm[1024];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) s += log(L[(size_t)i * ld + i]);
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 512; o; o >>= 1) {
+        if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = 2.0 * sm[0];
+}
+
 // ZT = L^-T (upper triangular, row-major) by blocked forward substitution
 static int invert_factor(gpmpc_ctx *h, const double *L, double *ZT, int np)
 {
@@ -366,8 +381,11 @@ int fit_all(gpmpc_ctx *h, const bool *which)
         GP_LAUNCH_CHECK(h);
         int rc = cholesky_inplace(h, L, np);
         if (rc) return rc;
+        logdet_kernel<<<1, 1024, 0, h->stream>>>(L, ld, n, h->linv.as<double>());   // linv is free after the loop
+        GP_LAUNCH_CHECK(h);
         int info = 0;
         GP_CUDA(h, cudaMemcpyAsync(&info, h->info.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        GP_CUDA(h, cudaMemcpyAsync(&h->logdet[a], h->linv.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         GP_CUDA(h, cudaStreamSynchronize(h->stream));
         if (info != 0) {
             char msg[160];

@@ -10,9 +10,12 @@ Reference quirks that are reproduced on purpose because they move results by mor
     (`src/gpr.py:59,72,85`) -- the same torch expression is used here;
   * the noise term is added through an fp32 identity (`src/gpr.py:170`), so the diagonal gets
     float32(sigma_n^2).
-Hyper-parameter training (`update_hyperparams`, `compute_marginal_likelihood`, `kernel_matrix_gradient`,
-`marginal_likelihood_grad`, `update_Ky_inv_mat`; `src/gpr.py:137-157,173-251,334-370`) is outside the
-rollout hot path and raises NotImplementedError.
+Hyper-parameter training: `compute_marginal_likelihood` evaluates the log marginal
+likelihood on the device from the Cholesky factor (2 sum log diag L instead of the reference's
+log(det(Ky)), which under/overflows for large n, `src/gpr.py:245-247`) and carries an exact analytic
+gradient into autograd; `update_hyperparams` is the reference's Adam loop on top of it
+(`src/gpr.py:334-370`).  `kernel_matrix_gradient`, `marginal_likelihood_grad` (marked wrong in the reference,
+`src/gpr.py:204`) and `update_Ky_inv_mat` (marked "don't use", `src/gpr.py:139`) are not provided.
 """
 from __future__ import annotations
 
@@ -34,6 +37,27 @@ def noise_variance(sigma_n: float) -> float:
     return float(np.float32(float(sigma_n) ** 2))
 
 
+class _MarginalLikelihood(torch.autograd.Function):
+    """ml(log_lambdas, log_sigma_f, log_sigma_n) for the state of the last build; the backward pass hands the
+    device-computed gradient 1/2 tr((alpha alpha^T - Ky^-1) dKy/dtheta) to autograd."""
+
+    @staticmethod
+    def forward(ctx, gpr, log_lambdas, log_sigma_f, log_sigma_n):
+        bundle, a = gpr._bundle_and_index()
+        resid = None
+        if gpr.f_nom is not None:
+            resid = (gpr.y_train - gpr.f_nom(gpr.X_train)).reshape(-1)
+        ml, grad = bundle.marginal_likelihood(a, resid, want_grad=True)
+        ctx.grad = torch.tensor(grad, dtype=F64, device=log_lambdas.device)
+        return torch.full((1, 1), ml, dtype=F64, device=log_lambdas.device)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.reshape(())
+        D = ctx.grad.shape[0] - 2
+        return None, g * ctx.grad[:D], g * ctx.grad[D], g * ctx.grad[D + 1]
+
+
 class GaussianProcessRegression(object):
     """Exact GP regression with the squared-exponential ARD kernel (lambdas are squared length-scales)."""
 
@@ -52,6 +76,10 @@ class GaussianProcessRegression(object):
         self._index = _index
         self._bundle = None                  # standalone 1-output bundle, created at first fit
         self._mats = {}                      # materialised Kf / Ky / Ky_inv
+        # like the reference, the optimiser is bound to the tensors created here (`src/gpr.py:46-49`): after a
+        # set_* call it keeps training the originals
+        self.optimizer = torch.optim.Adam(params=[self.log_lambdas, self.log_sigma_n, self.log_sigma_f],
+                                          lr=0.1, betas=(0.9, 0.999), maximize=True)
 
     # ---- hyper-parameters (src/gpr.py:51-88) ------------------------------------------------
     def set_lambdas(self, lambdas):
@@ -178,13 +206,44 @@ class GaussianProcessRegression(object):
         mean, cov = bundle.predict(a, Xp, covar, targets)
         return mean[:, None], (cov if covar else None)
 
-    # ---- out of scope (hyper-parameter training) -------------------------------------------------
-    def _out_of_scope(self, *_a, **_k):
-        raise NotImplementedError("hyper-parameter training is outside the rollout hot path of this build "
-                                  "(SURVEY.md 8f, row N3)")
+    # ---- hyper-parameter training (src/gpr.py:240-251,334-370) ---------------------------------------
+    def compute_marginal_likelihood(self):
+        """Log marginal likelihood as a (1,1) tensor; differentiable w.r.t. the three log hyper-parameters."""
+        if self.num_train == 0:
+            raise RuntimeError("no training data")
+        return _MarginalLikelihood.apply(self, self.log_lambdas, self.log_sigma_f, self.log_sigma_n)
 
-    update_Ky_inv_mat = _out_of_scope
-    kernel_matrix_gradient = _out_of_scope
-    marginal_likelihood_grad = _out_of_scope
-    compute_marginal_likelihood = _out_of_scope
-    update_hyperparams = _out_of_scope
+    def update_hyperparams(self, num_iters=1000, verbose=True):
+        """Adam ascent on the log marginal likelihood with the reference's schedule: step, rebuild the matrices,
+        stop when every gradient component is below 1e-5."""
+        for it in range(num_iters):
+            self.optimizer.zero_grad()
+            ml = self.compute_marginal_likelihood()
+            ml.backward()
+            self.optimizer.step()
+            self.build_Ky_inv_mat()
+            g_lam = self.log_lambdas.grad.cpu().detach().numpy()
+            g_sf = self.log_sigma_f.grad.item()
+            g_sn = self.log_sigma_n.grad.item()
+            if verbose:
+                print('Iter: ', it)
+                print('ml: ', ml.item())
+                print('lambdas: ', self.get_lambdas())
+                print('sigma_f: ', self.get_sigma_f())
+                print('sigma_n: ', self.get_sigma_n())
+                print('log_lambdas.grad: ', g_lam)
+                print('log_sigma_f.grad: ', g_sf)
+                print('log_sigma_n.grad: ', g_sn)
+                print('----------------------------------------')
+            if (np.abs(g_lam) < 1e-5).all() and np.abs(g_sf) < 1e-5 and np.abs(g_sn) < 1e-5:
+                break
+
+    # ---- not provided -------------------------------------------------------------------------------
+    def _not_provided(self, *_a, **_k):
+        raise NotImplementedError("not provided: the reference marks this method as wrong / unused "
+                                  "(src/gpr.py:139,204); the analytic gradient lives in libgpmpc "
+                                  "(gpmpc_marginal_likelihood)")
+
+    update_Ky_inv_mat = _not_provided
+    kernel_matrix_gradient = _not_provided
+    marginal_likelihood_grad = _not_provided

@@ -84,6 +84,14 @@ int gpmpc_kernel_matrix(gpmpc_handle h, int a, int p, const double *Xs, double *
  * add_noise).  Replaces predict_latent_vars with f_nom = None (src/gpr.py:285-332).                  */
 int gpmpc_predict(gpmpc_handle h, int a, int p, const double *Xs, double *mean, double *cov, int add_noise);
 
+/* Log marginal likelihood of output a for the hyper-parameters of the last fit,
+ *   ml = -1/2 r^T Ky^-1 r - 1/2 log det Ky - n/2 log 2 pi,   r = resid (or the training targets if resid == NULL),
+ * with log det Ky = 2 sum log diag(L) from the Cholesky factor, and (if grad != NULL) its gradient w.r.t.
+ * [log lambda_1..D, log sigma_f, log sigma_n] = 1/2 tr((alpha alpha^T - Ky^-1) dKy/dtheta), alpha = Ky^-1 r.
+ * Replaces compute_marginal_likelihood + the autograd backward used by update_hyperparams
+ * (src/gpr.py:240-251,334-370).                                                                       */
+int gpmpc_marginal_likelihood(gpmpc_handle h, int a, const double *resid, double *ml, double *grad);
+
 /* Exact moments of all E GP outputs for B Gaussian inputs N(U_b, S_b).  S is [B,D] (diagonal variances,
  * s_is_full = 0) or [B,D,D] (full covariance, s_is_full = 1).  mean[B,E], var[B,E] (latent variance, no
  * noise term).  Replaces mean_prop_torch + variance_prop_torch called on a fitted bundle

@@ -75,6 +75,13 @@ def predict(X, y, lambdas, sigma_f, sigma_n, X_pred, covar=False, targets=False,
     return mean, cov
 
 
+def marginal_likelihood(X, y, lambdas, sigma_f, sigma_n):
+    """Log marginal likelihood, `src/gpr.py:240-247` (f_nom = None): -1/2 y^T Ky^-1 y - 1/2 log det Ky - n/2 log 2pi."""
+    f = fit(X, y, lambdas, sigma_f, sigma_n)
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    return float(-0.5 * y @ f["Ky_inv"] @ y - 0.5 * np.log(np.linalg.det(f["Ky"])) - 0.5 * len(y) * np.log(2 * np.pi))
+
+
 # --------------------------------------------------------------------------------------------
 # Moment matching (src/tools/uncertainty_prop.py) -- general (full) input covariance S
 # --------------------------------------------------------------------------------------------

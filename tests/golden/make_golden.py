@@ -194,6 +194,33 @@ def shipped_case():
     return out
 
 
+def hyper_cases():
+    """Marginal likelihood, its autograd gradient and three Adam steps (src/gpr.py:240-251,334-370)."""
+    import io, contextlib
+    out = {}
+    rng = np.random.default_rng(21)
+    n, D = 60, 3
+    X = rng.normal(size=(n, D)); y = np.sin(X @ np.array([1.0, 0.5, -0.7])) + 0.1 * rng.normal(size=n)
+    g = GaussianProcessRegression(D)
+    g.set_lambdas(np.array([0.8, 1.5, 2.2])); g.set_sigma_f(np.float64(1.3)); g.set_sigma_n(np.float64(0.25))
+    # the optimiser of the reference keeps the tensors created in __init__ (SURVEY B.8): rebuild it on the new ones
+    g.optimizer = torch.optim.Adam(params=[g.log_lambdas, g.log_sigma_n, g.log_sigma_f], lr=0.1, betas=(0.9, 0.999),
+                                   maximize=True)
+    g.append_train_data(X, y)
+    ml = g.compute_marginal_likelihood()
+    ml.backward()
+    out.update({"hy_X": X, "hy_y": y, "hy_lam0": g.get_lambdas(), "hy_sf0": g.get_sigma_f(), "hy_sn0": g.get_sigma_n(),
+                "hy_ml": ml.item(), "hy_dlam": g.log_lambdas.grad.numpy().copy(),
+                "hy_dsf": g.log_sigma_f.grad.item(), "hy_dsn": g.log_sigma_n.grad.item()})
+    g.optimizer.zero_grad()
+    g.build_Ky_inv_mat()
+    with contextlib.redirect_stdout(io.StringIO()):
+        g.update_hyperparams(num_iters=3)
+    out.update({"hy_lam3": g.get_lambdas(), "hy_sf3": g.get_sigma_f(), "hy_sn3": g.get_sigma_n(),
+                "hy_ml3": g.compute_marginal_likelihood().item()})
+    return out
+
+
 def cost_kats():
     """Deterministic known-answer tests of the reference, src/test/test_mpc.py:15-57,245-274."""
     out = {}
@@ -219,4 +246,5 @@ if __name__ == "__main__":
     np.savez_compressed(os.path.join(OUT, "rollout.npz"), **rollout_cases())
     np.savez_compressed(os.path.join(OUT, "shipped.npz"), **shipped_case())
     np.savez_compressed(os.path.join(OUT, "cost_kat.npz"), **cost_kats())
+    np.savez_compressed(os.path.join(OUT, "hyper.npz"), **hyper_cases())
     print("golden vectors written to", OUT)

@@ -385,3 +385,27 @@ def test_errors_are_reported(gp):
     X = np.zeros((3, 2))                       # three identical points and no noise: Ky is singular
     with pytest.raises(gp.GpmpcError):
         gpr.append_train_data(X, np.zeros(3))
+
+
+def test_marginal_likelihood_gradient_and_adam_steps(gp):
+    """ml, its gradient (the reference uses autograd through inv/det) and three Adam steps."""
+    g = golden("hyper")
+    gpr = gp.GaussianProcessRegression(3)
+    gpr.set_lambdas(np.asarray(g["hy_lam0"], dtype=np.float64)); gpr.set_sigma_f(np.float64(g["hy_sf0"]))
+    gpr.set_sigma_n(np.float64(g["hy_sn0"]))
+    gpr.optimizer = torch.optim.Adam(params=[gpr.log_lambdas, gpr.log_sigma_n, gpr.log_sigma_f], lr=0.1,
+                                     betas=(0.9, 0.999), maximize=True)
+    gpr.append_train_data(g["hy_X"], g["hy_y"])
+    ml = gpr.compute_marginal_likelihood()
+    assert ml.shape == (1, 1)
+    close(ml.item(), float(g["hy_ml"]), 1e-9)
+    ml.backward()
+    norm_close(gpr.log_lambdas.grad.cpu().numpy(), g["hy_dlam"], 1e-7)
+    close(gpr.log_sigma_f.grad.item(), float(g["hy_dsf"]), 1e-7)
+    close(gpr.log_sigma_n.grad.item(), float(g["hy_dsn"]), 1e-6)     # fp32 noise eye in the reference's graph
+    gpr.optimizer.zero_grad()
+    gpr.update_hyperparams(num_iters=3, verbose=False)
+    norm_close(gpr.get_lambdas(), g["hy_lam3"], 1e-6)
+    close(gpr.get_sigma_f(), float(g["hy_sf3"]), 1e-6)
+    close(gpr.get_sigma_n(), float(g["hy_sn3"]), 1e-6)
+    close(gpr.compute_marginal_likelihood().item(), float(g["hy_ml3"]), 1e-6)

@@ -173,3 +173,31 @@ def test_sharded_gather_world2_gloo(B):
         assert p.exitcode == 0
     assert out[0][0] and out[1][0]
     assert out[0][1] + out[1][1] == B        # shards cover the batch exactly once
+
+
+def test_batched_solver_matches_lbfgsb_on_box_constrained_quadratics():
+    """N1 driver (lock-step projected L-BFGS over many problems) against scipy on a fake evaluator."""
+    from scipy.optimize import minimize
+    from gpmpc_b200 import BatchedRollouts, BatchedSolver
+    rng = np.random.default_rng(0)
+    B, H, m = 6, 4, 2
+    n = H * m
+    A = rng.normal(size=(B, n, n)); Q = np.einsum("bij,bkj->bik", A, A) + 0.5 * np.eye(n)
+    c = rng.normal(size=(B, n)) * 3
+
+    def fake(x0, U, gamma, last_u=None, host_out=True, want_grad=True):
+        X = U.reshape(U.shape[0], -1)
+        QX = np.einsum("bij,bj->bi", Q, X)
+        f = 0.5 * np.einsum("bi,bi->b", X, QX) + np.einsum("bi,bi->b", c, X)
+        f[3] = np.where(np.abs(X[3]).max() > 0.9, np.nan, f[3])      # a NaN region must be treated as a rejected step
+        return f, (QX + c).reshape(U.shape)
+
+    sol = BatchedSolver(BatchedRollouts(evaluate_fn=fake), H, m, lb=[-1, -1], ub=[1, 1], max_iter=300, gtol=1e-8)
+    r = sol.solve(np.zeros((B, 3)), np.full(B, -1.0))
+    for b in range(B):
+        if b == 3:
+            assert np.isfinite(r["cost"][b]) and np.abs(r["U"][b]).max() <= 0.9 + 1e-12
+            continue
+        ref = minimize(lambda x: (0.5 * x @ Q[b] @ x + c[b] @ x, Q[b] @ x + c[b]), np.zeros(n), jac=True, method="L-BFGS-B",
+                       bounds=[(-1, 1)] * n, options={"gtol": 1e-10, "ftol": 1e-15})
+        assert r["converged"][b] and abs(r["cost"][b] - ref.fun) < 1e-8 and np.max(np.abs(r["U"][b].ravel() - ref.x)) < 1e-4

@@ -166,3 +166,20 @@ def test_ref_port_matches_reference():
         c, grad, means, vars_ = p.cost_and_grad(g[f"{name}_x0"], g[f"{name}_U"])
         assert abs(c - float(g[f"{name}_cost"])) < 1e-9 * max(1, abs(c))
         np.testing.assert_allclose(grad, g[f"{name}_grad"], rtol=1e-7, atol=1e-9)
+
+
+def test_marginal_likelihood_and_reference_gradient():
+    """ML value, and the reference's autograd gradient checked by central differences of the oracle."""
+    g = golden("hyper")
+    X, y = g["hy_X"], g["hy_y"]
+    lam, sf, sn = g["hy_lam0"], float(g["hy_sf0"]), float(g["hy_sn0"])
+    sn_eff = float(np.float32(sn ** 2)) ** 0.5
+    ml = orc.marginal_likelihood(X, y, lam, sf, sn_eff)
+    assert abs(ml - float(g["hy_ml"])) < 1e-8 * abs(ml)
+    h = 1e-6
+    for k in range(3):
+        e = np.zeros(3); e[k] = h
+        fd = (orc.marginal_likelihood(X, y, lam * np.exp(e), sf, sn_eff) - orc.marginal_likelihood(X, y, lam * np.exp(-e), sf, sn_eff)) / (2 * h)
+        assert abs(fd - g["hy_dlam"][k]) < 1e-5 * max(1, abs(fd))
+    fd = (orc.marginal_likelihood(X, y, lam, sf * np.exp(h), sn_eff) - orc.marginal_likelihood(X, y, lam, sf * np.exp(-h), sn_eff)) / (2 * h)
+    assert abs(fd - float(g["hy_dsf"])) < 1e-5 * abs(fd)
