@@ -21,6 +21,7 @@ SIGNATURES = {
     "gpmpc_num_train": (c_int, [_P]),
     "gpmpc_fit": (c_int, [_P, c_int, _P, _P, _P, _P, _P]),
     "gpmpc_refit_output": (c_int, [_P, c_int, _P, _P, c_double, c_double]),
+    "gpmpc_append_point": (c_int, [_P, _P, _P]),
     "gpmpc_set_propagation_hypers": (c_int, [_P, _P, _P]),
     "gpmpc_get_matrix": (c_int, [_P, c_int, c_int, _P]),
     "gpmpc_kernel_matrix": (c_int, [_P, c_int, c_int, _P, _P]),

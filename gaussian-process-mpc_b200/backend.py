@@ -85,6 +85,17 @@ class GPBundle:
         check(self.h, self.lib.gpmpc_fit(self.h, n, _ptr(X), _ptr(Y), _ptr(lam), _ptr(sf), _ptr(nv)), "gpmpc_fit")
         self.n = n
 
+    def append_point(self, x, y):
+        """Bordered update for one observation; returns False when a full fit is required instead."""
+        self._sync_stream()
+        x = as_f64(x).reshape(self.D); y = as_f64(y).reshape(self.E)
+        rc = self.lib.gpmpc_append_point(self.h, _ptr(x), _ptr(y))
+        if rc == 1:
+            return False
+        check(self.h, rc, "gpmpc_append_point")
+        self.n += 1
+        return True
+
     def refit_output(self, a, y, lambdas_a, sigma_f_a, noise_var_a):
         self._sync_stream()
         y = None if y is None else as_f64(y).reshape(-1)

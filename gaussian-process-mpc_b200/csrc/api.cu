@@ -106,6 +106,14 @@ static int fetch_host(gpmpc_ctx *h, const double *src, double *dst, size_t cnt)
 }
 
 namespace gpmpc {
+struct KsArg { double inv_lam[kMaxD]; double sf2; };     // fit-time kernel hyper-parameters of one output
+static KsArg ks_arg(const gpmpc_ctx *h, int a)
+{
+    KsArg k;
+    for (int i = 0; i < kMaxD; ++i) k.inv_lam[i] = i < h->D ? 1.0 / h->lam_fit[a][i] : 0.0;
+    k.sf2 = h->sf_fit[a] * h->sf_fit[a];
+    return k;
+}
 __global__ void transpose_y_kernel(const double *__restrict__ Y, int n, int E, int ld, double *__restrict__ Yt)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -187,6 +195,110 @@ extern "C" int gpmpc_refit_output(gpmpc_handle h, int a, const double *y, const 
     return fit_all(h, which);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Incremental refit: bordered update of Ky^-1 for one new training point
+// ---------------------------------------------------------------------------------------------
+namespace gpmpc {
+// kv[i] = sf^2 exp(-1/2 sum_k (x_ik - xs_k)^2 / lam_k), i < n
+__global__ void knew_kernel(const double *__restrict__ X, int n, int D, KsArg hp, const double *__restrict__ xs,
+                            double *__restrict__ kv)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double q = 0.0;
+    for (int k = 0; k < D; ++k) { const double d = X[(size_t)i * D + k] - xs[k]; q = fma(d * d, hp.inv_lam[k], q); }
+    kv[i] = hp.sf2 * exp(-0.5 * q);
+}
+// scal[0] = kappa - sum_i kv_i v_i  (Schur complement), scal[1] = 1 / scal[0]      (single block, fixed order)
+__global__ void __launch_bounds__(1024) schur_kernel(const double *__restrict__ kv, const double *__restrict__ v, int n,
+                                                      double kappa, double *__restrict__ scal)
+{
+    __shared__ double sm[1024];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) s = fma(kv[i], v[i], s);
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 512; o; o >>= 1) { if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) { const double sc = kappa - sm[0]; scal[0] = sc; scal[1] = 1.0 / sc; }
+}
+// Kinv[0:n,0:n] += v v^T / s;  Kinv[i][n] = Kinv[n][i] = -v_i / s;  Kinv[n][n] = 1 / s
+__global__ void border_update_kernel(double *__restrict__ Kinv, int ld, int n, const double *__restrict__ v,
+                                     const double *__restrict__ scal)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i > n || j > n) return;
+    const double is = scal[1];
+    double *p = Kinv + (size_t)i * ld + j;
+    if (i < n && j < n) *p = fma(v[i] * is, v[j], *p);
+    else if (i == n && j == n) *p = is;
+    else *p = -(i == n ? v[j] : v[i]) * is;
+}
+}  // namespace gpmpc
+
+extern "C" int gpmpc_append_point(gpmpc_handle h, const double *x, const double *y)
+{
+    if (!h) return GPMPC_ERR_INVALID;
+    if (!x || !y) return fail(h, GPMPC_ERR_INVALID, "gpmpc_append_point: null");
+    if (!h->fitted || h->n <= 0) return GPMPC_REFIT_NEEDED;
+    if (h->n + 1 > h->ld) return GPMPC_REFIT_NEEDED;
+    GP_CUDA(h, cudaSetDevice(h->device));
+    const int n = h->n, D = h->D, E = h->E, ld = h->ld;
+    const size_t mat = (size_t)ld * ld;
+    double xh[kMaxD], yh[kMaxE];
+    int rc;
+    if ((rc = fetch_host(h, x, xh, D))) return rc;
+    if ((rc = fetch_host(h, y, yh, E))) return rc;
+    // workspace: xs [D] | kv [ld] | v [ld] | scal [2 * E]
+    GP_CUDA(h, h->gbuf.reserve(((size_t)2 * ld + kMaxD + 2 * kMaxE + 8) * sizeof(double)));
+    double *w = h->gbuf.as<double>();
+    double *xs = w; w += kMaxD;
+    double *kv = w; w += ld;
+    double *v = w; w += ld;
+    double *scal = w;
+    GP_CUDA(h, cudaMemcpyAsync(xs, xh, D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    // first pass: Schur complements of all outputs (nothing is modified until every one is known to be positive)
+    std::vector<double> hs(2 * E);
+    for (int a = 0; a < E; ++a) {
+        knew_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->X.as<double>(), n, D, ks_arg(h, a), xs, kv);
+        GP_LAUNCH_CHECK(h);
+        gpmpc_rowdot_kernel<<<(n + 7) / 8, 256, 0, h->stream>>>(h->Kinv.as<double>() + a * mat, ld, n, kv, v, n);
+        GP_LAUNCH_CHECK(h);
+        schur_kernel<<<1, 1024, 0, h->stream>>>(kv, v, n, h->sf_fit[a] * h->sf_fit[a] + h->noise[a], scal + 2 * a);
+        GP_LAUNCH_CHECK(h);
+    }
+    GP_CUDA(h, cudaMemcpyAsync(hs.data(), scal, 2 * E * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    GP_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int a = 0; a < E; ++a)
+        if (!(hs[2 * a] > 0.0) || !std::isfinite(hs[2 * a])) return GPMPC_REFIT_NEEDED;
+    // second pass: apply
+    GP_CUDA(h, cudaMemcpyAsync(h->X.as<double>() + (size_t)n * D, xh, D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    for (int a = 0; a < E; ++a) {
+        double *Kinv = h->Kinv.as<double>() + a * mat;
+        knew_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->X.as<double>(), n, D, ks_arg(h, a), xs, kv);
+        GP_LAUNCH_CHECK(h);
+        gpmpc_rowdot_kernel<<<(n + 7) / 8, 256, 0, h->stream>>>(Kinv, ld, n, kv, v, n);
+        GP_LAUNCH_CHECK(h);
+        dim3 blk(32, 8), grid((n + 1 + 31) / 32, (n + 1 + 7) / 8);
+        border_update_kernel<<<grid, blk, 0, h->stream>>>(Kinv, ld, n, v, scal + 2 * a);
+        GP_LAUNCH_CHECK(h);
+        GP_CUDA(h, cudaMemcpyAsync(h->Y.as<double>() + (size_t)a * ld + n, &yh[a], sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        h->logdet[a] += std::log(hs[2 * a]);
+    }
+    GP_CUDA(h, cudaStreamSynchronize(h->stream));     // xh / yh are stack buffers
+    h->n = n + 1;
+    for (int a = 0; a < E; ++a) {
+        // beta = Ky^-1 y over the n+1 points, then the weight matrix
+        gpmpc_rowdot_kernel<<<(n + 1 + 7) / 8, 256, 0, h->stream>>>(h->Kinv.as<double>() + a * mat, ld, n + 1,
+                                                                   h->Y.as<double>() + (size_t)a * ld,
+                                                                   h->beta.as<double>() + (size_t)a * ld, n + 1);
+        GP_LAUNCH_CHECK(h);
+        if ((rc = derive_weights(h, a))) return rc;
+    }
+    h->tape_B = h->tape_H = 0;
+    return GPMPC_OK;
+}
+
 extern "C" int gpmpc_set_propagation_hypers(gpmpc_handle h, const double *lambdas, const double *sigma_f)
 {
     if (!h) return GPMPC_ERR_INVALID;
@@ -263,7 +375,6 @@ extern "C" int gpmpc_get_matrix(gpmpc_handle h, int which, int a, double *out)
 // K(X*, X) and the posterior (src/gpr.py:253-332)
 // ---------------------------------------------------------------------------------------------
 namespace gpmpc {
-struct KsArg { double inv_lam[kMaxD]; double sf2; };
 __global__ void kstar_kernel(const double *__restrict__ Xs, int p, const double *__restrict__ X, int n, int D, KsArg hp,
                              double *__restrict__ out, int ldo, int pp, int np)
 {
@@ -280,13 +391,6 @@ __global__ void kstar_kernel(const double *__restrict__ Xs, int p, const double 
         v = hp.sf2 * exp(-0.5 * q);
     }
     out[(size_t)i * ldo + j] = v;
-}
-static KsArg ks_arg(const gpmpc_ctx *h, int a)
-{
-    KsArg k;
-    for (int i = 0; i < kMaxD; ++i) k.inv_lam[i] = i < h->D ? 1.0 / h->lam_fit[a][i] : 0.0;
-    k.sf2 = h->sf_fit[a] * h->sf_fit[a];
-    return k;
 }
 // cov[i][j] = K**[i][j] - sum_k T[i][k] Ks[j][k] (+ noise on the diagonal)
 __global__ void post_cov_kernel(const double *__restrict__ Xs, int p, int D, KsArg hp, const double *__restrict__ TK, int ldt,

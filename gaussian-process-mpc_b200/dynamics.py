@@ -52,6 +52,8 @@ class Dynamics(object):
         self._X = None          # [n, D] device tensor shared by all members
         self._Y = None          # [n, E]
         self._prop_key = None   # hyper-parameter snapshot last pushed to the device
+        self._fit_key = None    # hyper-parameter snapshot of the last full fit
+        self.incremental = True # use gpmpc_append_point for single observations
         self._tape_serial = 0
 
     # ---- data ingestion (src/dynamics.py:39-60) ----------------------------------------------
@@ -81,6 +83,15 @@ class Dynamics(object):
         else:
             self._X = torch.cat((self._X, x), dim=0)
             self._Y = torch.cat((self._Y, y), dim=0)
+        # one new observation and unchanged hyper-parameters: bordered O(n^2) update (the closed loop of
+        # src/simulator.py:55 appends one point per step); otherwise, or when the library asks for it, refit
+        if (self.incremental and self._bundle is not None and x.shape[0] == 1
+                and self._fit_key == tuple(g._hyper_key() for g in self.gpr_err)
+                and self._bundle.append_point(x[0], y[0])):
+            for g in self.gpr_err:
+                g.num_train = self._X.shape[0]
+                g._mats = {}
+            return
         self._fit_all()
 
     def _collect_hypers(self):
@@ -95,6 +106,7 @@ class Dynamics(object):
         lam, sf, nv = self._collect_hypers()
         self._bundle.fit(self._X, self._Y, lam, sf, nv)
         self._prop_key = tuple(g._hyper_key() for g in self.gpr_err)
+        self._fit_key = self._prop_key
         for g in self.gpr_err:
             g.num_train = self._X.shape[0]
             g._mats = {}
@@ -102,6 +114,7 @@ class Dynamics(object):
     def _refit_member(self, index, lam, sf, nv):
         self._bundle.refit_output(index, None, lam, sf, nv)
         self._prop_key = None            # forces a re-sync of the other members' propagation hypers
+        self._fit_key = None             # mixed fit state: the next append does a full fit
 
     def _sync_propagation_hypers(self):
         """The reference reads lambdas / sigma_f at rollout time (src/dynamics.py:171,173) while Ky_inv

@@ -69,6 +69,15 @@ int gpmpc_fit(gpmpc_handle h, int n, const double *X, const double *Y, const dou
 int gpmpc_refit_output(gpmpc_handle h, int a, const double *y, const double *lambdas_a, double sigma_f_a,
                        double noise_var_a);
 
+/* Append ONE observation (x[D], y[E]) to a fitted bundle with a bordered (rank-1) update of every Ky^-1, beta,
+ * log det Ky and weight matrix: O(E n^2) instead of the O(E n^3) rebuild the reference performs on every
+ * closed-loop step (src/simulator.py:55 -> src/gpr.py:122,171; its own attempt at this, src/gpr.py:137-157, is
+ * marked "don't use").  Returns GPMPC_OK, or GPMPC_REFIT_NEEDED (> 0, not an error) when the padded layout
+ * is full or a Schur complement is not positive: the caller then calls gpmpc_fit with all the data, which also
+ * bounds the drift of repeated updates to at most 63 of them.                                        */
+#define GPMPC_REFIT_NEEDED 1
+int gpmpc_append_point(gpmpc_handle h, const double *x, const double *y);
+
 /* Change the length-scales / amplitudes used by the MOMENT-MATCHING formulas without refitting Ky^-1.
  * The reference reads log_lambdas / sigma_f at rollout time (src/dynamics.py:171,173) but Ky_inv from the
  * last build (src/dynamics.py:170), so setters without a rebuild affect only the propagation.           */

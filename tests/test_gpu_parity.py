@@ -409,3 +409,35 @@ def test_marginal_likelihood_gradient_and_adam_steps(gp):
     close(gpr.get_sigma_f(), float(g["hy_sf3"]), 1e-6)
     close(gpr.get_sigma_n(), float(g["hy_sn3"]), 1e-6)
     close(gpr.compute_marginal_likelihood().item(), float(g["hy_ml3"]), 1e-6)
+
+
+def test_incremental_append_matches_full_refit(gp):
+    """one-point bordered updates (closed loop, src/simulator.py:55) vs rebuilding from scratch."""
+    n0, extra, E, m = 250, 9, 2, 1                 # 250 -> 259 crosses the 256 padding boundary: forces one full refit
+    S, A, nxt, rng = _synth(n0 + extra, E, m, seed=8)
+    def make():
+        d = gp.Dynamics(E, m)
+        for a in range(E):
+            d.gpr_err[a].set_lambdas(np.full(E + m, 1.5)); d.gpr_err[a].set_sigma_n(np.float64(0.1))
+        return d
+    inc = make()
+    inc.append_train_data(S[:n0], A[:n0], nxt[:n0])
+    for i in range(n0, n0 + extra):
+        inc.append_train_data(S[i], A[i], nxt[i])
+    full = make()
+    full.append_train_data(S, A, nxt)
+    assert inc.gpr_err[0].num_train == n0 + extra == full.gpr_err[0].num_train
+    for a in range(E):
+        norm_close(inc.gpr_err[a].Ky_inv.cpu().numpy(), full.gpr_err[a].Ky_inv.cpu().numpy(), 1e-9)
+        close(inc.gpr_err[a].compute_marginal_likelihood().item(), full.gpr_err[a].compute_marginal_likelihood().item(), 1e-9)
+    x0 = np.array([0.2, -0.1]); U = rng.uniform(-0.3, 0.3, (4, m))
+    mi, ci = inc.forward_propagate(4, x0, U)
+    mf, cf = full.forward_propagate(4, x0, U)
+    norm_close(mi, mf, 1e-9)
+    assert np.max(np.abs(ci - cf)) <= 1e-8 * max(np.max(np.abs(cf)), 1e-3)
+    # a changed hyper-parameter must trigger a full rebuild on the next append (reference semantics)
+    inc.gpr_err[0].set_sigma_n(np.float64(0.2)); full2 = make(); full2.gpr_err[0].set_sigma_n(np.float64(0.2))
+    Sx, Ax, nx, _ = _synth(1, E, m, seed=9)
+    inc.append_train_data(Sx[0], Ax[0], nx[0])
+    full2.append_train_data(np.concatenate([S, Sx]), np.concatenate([A, Ax]), np.concatenate([nxt, nx]))
+    norm_close(inc.gpr_err[0].Ky_inv.cpu().numpy(), full2.gpr_err[0].Ky_inv.cpu().numpy(), 1e-9)
