@@ -28,6 +28,7 @@ SIGNATURES = {
     "gpmpc_predict": (c_int, [_P, c_int, c_int, _P, _P, _P, c_int]),
     "gpmpc_marginal_likelihood": (c_int, [_P, c_int, _P, _P, _P]),
     "gpmpc_moment_match": (c_int, [_P, c_int, _P, _P, c_int, _P, _P]),
+    "gpmpc_moment_match_cov": (c_int, [_P, c_int, _P, _P, _P, _P]),
     "gpmpc_moment_match_raw": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P, c_double, _P, _P, _P, _P]),
     "gpmpc_covariance_raw": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, c_double, c_double, _P, _P,
                                      c_double, c_double, c_int, _P]),

@@ -160,6 +160,16 @@ class GPBundle:
               "gpmpc_moment_match")
         return mean, var
 
+    def moment_match_cov(self, U, S):
+        """U [B,D], full S [B,D,D] -> mean [B,E], full output covariance [B,E,E] (numpy)."""
+        self._sync_stream()
+        U = as_f64(U); S = as_f64(S)
+        B = U.shape[0]
+        mean = np.empty((B, self.E)); cov = np.empty((B, self.E, self.E))
+        check(self.h, self.lib.gpmpc_moment_match_cov(self.h, B, _ptr(U), _ptr(S), _ptr(mean), _ptr(cov)),
+              "gpmpc_moment_match_cov")
+        return mean, cov
+
     def rollout(self, x0, U, out_device=True):
         """x0 [B,E], U [B,H,m] -> means [B,H+1,E], vars [B,H+1,E]; keeps the tape for rollout_vjp."""
         self._sync_stream()

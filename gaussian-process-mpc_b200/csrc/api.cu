@@ -704,12 +704,31 @@ static void full_setup(int D, const double *lam, const double *u, const double *
 
 }  // namespace gpmpc
 
+static int moment_match_impl(gpmpc_handle h, int B, const double *U, const double *S, int s_is_full,
+                             double *mean, double *var, double *cov);
+static int cov_core(gpmpc_ctx *h, int n, int D, const double *l1, const double *l2, const double *uh, const double *Sh,
+                    const double *Xd, const double *b1, const double *b2, double mean1, double mean2, double sf1,
+                    double sf2, int bugcompat, double *rows, double *scal, double *out_host);
+
 extern "C" int gpmpc_moment_match(gpmpc_handle h, int B, const double *U, const double *S, int s_is_full,
                                   double *mean, double *var)
 {
+    return moment_match_impl(h, B, U, S, s_is_full, mean, var, nullptr);
+}
+
+extern "C" int gpmpc_moment_match_cov(gpmpc_handle h, int B, const double *U, const double *S, double *mean,
+                                      double *cov)
+{
+    if (!cov) return fail(h, GPMPC_ERR_INVALID, "gpmpc_moment_match_cov: cov is null");
+    return moment_match_impl(h, B, U, S, 1, mean, nullptr, cov);
+}
+
+static int moment_match_impl(gpmpc_handle h, int B, const double *U, const double *S, int s_is_full,
+                             double *mean, double *var, double *cov)
+{
     if (!h) return GPMPC_ERR_INVALID;
     if (!h->fitted) return fail(h, GPMPC_ERR_NOT_FIT, "gpmpc_moment_match: not fitted");
-    if (B <= 0 || !U || !S || !mean || !var) return fail(h, GPMPC_ERR_INVALID, "gpmpc_moment_match: bad argument");
+    if (B <= 0 || !U || !S || !mean || (!var && !cov)) return fail(h, GPMPC_ERR_INVALID, "gpmpc_moment_match: bad argument");
     GP_CUDA(h, cudaSetDevice(h->device));
     const int D = h->D, E = h->E, n = h->n, ld = h->ld;
     if (!s_is_full) {
@@ -750,8 +769,27 @@ extern "C" int gpmpc_moment_match(gpmpc_handle h, int B, const double *U, const 
             mh[(size_t)b * E + a] = m;
             vh[(size_t)b * E + a] = h->sf_prop[a] * h->sf_prop[a] - fs.var_pref * r2[1] - m * m;
         }
+    std::vector<double> ch;
+    if (cov) {
+        // full E x E output covariance: variances on the diagonal, cross-covariances from the published formula
+        ch.assign((size_t)B * E * E, 0.0);
+        for (int b = 0; b < B; ++b)
+            for (int a = 0; a < E; ++a) {
+                ch[((size_t)b * E + a) * E + a] = vh[(size_t)b * E + a];
+                for (int c2 = a + 1; c2 < E; ++c2) {
+                    double c = 0.0;
+                    if ((rc = cov_core(h, n, D, h->lam_prop[a], h->lam_prop[c2], &Uh[(size_t)b * D], &Sh[(size_t)b * D * D],
+                                       h->X.as<double>(), h->beta.as<double>() + (size_t)a * ld,
+                                       h->beta.as<double>() + (size_t)c2 * ld, mh[(size_t)b * E + a], mh[(size_t)b * E + c2],
+                                       h->sf_prop[a], h->sf_prop[c2], 0, rows, scal, &c))) return rc;
+                    ch[((size_t)b * E + a) * E + c2] = c;
+                    ch[((size_t)b * E + c2) * E + a] = c;
+                }
+            }
+        GP_CUDA(h, cudaMemcpyAsync(cov, ch.data(), ch.size() * sizeof(double), cudaMemcpyDefault, h->stream));
+    }
     GP_CUDA(h, cudaMemcpyAsync(mean, mh.data(), mh.size() * sizeof(double), cudaMemcpyDefault, h->stream));
-    GP_CUDA(h, cudaMemcpyAsync(var, vh.data(), vh.size() * sizeof(double), cudaMemcpyDefault, h->stream));
+    if (var) GP_CUDA(h, cudaMemcpyAsync(var, vh.data(), vh.size() * sizeof(double), cudaMemcpyDefault, h->stream));
     GP_CUDA(h, cudaStreamSynchronize(h->stream));
     return GPMPC_OK;
 }
@@ -822,6 +860,37 @@ extern "C" int gpmpc_moment_match_raw(gpmpc_handle h, int n, int D, const double
     return GPMPC_OK;
 }
 
+// cov = sf1^2 sf2^2 |R|^-1/2 sum_ij beta1_i beta2_j k1_i k2_j exp(1/2 z_ij^T T z_ij) - mean1 mean2 on device vectors
+// (src/tools/uncertainty_prop.py:212-236 / 433-465); rows [n] and scal [1] are device scratch.
+static int cov_core(gpmpc_ctx *h, int n, int D, const double *l1, const double *l2, const double *uh, const double *Sh,
+                    const double *Xd, const double *b1, const double *b2, double mean1, double mean2, double sf1,
+                    double sf2, int bugcompat, double *rows, double *scal, double *out_host)
+{
+    // R = S (Lam1^-1 + Lam2^-1) + I, T = R^-1 S  (:439-443)
+    double R[kMaxD * kMaxD], Ri[kMaxD * kMaxD], T[kMaxD * kMaxD];
+    for (int r = 0; r < D; ++r) for (int k = 0; k < D; ++k) R[r * D + k] = Sh[r * D + k] * (1.0 / l1[k] + 1.0 / l2[k]) + (r == k ? 1.0 : 0.0);
+    const double det = host_lu(D, R, Ri);
+    for (int r = 0; r < D; ++r) for (int k = 0; k < D; ++k) {
+        double acc = 0.0;
+        for (int q = 0; q < D; ++q) acc += Ri[r * D + q] * Sh[q * D + k];
+        T[r * D + k] = acc;
+    }
+    CovArg ca;
+    ca.D = D; ca.bugcompat = bugcompat ? 1 : 0;
+    for (int r = 0; r < D; ++r) for (int k = 0; k < D; ++k)
+        ca.T[r * D + k] = bugcompat ? T[r * D + k] : 0.5 * (T[r * D + k] + T[k * D + r]);
+    for (int k = 0; k < D; ++k) { ca.u[k] = uh[k]; ca.il1[k] = 1.0 / l1[k]; ca.il2[k] = 1.0 / l2[k]; }
+    cov_rows_kernel<<<(n + 7) / 8, 256, 0, h->stream>>>(Xd, n, ca, b1, b2, rows);
+    GP_LAUNCH_CHECK(h);
+    sum_kernel<<<1, 1024, 0, h->stream>>>(rows, n, scal);
+    GP_LAUNCH_CHECK(h);
+    double r = 0.0;
+    GP_CUDA(h, cudaMemcpyAsync(&r, scal, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    GP_CUDA(h, cudaStreamSynchronize(h->stream));
+    *out_host = sf1 * sf1 * sf2 * sf2 * std::pow(det, -0.5) * r - mean1 * mean2;
+    return GPMPC_OK;
+}
+
 extern "C" int gpmpc_covariance_raw(gpmpc_handle h, int n, int D, const double *lambdas1, const double *lambdas2,
                                     const double *u, const double *S, const double *X, double mean1, double mean2,
                                     const double *beta1, const double *beta2, double sigma_f1, double sigma_f2,
@@ -837,20 +906,6 @@ extern "C" int gpmpc_covariance_raw(gpmpc_handle h, int n, int D, const double *
     if ((rc = fetch_host(h, lambdas2, l2, D))) return rc;
     if ((rc = fetch_host(h, u, uh, D))) return rc;
     if ((rc = fetch_host(h, S, Sh, (size_t)D * D))) return rc;
-    // R = S (Lam1^-1 + Lam2^-1) + I, T = R^-1 S  (src/tools/uncertainty_prop.py:439-443)
-    double R[kMaxD * kMaxD], Ri[kMaxD * kMaxD], T[kMaxD * kMaxD];
-    for (int r = 0; r < D; ++r) for (int k = 0; k < D; ++k) R[r * D + k] = Sh[r * D + k] * (1.0 / l1[k] + 1.0 / l2[k]) + (r == k ? 1.0 : 0.0);
-    const double det = host_lu(D, R, Ri);
-    for (int r = 0; r < D; ++r) for (int k = 0; k < D; ++k) {
-        double s = 0.0;
-        for (int q = 0; q < D; ++q) s += Ri[r * D + q] * Sh[q * D + k];
-        T[r * D + k] = s;
-    }
-    CovArg ca;
-    ca.D = D; ca.bugcompat = bugcompat ? 1 : 0;
-    for (int r = 0; r < D; ++r) for (int k = 0; k < D; ++k)
-        ca.T[r * D + k] = bugcompat ? T[r * D + k] : 0.5 * (T[r * D + k] + T[k * D + r]);
-    for (int k = 0; k < D; ++k) { ca.u[k] = uh[k]; ca.il1[k] = 1.0 / l1[k]; ca.il2[k] = 1.0 / l2[k]; }
     const size_t cnt = (size_t)n * D + 3 * (size_t)n + 16;
     GP_CUDA(h, h->gbuf.reserve(cnt * sizeof(double)));
     double *w = h->gbuf.as<double>();
@@ -861,16 +916,8 @@ extern "C" int gpmpc_covariance_raw(gpmpc_handle h, int n, int D, const double *
     w += n;
     if (!is_device_ptr(beta2)) { GP_CUDA(h, cudaMemcpyAsync(w, beta2, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream)); b2 = w; }
     w += n;
-    double *rows = w; w += n;
-    double *scal = w;
-    cov_rows_kernel<<<(n + 7) / 8, 256, 0, h->stream>>>(Xd, n, ca, b1, b2, rows);
-    GP_LAUNCH_CHECK(h);
-    sum_kernel<<<1, 1024, 0, h->stream>>>(rows, n, scal);
-    GP_LAUNCH_CHECK(h);
-    double r = 0.0;
-    GP_CUDA(h, cudaMemcpyAsync(&r, scal, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    GP_CUDA(h, cudaStreamSynchronize(h->stream));
-    const double c = sigma_f1 * sigma_f1 * sigma_f2 * sigma_f2 * std::pow(det, -0.5) * r - mean1 * mean2;
+    double c = 0.0;
+    if ((rc = cov_core(h, n, D, l1, l2, uh, Sh, Xd, b1, b2, mean1, mean2, sigma_f1, sigma_f2, bugcompat, w, w + n, &c))) return rc;
     GP_CUDA(h, cudaMemcpyAsync(cov, &c, sizeof(double), cudaMemcpyDefault, h->stream));
     GP_CUDA(h, cudaStreamSynchronize(h->stream));
     return GPMPC_OK;

@@ -160,3 +160,26 @@ class Dynamics(object):
         for t in range(horizon + 1):
             covs[t] = np.diag(vars_[0, t])
         return means[0], covs
+
+    def forward_propagate_full(self, horizon, curr_state, actions):
+        """Full-covariance moment-matched rollout (the reference's TODO at `src/dynamics.py:184`):
+        Sigma_t keeps the cross-covariances between the outputs, computed with the published formula
+        (`src/tools/uncertainty_prop.py:187-236`).  Forward values only (NumPy arrays (H+1, E), (H+1, E, E));
+        the input covariance is blockdiag(Sigma_{t-1}, fp32(1e-3) I) as in the variance-only rollout."""
+        self._require_data()
+        self._sync_propagation_hypers()
+        E, m = self.state_dim, self.action_dim
+        means = np.zeros((horizon + 1, E)); covs = np.zeros((horizon + 1, E, E))
+        means[0] = np.asarray(curr_state, dtype=np.float64).reshape(E)
+        covs[0] = 1e-3 * np.eye(E)
+        U = np.asarray(actions, dtype=np.float64).reshape(-1, m)
+        act_var = float(np.float32(1e-3))
+        for t in range(1, horizon + 1):
+            u = np.concatenate([means[t - 1], U[t - 1]])[None, :]
+            S = np.zeros((1, E + m, E + m))
+            S[0, :E, :E] = covs[t - 1]
+            S[0, E:, E:] = act_var * np.eye(m)
+            mu, cov = self._bundle.moment_match_cov(u, S)
+            means[t], covs[t] = mu[0], cov[0]
+        self._tape_serial += 1
+        return means, covs

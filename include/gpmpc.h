@@ -108,6 +108,12 @@ int gpmpc_marginal_likelihood(gpmpc_handle h, int a, const double *resid, double
 int gpmpc_moment_match(gpmpc_handle h, int B, const double *U, const double *S, int s_is_full,
                        double *mean, double *var);
 
+/* Same for a FULL input covariance S[B,D,D], returning the full E x E output covariance cov[B,E,E]: variances on
+ * the diagonal and cross-covariances beta_a^T Qt beta_b - m_a m_b off it (src/tools/uncertainty_prop.py:187-236,
+ * the formula-correct NumPy form).  This is the moment-matching step of a full-covariance rollout, which the
+ * reference leaves as a TODO (src/dynamics.py:184); generic kernels, not the batched hot path.               */
+int gpmpc_moment_match_cov(gpmpc_handle h, int B, const double *U, const double *S, double *mean, double *cov);
+
 /* Stateless form of the same two functions for caller-supplied matrices (no handle state is used except
  * the device/stream): Kinv[n,n], lambdas[D], u[D], S[D,D] full, X[n,D], y[n].
  * Outputs: mean[1], var[1] (may be NULL), beta[n] (may be NULL), l[n] (may be NULL).

@@ -441,3 +441,37 @@ def test_incremental_append_matches_full_refit(gp):
     inc.append_train_data(Sx[0], Ax[0], nx[0])
     full2.append_train_data(np.concatenate([S, Sx]), np.concatenate([A, Ax]), np.concatenate([nxt, nx]))
     norm_close(inc.gpr_err[0].Ky_inv.cpu().numpy(), full2.gpr_err[0].Ky_inv.cpu().numpy(), 1e-9)
+
+
+def test_full_covariance_propagation_vs_numpy_oracle(gp):
+    """SURVEY 8f N4 (forward values): full E x E covariance rollout against the NumPy oracle assembled from
+    mean_prop / variance_prop / covariance_prop (the reference wires no such rollout, src/dynamics.py:184)."""
+    from oracle import oracle as orc
+    g = golden("rollout")
+    name = "r3"                                    # ARD length-scales differ per output: exercises the cross term
+    dyn = _fit_dynamics(gp, g, name)
+    S, A, nxt = g[f"{name}_S"], g[f"{name}_A"], g[f"{name}_next"]
+    X = np.concatenate([S, A], 1)
+    E, m = nxt.shape[1], A.shape[1]
+    lam, sf, sn = g[f"{name}_lam"], g[f"{name}_sf"], g[f"{name}_sn"]
+    fits = [orc.fit(X, nxt[:, a], lam[a], sf[a], float(np.float32(sn[a] ** 2)) ** 0.5) for a in range(E)]
+    H = 3
+    x0 = g[f"{name}_x0"]; U = g[f"{name}_U"][:H]
+    means, covs = dyn.forward_propagate_full(H, x0, U)
+    mu = x0.copy(); Sig = 1e-3 * np.eye(E)
+    for t in range(1, H + 1):
+        u = np.concatenate([mu, U[t - 1]])
+        Sin = np.zeros((E + m, E + m)); Sin[:E, :E] = Sig; Sin[E:, E:] = float(np.float32(1e-3)) * np.eye(m)
+        ms, bs = [], []
+        Sig_new = np.zeros((E, E))
+        for a in range(E):
+            ma, ba, _ = orc.mean_prop(fits[a]["Ky_inv"], lam[a], u, Sin, X, nxt[:, a], sf[a])
+            ms.append(ma); bs.append(ba)
+            Sig_new[a, a] = orc.variance_prop(fits[a]["Ky_inv"], lam[a], u, Sin, X, ma, ba, sf[a])
+        for a in range(E):
+            for b in range(a + 1, E):
+                c = orc.covariance_prop(lam[a], lam[b], u, Sin, X, ms[a], ms[b], bs[a], bs[b], sf[a], sf[b])
+                Sig_new[a, b] = Sig_new[b, a] = c
+        mu, Sig = np.array(ms), Sig_new
+        norm_close(means[t], mu, 1e-8)
+        assert np.max(np.abs(covs[t] - Sig)) <= RTOL * max(np.max(np.abs(Sig)), 1e-3)
