@@ -272,6 +272,33 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "roofline": roofline,
     }
+    if rank == 0 and world == 1 and not args.no_latency:
+        # single-sequence latency (the cyipopt callback pattern, B = 1) and the p50 of one NLP solve on the same GP
+        mpc = gp.RiskSensitiveMPC(-1.0, H, E, m, Q, R)
+        mpc.dynamics = dyn
+        mpc.set_lb([-1.0] * m); mpc.set_ub([1.0] * m)
+        mpc.curr_state = torch.tensor(x0, device=dev)
+        xs = U_all[0].reshape(-1)
+        for _ in range(3):
+            mpc.objective(xs); mpc.gradient(xs)
+        lat = []
+        for i in range(10):
+            xi = xs + 1e-3 * (i + 1)
+            t1 = time.perf_counter(); mpc.objective(xi); mpc.gradient(xi); lat.append(time.perf_counter() - t1)
+        solves = []
+        for i in range(5):
+            n0 = mpc.n_evals
+            t1 = time.perf_counter(); mpc.get_optimal_trajectory(rng.uniform(-0.5, 0.5, E)); dt = time.perf_counter() - t1
+            solves.append((dt, mpc.n_evals - n0))
+        try:
+            import cyipopt  # noqa: F401
+            solver = "cyipopt"
+        except ImportError:
+            solver = "scipy L-BFGS-B over the same callbacks (cyipopt is not installed)"
+        line["single_solve"] = {"objective_plus_gradient_ms": 1e3 * float(np.median(lat)),
+                                "solve_p50_ms": 1e3 * float(np.median([t for t, _ in solves])),
+                                "evals_per_solve": [k for _, k in solves], "solver": solver,
+                                "note": "B=1 path (lanes<->pairs kernels), wall clock incl. host<->device copies"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         _, one, tf = cpu_reference_sample(n, E, m, H, 1, 0, threads)
@@ -313,6 +340,7 @@ def main():
     ap.add_argument("--H", type=int, default=30)
     ap.add_argument("--B", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

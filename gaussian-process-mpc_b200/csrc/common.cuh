@@ -12,7 +12,11 @@
 namespace gpmpc {
 
 constexpr int kTile = 64;          // padding granule of n (fit GEMM tiles are 64x64)
-constexpr int kPairTile = 32;      // pair-space tile edge of the moment-matching kernels
+constexpr int kPairTile = 32;      // pair-space tile rows of the moment-matching kernels
+#ifndef GPMPC_PTJ
+#define GPMPC_PTJ 32
+#endif
+constexpr int kPairTileJ = GPMPC_PTJ;   // tile columns of mm_pairs_batch (must match mm_pairs.cuh)
 constexpr int kMaxD = GPMPC_MAX_D;
 constexpr int kMaxE = GPMPC_MAX_E;
 constexpr int kGroupMax = 4;       // outputs evaluated per pair-kernel pass (sharing one exp)

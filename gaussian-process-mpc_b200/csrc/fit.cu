@@ -345,7 +345,7 @@ int encode_wt_maps(gpmpc_ctx *h)
     for (int a = 0; a < h->E; ++a) {
         const cuuint64_t dims[2] = {(cuuint64_t)h->ld, (cuuint64_t)h->ld};
         const cuuint64_t strides[1] = {(cuuint64_t)h->ld * sizeof(double)};
-        const cuuint32_t box[2] = {(cuuint32_t)kPairTile, (cuuint32_t)kPairTile};
+        const cuuint32_t box[2] = {(cuuint32_t)kPairTileJ, (cuuint32_t)kPairTile};   // {columns, rows}
         const cuuint32_t estr[2] = {1, 1};
         CUresult r = encode(&h->wt_map[a], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, h->Wt.as<double>() + a * mat, dims, strides,
                             box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,

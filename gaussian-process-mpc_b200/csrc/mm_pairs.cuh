@@ -44,6 +44,12 @@ namespace gpmpc {
 #ifndef GPMPC_USE_TMA
 #define GPMPC_USE_TMA 1          // 1: Wt tiles by TMA (cp.async.bulk.tensor.2d + mbarrier), 0: cp.async (LDGSTS)
 #endif
+#ifndef GPMPC_PTJ
+#define GPMPC_PTJ 32             // columns of a Wt tile of mm_pairs_batch (rows are always 32)
+#endif
+#ifndef GPMPC_PIPELINE
+#define GPMPC_PIPELINE 1         // 1: software-pipelined pair loop (exp chain of pair p+1 overlaps the sums of pair p)
+#endif
 #ifndef GPMPC_MINBLOCKS
 #define GPMPC_MINBLOCKS 2        // CTAs per SM promised to ptxas
 #endif
@@ -213,12 +219,21 @@ struct PairArgs {
 #endif
 };
 
-constexpr int PT = kPairTile;      // 32
+constexpr int PT = kPairTile;      // 32: tile rows (and tile columns of mm_pairs_single)
+constexpr int PTJ = GPMPC_PTJ;     // tile columns of mm_pairs_batch
 constexpr int PAIR_THREADS = 128;
 constexpr int RI = GPMPC_RI;       // rows of the register micro-tile
 
 template <int D, int EG>
-__host__ __device__ constexpr size_t pair_stage_doubles() { return (size_t)EG * PT * PT + 2 * PT * D; }
+__host__ __device__ constexpr size_t pair_stage_doubles() { return (size_t)EG * PT * PTJ + (PT + PTJ) * D; }
+// number of PT x PTJ tiles that intersect the upper triangle (row block I owns column blocks J >= I*PT/PTJ)
+__host__ __device__ inline long long pair_batch_tiles(int ld)
+{
+    const long long nr = ld / PT, nc = ld / PTJ;
+    long long t = 0;
+    for (long long i = 0; i < nr; ++i) t += nc - i * PT / PTJ;
+    return t;
+}
 // dynamic shared memory of mm_pairs_batch: two stages + the 16-entry exp table
 template <int D, int EG>
 __host__ __device__ constexpr size_t pair_smem_bytes()
@@ -279,10 +294,10 @@ mm_pairs_batch(const PairArgs a, const __grid_constant__ PairTma tm)
             void *bar = &full[stage];
             mbar_expect_tx(bar, STAGE_BYTES);
 #pragma unroll
-            for (int g = 0; g < EG; ++g) tma_load_2d(base + (size_t)g * PT * PT, &tm.map[g], tj * PT, ti * PT, bar);
-            double *xi = base + (size_t)EG * PT * PT;
+            for (int g = 0; g < EG; ++g) tma_load_2d(base + (size_t)g * PT * PTJ, &tm.map[g], tj * PTJ, ti * PT, bar);
+            double *xi = base + (size_t)EG * PT * PTJ;
             bulk_load_1d(xi, a.X + (size_t)ti * PT * D, PT * D * sizeof(double), bar);
-            bulk_load_1d(xi + PT * D, a.X + (size_t)tj * PT * D, PT * D * sizeof(double), bar);
+            bulk_load_1d(xi + PT * D, a.X + (size_t)tj * PTJ * D, PTJ * D * sizeof(double), bar);
         }
     };
     auto wait_stage = [&](int stage) {
@@ -294,21 +309,17 @@ mm_pairs_batch(const PairArgs a, const __grid_constant__ PairTma tm)
         double *base = smem + (size_t)stage * STAGE;
 #pragma unroll
         for (int g = 0; g < EG; ++g) {
-            const double *src = a.Wt[g] + (size_t)ti * PT * a.ld + (size_t)tj * PT;
-            double *dst = base + (size_t)g * PT * PT;
-#pragma unroll
-            for (int q = 0; q < (PT * PT / 2) / PAIR_THREADS; ++q) {
-                const int chunk = tid + q * PAIR_THREADS;      // 16-byte chunk id: 16 per row
-                const int r = chunk >> 4, cc = (chunk & 15) * 2;
-                cpa16(dst + r * PT + cc, src + (size_t)r * a.ld + cc);
+            const double *src = a.Wt[g] + (size_t)ti * PT * a.ld + (size_t)tj * PTJ;
+            double *dst = base + (size_t)g * PT * PTJ;
+            for (int chunk = tid; chunk < PT * PTJ / 2; chunk += PAIR_THREADS) {   // 16-byte chunks, PTJ/2 per row
+                const int r = chunk / (PTJ / 2), cc = (chunk % (PTJ / 2)) * 2;
+                cpa16(dst + r * PTJ + cc, src + (size_t)r * a.ld + cc);
             }
         }
-        double *xi = base + (size_t)EG * PT * PT;
+        double *xi = base + (size_t)EG * PT * PTJ;
         double *xj = xi + PT * D;
-        for (int chunk = tid; chunk < PT * D / 2; chunk += PAIR_THREADS) {
-            cpa16(xi + chunk * 2, a.X + (size_t)ti * PT * D + chunk * 2);
-            cpa16(xj + chunk * 2, a.X + (size_t)tj * PT * D + chunk * 2);
-        }
+        for (int chunk = tid; chunk < PT * D / 2; chunk += PAIR_THREADS) cpa16(xi + chunk * 2, a.X + (size_t)ti * PT * D + chunk * 2);
+        for (int chunk = tid; chunk < PTJ * D / 2; chunk += PAIR_THREADS) cpa16(xj + chunk * 2, a.X + (size_t)tj * PTJ * D + chunk * 2);
         cpa_commit();
     };
 #endif
@@ -341,18 +352,19 @@ mm_pairs_batch(const PairArgs a, const __grid_constant__ PairTma tm)
 
         const int t_begin = (int)((long long)a.total_tiles * item / a.n_items);
         const int t_end = (int)((long long)a.total_tiles * (item + 1) / a.n_items);
+        const int ncol = a.ld / PTJ;                 // column blocks; row block I starts at column block I*PT/PTJ
         int I = 0, J = 0;
         {
             int rem = t_begin;
             int row = 0;
-            while (rem >= a.ntile - row) { rem -= a.ntile - row; ++row; }
-            I = row; J = row + rem;
+            while (rem >= ncol - row * PT / PTJ) { rem -= ncol - row * PT / PTJ; ++row; }
+            I = row; J = row * PT / PTJ + rem;
         }
         if (t_begin < t_end) issue(0, I, J);
         int stage = 0;
         for (int t = t_begin; t < t_end; ++t) {
             int In = I, Jn = J + 1;
-            if (Jn == a.ntile) { ++In; Jn = In; }
+            if (Jn == ncol) { ++In; Jn = In * PT / PTJ; }
 #if GPMPC_USE_TMA
             if (t + 1 < t_end) issue(stage ^ 1, In, Jn);
             wait_stage(stage);
@@ -363,9 +375,73 @@ mm_pairs_batch(const PairArgs a, const __grid_constant__ PairTma tm)
 #endif
 
             const double *Ws = smem + (size_t)stage * STAGE;
-            const double *xi = Ws + (size_t)EG * PT * PT;
+            const double *xi = Ws + (size_t)EG * PT * PTJ;
             const double *xj = xi + PT * D;
 
+#if GPMPC_PIPELINE
+            // One pair = chain (q, q^2, S, exp: a ~15-deep dependency chain) + sums (4 + 44 independent FMAs).
+            // ptxas does not software-pipeline loops, so the loop is rotated by hand: the chain of pair p+1 and the
+            // sums of pair p sit in the same basic block and overlap.  Pairs are visited (j, r)-major; the chain
+            // issued after the last pair of a strip is a dummy (clamped column) whose result is dropped.
+            auto chain = [&](const double (&za)[D], const double (&zb)[D], double (&q)[D], double (&qq)[D]) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) { q[k] = za[k] + zb[k]; qq[k] = q[k] * q[k]; }
+                double S = qq[0];
+                if (D >= 4) {
+                    double S2 = qq[2] + qq[3];
+                    S += qq[1];
+#pragma unroll
+                    for (int k = 4; k < D; k += 2) { S += qq[k]; if (k + 1 < D) S2 += qq[k + 1]; }
+                    S += S2;
+                } else {
+#pragma unroll
+                    for (int k = 1; k < D; ++k) S += qq[k];
+                }
+                return exp_neg(S, tab);
+            };
+#pragma unroll 1
+            for (int r0 = 0; r0 < PT; r0 += RI) {
+                double zi[RI][D], zj[D];
+#pragma unroll
+                for (int r = 0; r < RI; ++r)
+#pragma unroll
+                    for (int k = 0; k < D; ++k) zi[r][k] = fma(-GP_C(k), xi[(r0 + r) * D + k], GP_CU(k));
+#pragma unroll
+                for (int k = 0; k < D; ++k) zj[k] = fma(-GP_C(k), xj[k], GP_CU(k));
+                double qc[D], qqc[D];
+                double ec = chain(zi[0], zj, qc, qqc);
+#pragma unroll 1
+                for (int j = 0; j < PTJ; ++j) {
+#pragma unroll
+                    for (int r = 0; r < RI; ++r) {
+                        double qn[D], qqn[D], en;
+                        if (r + 1 < RI) {
+                            en = chain(zi[r + 1], zj, qn, qqn);
+                        } else {
+                            const int jn = min(j + 1, PTJ - 1);
+#pragma unroll
+                            for (int k = 0; k < D; ++k) zj[k] = fma(-GP_C(k), xj[jn * D + k], GP_CU(k));
+                            en = chain(zi[0], zj, qn, qqn);
+                        }
+#pragma unroll
+                        for (int g = 0; g < EG; ++g) {
+                            const double w = Ws[(size_t)g * PT * PTJ + (r0 + r) * PTJ + j] * ec;
+                            accT[g] += w;
+                            if (GRAD) {
+#pragma unroll
+                                for (int k = 0; k < D; ++k) {
+                                    acc1[g][k] = fma(w, qc[k], acc1[g][k]);
+                                    acc2[g][k] = fma(w, qqc[k], acc2[g][k]);
+                                }
+                            }
+                        }
+                        ec = en;
+#pragma unroll
+                        for (int k = 0; k < D; ++k) { qc[k] = qn[k]; qqc[k] = qqn[k]; }
+                    }
+                }
+            }
+#else
 #pragma unroll 1
             for (int r0 = 0; r0 < PT; r0 += RI) {
                 double zi[RI][D];
@@ -374,7 +450,7 @@ mm_pairs_batch(const PairArgs a, const __grid_constant__ PairTma tm)
 #pragma unroll
                     for (int k = 0; k < D; ++k) zi[r][k] = fma(-GP_C(k), xi[(r0 + r) * D + k], GP_CU(k));
 #pragma unroll 1
-                for (int j = 0; j < PT; ++j) {
+                for (int j = 0; j < PTJ; ++j) {
                     double zj[D];
 #pragma unroll
                     for (int k = 0; k < D; ++k) zj[k] = fma(-GP_C(k), xj[j * D + k], GP_CU(k));
@@ -398,7 +474,7 @@ mm_pairs_batch(const PairArgs a, const __grid_constant__ PairTma tm)
 #if GPMPC_ACC_ORDER == 0
 #pragma unroll
                         for (int g = 0; g < EG; ++g) {
-                            const double w = Ws[(size_t)g * PT * PT + (r0 + r) * PT + j] * e;
+                            const double w = Ws[(size_t)g * PT * PTJ + (r0 + r) * PTJ + j] * e;
                             accT[g] += w;
                             if (GRAD) {
 #pragma unroll
@@ -412,7 +488,7 @@ mm_pairs_batch(const PairArgs a, const __grid_constant__ PairTma tm)
                         double w[EG];
 #pragma unroll
                         for (int g = 0; g < EG; ++g) {
-                            w[g] = Ws[(size_t)g * PT * PT + (r0 + r) * PT + j] * e;
+                            w[g] = Ws[(size_t)g * PT * PTJ + (r0 + r) * PTJ + j] * e;
                             accT[g] += w[g];
                         }
                         if (GRAD) {
@@ -433,7 +509,7 @@ mm_pairs_batch(const PairArgs a, const __grid_constant__ PairTma tm)
                         }
 #pragma unroll
                         for (int g = 0; g < EG; ++g) {
-                            const double wt = Ws[(size_t)g * PT * PT + (r0 + r) * PT + j];
+                            const double wt = Ws[(size_t)g * PT * PTJ + (r0 + r) * PTJ + j];
                             accT[g] = fma(wt, e, accT[g]);
                             if (GRAD) {
 #pragma unroll
@@ -447,6 +523,7 @@ mm_pairs_batch(const PairArgs a, const __grid_constant__ PairTma tm)
                     }
                 }
             }
+#endif
             __syncthreads();
             stage ^= 1; I = In; J = Jn;
         }

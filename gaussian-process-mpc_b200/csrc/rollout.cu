@@ -755,7 +755,7 @@ static int reserve_rollout(gpmpc_ctx *h, int B, int H, RolloutWork &w)
     w.d = make_dims(h, B);
     const StepDims &d = w.d;
     const long long nt = h->ld / PT;
-    w.total_tiles = nt * (nt + 1) / 2;
+    w.total_tiles = (B < kSingleMaxB) ? nt * (nt + 1) / 2 : pair_batch_tiles(h->ld);
     pair_geometry(h, B, w.total_tiles, w.ctas, w.P);
     GP_CUDA(h, h->tickets.reserve(((B + PAIR_THREADS - 1) / PAIR_THREADS) * sizeof(int)));
     const size_t Bp = d.Bpad;

@@ -4,6 +4,9 @@
 #include <vector>
 #include <random>
 using namespace gpmpc;
+#ifndef GPMPC_BENCH_GRAD
+#define GPMPC_BENCH_GRAD true
+#endif
 
 __global__ void dfma_latency_kernel(double *out, int iters, double m, double c)
 {
@@ -57,7 +60,7 @@ int main(int argc, char **argv)
     cudaMalloc(&dc, hc.size() * 8); cudaMemcpy(dc, hc.data(), hc.size() * 8, cudaMemcpyHostToDevice);
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     const int chunks = (B + PAIR_THREADS - 1) / PAIR_THREADS;
-    const long long nt = ld / PT, total = nt * (nt + 1) / 2;
+    const long long nt = ld / PT, total = pair_batch_tiles(ld);
 #ifndef GPMPC_CTAS_PER_SM
 #define GPMPC_CTAS_PER_SM 2
 #endif
@@ -76,15 +79,33 @@ int main(int argc, char **argv)
 #ifdef GPMPC_PAIR_TIMING
     unsigned long long *dtimes; cudaMalloc(&dtimes, (size_t)ctas * chunks * 3 * 8); a.cta_times = dtimes;
 #endif
+    PairTma tm;
+    {
+        typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void *fn = nullptr; cudaDriverEntryPointQueryResult qres;
+        cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        encode_fn encode = reinterpret_cast<encode_fn>(fn);
+        for (int g = 0; g < EG; ++g) {
+            const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)ld};
+            const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
+            const cuuint32_t box[2] = {PTJ, PT}, estr[2] = {1, 1};
+            CUresult r = encode(&tm.map[g], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, dW[g], dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { printf("tensor map encode failed %d\n", (int)r); return 1; }
+        }
+    }
     const size_t smem = pair_smem_bytes<D, EG>();
-    cudaFuncSetAttribute(mm_pairs_batch<D, EG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(mm_pairs_batch<D, EG, GPMPC_BENCH_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(ctas * chunks);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {
         cudaMemset(dcnt, 0, chunks * sizeof(int));
         cudaEventRecord(e0);
-        mm_pairs_batch<D, EG, true><<<grid, PAIR_THREADS, smem>>>(a);
+        mm_pairs_batch<D, EG, GPMPC_BENCH_GRAD><<<grid, PAIR_THREADS, smem>>>(a, tm);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
     }
