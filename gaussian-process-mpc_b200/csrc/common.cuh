@@ -75,7 +75,7 @@ struct gpmpc_ctx {
     CUtensorMap wt_map[gpmpc::kMaxE];   // TMA descriptors of the Wt matrices (2-D, box 32x32), see fit.cu
 
     // rollout workspaces (grow-only)
-    gpmpc::DevBuf mu, var, tape, cst, part, mpart, stage_in, stage_out, gbuf, tickets, zall;
+    gpmpc::DevBuf mu, var, tape, cst, part, mpart, stage_in, stage_out, gbuf, tickets;
     int tape_B = 0, tape_H = 0;    // shape of the tape held from the last rollout
 
     // timing of the last pair-kernel sequence

@@ -211,7 +211,6 @@ struct PairArgs {
     const double *cst;             // this group's per-rollout constants [4D][Bpad]: c, c*u, cm, cm*u
     double *part;                  // [n_items][E][nacc][Bpad]
     int *counters;                 // [rollout chunks] work-item tickets, zeroed before the launch
-    const double *zall;            // mm_pairs_single only: this group's z[b][ld][D] (see zprep_kernel)
     int ld, ntile, B, Bpad, E, n_items, chunks;
     int total_tiles;
 #ifdef GPMPC_PAIR_TIMING

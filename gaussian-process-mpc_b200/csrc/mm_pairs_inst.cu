@@ -1,7 +1,7 @@
-// Explicit instantiations of the batched pair-sum kernel for one input dimension D (compiled once per
+// Explicit instantiations of the batched pair-sum kernel and of the fused few-rollouts step kernel for one input dimension D (compiled once per
 // D = 2..8 with -DGPMPC_INST_D=<D> so that the seven translation units build in parallel).
 #include "mm_pairs.cuh"
-#include "mm_pairs_single.cuh"
+#include "mm_step_single.cuh"
 
 #ifndef GPMPC_INST_D
 #error "compile with -DGPMPC_INST_D=<2..8>"
@@ -41,32 +41,32 @@ static cudaError_t launch_d(int EG, bool grad, const PairArgs &a, const PairTma 
 }
 
 template <int D, int EG, bool GRAD>
-static cudaError_t launch_single_one(const PairArgs &a, dim3 grid, cudaStream_t st)
+static cudaError_t launch_single_one(const SingleStepArgs &a, const PairTma &tm, dim3 grid, cudaStream_t st)
 {
     const size_t smem = single_smem_bytes<D, EG>();
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(mm_pairs_single<D, EG, GRAD>,
+        cudaError_t e = cudaFuncSetAttribute(mm_step_single<D, EG, GRAD>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    mm_pairs_single<D, EG, GRAD><<<grid, SINGLE_THREADS, smem, st>>>(a);
+    mm_step_single<D, EG, GRAD><<<grid, SINGLE_THREADS, smem, st>>>(a, tm);
     return cudaGetLastError();
 }
 
 template <int D>
-static cudaError_t launch_single_d(int EG, bool grad, const PairArgs &a, dim3 grid, cudaStream_t st)
+static cudaError_t launch_single_d(int EG, bool grad, const SingleStepArgs &a, const PairTma &tm, dim3 grid, cudaStream_t st)
 {
     switch (EG * 2 + (grad ? 1 : 0)) {
-        case 2: return launch_single_one<D, 1, false>(a, grid, st);
-        case 3: return launch_single_one<D, 1, true>(a, grid, st);
-        case 4: return launch_single_one<D, 2, false>(a, grid, st);
-        case 5: return launch_single_one<D, 2, true>(a, grid, st);
-        case 6: return launch_single_one<D, 3, false>(a, grid, st);
-        case 7: return launch_single_one<D, 3, true>(a, grid, st);
-        case 8: return launch_single_one<D, 4, false>(a, grid, st);
-        case 9: return launch_single_one<D, 4, true>(a, grid, st);
+        case 2: return launch_single_one<D, 1, false>(a, tm, grid, st);
+        case 3: return launch_single_one<D, 1, true>(a, tm, grid, st);
+        case 4: return launch_single_one<D, 2, false>(a, tm, grid, st);
+        case 5: return launch_single_one<D, 2, true>(a, tm, grid, st);
+        case 6: return launch_single_one<D, 3, false>(a, tm, grid, st);
+        case 7: return launch_single_one<D, 3, true>(a, tm, grid, st);
+        case 8: return launch_single_one<D, 4, false>(a, tm, grid, st);
+        case 9: return launch_single_one<D, 4, true>(a, tm, grid, st);
     }
     return cudaErrorInvalidValue;
 }
@@ -78,10 +78,10 @@ cudaError_t GPMPC_CAT(launch_pairs_batch_D, GPMPC_INST_D)(int EG, bool grad, con
 {
     return launch_d<GPMPC_INST_D>(EG, grad, a, tm, grid, st);
 }
-cudaError_t GPMPC_CAT(launch_pairs_single_D, GPMPC_INST_D)(int EG, bool grad, const PairArgs &a, dim3 grid,
-                                                           cudaStream_t st)
+cudaError_t GPMPC_CAT(launch_step_single_D, GPMPC_INST_D)(int EG, bool grad, const SingleStepArgs &a, const PairTma &tm,
+                                                          dim3 grid, cudaStream_t st)
 {
-    return launch_single_d<GPMPC_INST_D>(EG, grad, a, grid, st);
+    return launch_single_d<GPMPC_INST_D>(EG, grad, a, tm, grid, st);
 }
 
 }  // namespace gpmpc

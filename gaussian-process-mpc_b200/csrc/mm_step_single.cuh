@@ -1,0 +1,319 @@
+// One whole moment-matching step for FEW rollouts in ONE launch (a single IPOPT solve evaluates one control
+// sequence at a time: B = 1, src/mpc.py:202-255).
+//
+// mm_pairs_batch maps lanes to rollouts and needs >= 32 of them per warp.  Here lanes map to PAIRS: grid
+// (P, B); CTA (x, b) streams its contiguous share of the upper-triangular 32x32 tiles of Wt through a TMA +
+// mbarrier ring (full/empty barriers, no CTA-wide barrier in the loop), lane <-> column j of the tile,
+// warp <-> 8 rows, and every thread keeps the (1+2D)*EG accumulators of rollout b.  Per rollout and step the
+// kernel reads EG * n(n+1)/2 * 8 bytes of Wt exactly once (268 MB at n=4096, E=4): with one rollout it is bound
+// by HBM, not by the FP64 pipe (41 us vs 34 us per step at n=4096).
+//
+// The same launch also does what used to be four more kernels per step:
+//   * z_i = c*u - c*x_i is formed on the fly from X (per-warp rows; z_j from the X tile that travels with Wt),
+//   * the mean sums (uncertainty_prop.py:324-338) over this CTA's slice of the training set,
+//   * "last CTA done" finalize: the last CTA of rollout b to arrive (ticket counter) sums the P partials in a
+//     fixed order (deterministic), applies the prefactors and writes mean_t, var_t and the tape entry,
+//   * and, when all outputs share one lambda group, the constants of step t+1 (prep_step).
+// So a B = 1 rollout is H launches instead of 5H.
+#pragma once
+#include "mm_pairs.cuh"
+#include "step_common.cuh"
+
+namespace gpmpc {
+
+constexpr int SINGLE_THREADS = 128;    // 2 CTAs per SM
+constexpr int SINGLE_WARPS = SINGLE_THREADS / 32;
+constexpr int SINGLE_ROWS = PT / SINGLE_WARPS;       // rows of a tile handled by one thread (8)
+constexpr int SINGLE_STAGES = 3;       // ring slots per CTA: 2-3 tiles in flight (x2 CTAs per SM = ~200 KB per SM)
+
+static_assert(kPairTileJ == kPairTile, "mm_step_single uses the 32x32 TMA box of the Wt maps");
+
+struct SingleStepArgs {
+    const double *Wt[kGroupMax];   // only used to keep the argument list self-describing (tiles come through the maps)
+    const double *beta[kGroupMax];
+    int out_idx[kGroupMax];
+    const double *X;               // [ld, D]
+    const double *cst;             // this group's per-rollout constants [4D][Bpad]: c, c*u, cm, cm*u
+    double *spart;                 // [B][P][2*EG*NA] partial sums: pair sums (EG*NA) then mean sums (EG*NA)
+    int *tickets;                  // [B] arrival counters, zero before the launch; the last CTA re-zeroes its own
+    int ld, ntile, total_tiles;
+    // finalize (last CTA of each rollout)
+    StepDims d;
+    int t;
+    const double *us;              // [2D][Bpad] input mean / variances of this step
+    const double *hyp;
+    double *mu, *var, *tape;
+    int want_grad;
+    // constants of step t+1 (only when the model has ONE lambda group and t < H)
+    int prep_next;
+    const double *Uint;            // actions [H*m][Bpad]
+    const double *lam_group;       // [D] of group 0
+    double *us_w, *cst_w;
+    double act_var;
+};
+
+template <int D, int EG>
+__host__ __device__ constexpr size_t single_stage_doubles() { return (size_t)EG * PT * PT + PT * D; }
+template <int D, int EG>
+__host__ __device__ constexpr size_t single_smem_bytes() { return SINGLE_STAGES * single_stage_doubles<D, EG>() * sizeof(double); }
+
+__device__ __forceinline__ void mbar_arrive(void *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int D, int EG, bool GRAD>
+__global__ void __launch_bounds__(SINGLE_THREADS, 2)
+mm_step_single(const SingleStepArgs a, const __grid_constant__ PairTma tm)
+{
+    constexpr int NA = 1 + 2 * D;
+    constexpr int NV = 2 * EG * NA;
+    constexpr size_t STAGE = single_stage_doubles<D, EG>();
+    constexpr unsigned STAGE_BYTES = (unsigned)(STAGE * sizeof(double));
+    extern __shared__ __align__(128) double smem[];      // [slot][ Wt[EG][32*32] | x_j[32*D] ]
+    __shared__ double tab[16];
+    __shared__ double cs[4 * D];                         // c, c*u, cm, cm*u of this rollout
+    __shared__ double ziw[SINGLE_WARPS][SINGLE_ROWS * D];   // z_i of the 8 rows each warp handles
+    __shared__ double red[SINGLE_WARPS][EG * NA];
+    __shared__ double fin[NV];
+    __shared__ __align__(8) unsigned long long full[SINGLE_STAGES], empty[SINGLE_STAGES];
+    __shared__ int s_last;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int b = blockIdx.y;                            // rollout
+    const int P = gridDim.x;
+    if (tid < 16) tab[tid] = kExp2Tab[tid];
+    if (tid < 4 * D) cs[tid] = a.cst[(size_t)tid * a.d.Bpad + b];
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < SINGLE_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], SINGLE_WARPS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    double accT[EG], acc1[GRAD ? EG : 1][D], acc2[GRAD ? EG : 1][D];
+#pragma unroll
+    for (int g = 0; g < EG; ++g) accT[g] = 0.0;
+    if (GRAD) {
+#pragma unroll
+        for (int g = 0; g < EG; ++g)
+#pragma unroll
+            for (int k = 0; k < D; ++k) acc1[g][k] = acc2[g][k] = 0.0;
+    }
+
+    const int t_begin = (int)((long long)a.total_tiles * blockIdx.x / P);
+    const int t_end = (int)((long long)a.total_tiles * (blockIdx.x + 1) / P);
+    int I = 0, J = 0;                                    // tile being consumed
+    {
+        int rem = t_begin, row = 0;
+        while (rem >= a.ntile - row) { rem -= a.ntile - row; ++row; }
+        I = row; J = row + rem;
+    }
+    int Ii = I, Ji = J, issued = t_begin;                // next tile to issue (thread 0 only)
+    auto issue_next = [&]() {                            // thread 0: tile `issued` -> slot (issued - t_begin) % STAGES
+        const int slot = (issued - t_begin) % SINGLE_STAGES;
+        double *base = smem + (size_t)slot * STAGE;
+        void *bar = &full[slot];
+        mbar_expect_tx(bar, STAGE_BYTES);
+#pragma unroll
+        for (int g = 0; g < EG; ++g) tma_load_2d(base + (size_t)g * PT * PT, &tm.map[g], Ji * PT, Ii * PT, bar);
+        bulk_load_1d(base + (size_t)EG * PT * PT, a.X + (size_t)Ji * PT * D, PT * D * sizeof(double), bar);
+        ++issued; ++Ji;
+        if (Ji == a.ntile) { ++Ii; Ji = Ii; }
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < SINGLE_STAGES - 1; ++s)
+            if (issued < t_end) issue_next();
+    }
+
+    int curI = -1;
+    for (int t = t_begin; t < t_end; ++t) {
+        const int it = t - t_begin;
+        const int slot = it % SINGLE_STAGES;
+        // refill: tile t + STAGES - 1 goes into the slot tile t-1 used, once all four warps have released it
+        if (tid == 0 && issued < t_end) {
+            if (it > 0) mbar_wait(&empty[(it - 1) % SINGLE_STAGES], ((it - 1) / SINGLE_STAGES) & 1);
+            issue_next();
+        }
+        if (I != curI) {                                 // new row block: this warp's z_i = c*u - c*x_i (rare)
+            __syncwarp();
+            for (int idx = lane; idx < SINGLE_ROWS * D; idx += 32) {
+                const int m = idx / D, k = idx % D;
+                ziw[wid][idx] = fma(-cs[k], a.X[(size_t)(I * PT + wid + m * SINGLE_WARPS) * D + k], cs[D + k]);
+            }
+            __syncwarp();
+            curI = I;
+        }
+        mbar_wait(&full[slot], (it / SINGLE_STAGES) & 1);
+
+        const double *Ws = smem + (size_t)slot * STAGE;
+        const double *xjs = Ws + (size_t)EG * PT * PT;
+        double zj[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) zj[k] = fma(-cs[k], xjs[lane * D + k], cs[D + k]);
+#pragma unroll
+        for (int m = 0; m < SINGLE_ROWS; ++m) {
+            const int r = wid + m * SINGLE_WARPS;
+            double q[D], qq[D];
+#pragma unroll
+            for (int k = 0; k < D; ++k) { q[k] = ziw[wid][m * D + k] + zj[k]; qq[k] = q[k] * q[k]; }
+            double S = qq[0];
+            if (D >= 4) {                                // pairwise tree: shorter dependency chain
+                double S2 = qq[2] + qq[3];
+                S += qq[1];
+#pragma unroll
+                for (int k = 4; k < D; k += 2) { S += qq[k]; if (k + 1 < D) S2 += qq[k + 1]; }
+                S += S2;
+            } else {
+#pragma unroll
+                for (int k = 1; k < D; ++k) S += qq[k];
+            }
+            const double e = exp_neg(S, tab);
+#pragma unroll
+            for (int g = 0; g < EG; ++g) {
+                const double w = Ws[(size_t)g * PT * PT + r * PT + lane] * e;
+                accT[g] += w;
+                if (GRAD) {
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        acc1[g][k] = fma(w, q[k], acc1[g][k]);
+                        acc2[g][k] = fma(w, qq[k], acc2[g][k]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);        // this warp is done with the slot
+        ++J;
+        if (J == a.ntile) { ++I; J = I; }
+    }
+
+    // ---- CTA reduction of the pair sums in a fixed order: lanes (xor tree), then warps in index order ----
+    auto warp_sum = [](double v) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    };
+#pragma unroll
+    for (int g = 0; g < EG; ++g) {
+        double v = warp_sum(accT[g]);
+        if (lane == 0) red[wid][g * NA] = v;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const double v1 = warp_sum(GRAD ? acc1[g][k] : 0.0);
+            const double v2 = warp_sum(GRAD ? acc2[g][k] : 0.0);
+            if (lane == 0) { red[wid][g * NA + 1 + k] = v1; red[wid][g * NA + 1 + D + k] = v2; }
+        }
+    }
+    __syncthreads();                                     // also: every warp has left the tile ring
+    double *mine = a.spart + ((size_t)b * P + blockIdx.x) * NV;
+    if (tid < EG * NA) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < SINGLE_WARPS; ++w) s += red[w][tid];
+        mine[tid] = s;
+    }
+
+    // ---- mean sums over this CTA's slice of the training set (lanes <-> training points) ----
+    // p_k = cm_k (u_k - x_jk),  l_j = exp(-sum p_k^2),  M0 += beta_j l_j, M1_k += beta_j l_j p_k, M2_k += .. p_k^2
+    {
+        const int per = (a.ld + P - 1) / P;
+        const int j_begin = blockIdx.x * per;
+        const int j_end = min(a.ld, j_begin + per);
+        const int rows = min(max(j_end - j_begin, 0), SINGLE_THREADS);   // threads that own >= 1 point
+        double *scratch = smem;                          // [thread][EG*NA] (the ring is idle now)
+        if (tid < rows) {
+            double m0[EG], m1[EG][D], m2[EG][D];
+#pragma unroll
+            for (int g = 0; g < EG; ++g) {
+                m0[g] = 0.0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) m1[g][k] = m2[g][k] = 0.0;
+            }
+            for (int j = j_begin + tid; j < j_end; j += SINGLE_THREADS) {
+                double p[D], pp[D], S = 0.0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    p[k] = fma(-cs[2 * D + k], a.X[(size_t)j * D + k], cs[3 * D + k]);
+                    pp[k] = p[k] * p[k];
+                    S += pp[k];
+                }
+                const double l = exp_neg(S, tab);
+#pragma unroll
+                for (int g = 0; g < EG; ++g) {
+                    const double w = a.beta[g][j] * l;
+                    m0[g] += w;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) { m1[g][k] = fma(w, p[k], m1[g][k]); m2[g][k] = fma(w, pp[k], m2[g][k]); }
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < EG; ++g) {
+                scratch[(size_t)tid * (EG * NA) + g * NA] = m0[g];
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    scratch[(size_t)tid * (EG * NA) + g * NA + 1 + k] = m1[g][k];
+                    scratch[(size_t)tid * (EG * NA) + g * NA + 1 + D + k] = m2[g][k];
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < EG * NA) {
+            double s = 0.0;
+            for (int r = 0; r < rows; ++r) s += scratch[(size_t)r * (EG * NA) + tid];
+            mine[EG * NA + tid] = s;
+        }
+    }
+
+    // ---- last CTA of this rollout: deterministic reduction over the P partials, finalize, next-step constants ----
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&a.tickets[b], 1) == P - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    {
+        const double *src = a.spart + (size_t)b * P * NV;
+        for (int v = tid; v < NV; v += SINGLE_THREADS) {
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int p = 0;
+            for (; p + 4 <= P; p += 4) {
+                s0 += __ldcg(src + (size_t)(p + 0) * NV + v);
+                s1 += __ldcg(src + (size_t)(p + 1) * NV + v);
+                s2 += __ldcg(src + (size_t)(p + 2) * NV + v);
+                s3 += __ldcg(src + (size_t)(p + 3) * NV + v);
+            }
+            for (; p < P; ++p) s0 += __ldcg(src + (size_t)p * NV + v);
+            fin[v] = (s0 + s1) + (s2 + s3);
+        }
+    }
+    __syncthreads();
+    if (tid < EG)
+        finalize_math(a.d, a.t, a.out_idx[tid], b, &fin[tid * NA], &fin[EG * NA + tid * NA], a.us, a.hyp, a.mu, a.var,
+                      a.tape, a.want_grad);
+    if (tid == 0) a.tickets[b] = 0;                      // ready for the next launch on this stream
+    if (a.prep_next) {
+        __syncthreads();                                 // mean_t / var_t of all outputs are written
+        if (tid < D) {
+            const int k = tid, E = a.d.E;
+            double u, s;
+            if (k < E) {
+                u = a.mu[((size_t)a.t * E + k) * a.d.Bpad + b];
+                s = a.var[((size_t)a.t * E + k) * a.d.Bpad + b];
+            } else {
+                u = a.Uint[((size_t)a.t * a.d.m + (k - E)) * a.d.Bpad + b];
+                s = a.act_var;
+            }
+            a.us_w[(size_t)k * a.d.Bpad + b] = u;
+            a.us_w[(size_t)(D + k) * a.d.Bpad + b] = s;
+            double c, cu, cm, cmu;
+            step_constants(u, s, a.lam_group[k], c, cu, cm, cmu);
+            a.cst_w[(size_t)k * a.d.Bpad + b] = c;
+            a.cst_w[(size_t)(D + k) * a.d.Bpad + b] = cu;
+            a.cst_w[(size_t)(2 * D + k) * a.d.Bpad + b] = cm;
+            a.cst_w[(size_t)(3 * D + k) * a.d.Bpad + b] = cmu;
+        }
+    }
+}
+
+}  // namespace gpmpc

@@ -14,17 +14,18 @@
 //
 // Internal layouts put the rollout index last (coalesced across the lanes that own rollouts).
 #include "common.cuh"
+#include "step_common.cuh"
 #include "mm_pairs.cuh"
-#include "mm_pairs_single.cuh"
+#include "mm_step_single.cuh"
 
 namespace gpmpc {
 
 #define DECL_LAUNCH(D) cudaError_t launch_pairs_batch_D##D(int, bool, const PairArgs &, const PairTma &, dim3, cudaStream_t); \
-                       cudaError_t launch_pairs_single_D##D(int, bool, const PairArgs &, dim3, cudaStream_t);
+                       cudaError_t launch_step_single_D##D(int, bool, const SingleStepArgs &, const PairTma &, dim3, cudaStream_t);
 DECL_LAUNCH(2) DECL_LAUNCH(3) DECL_LAUNCH(4) DECL_LAUNCH(5) DECL_LAUNCH(6) DECL_LAUNCH(7) DECL_LAUNCH(8)
 #undef DECL_LAUNCH
 
-typedef cudaError_t (*pair_launch_fn)(int, bool, const PairArgs &, dim3, cudaStream_t);
+typedef cudaError_t (*pair_launch_fn)(int, bool, const SingleStepArgs &, const PairTma &, dim3, cudaStream_t);
 typedef cudaError_t (*pair_tma_launch_fn)(int, bool, const PairArgs &, const PairTma &, dim3, cudaStream_t);
 static pair_tma_launch_fn pair_launcher(int D)
 {
@@ -40,10 +41,10 @@ static pair_tma_launch_fn pair_launcher(int D)
 static pair_launch_fn single_launcher(int D)
 {
     switch (D) {
-        case 2: return launch_pairs_single_D2; case 3: return launch_pairs_single_D3;
-        case 4: return launch_pairs_single_D4; case 5: return launch_pairs_single_D5;
-        case 6: return launch_pairs_single_D6; case 7: return launch_pairs_single_D7;
-        case 8: return launch_pairs_single_D8;
+        case 2: return launch_step_single_D2; case 3: return launch_step_single_D3;
+        case 4: return launch_step_single_D4; case 5: return launch_step_single_D5;
+        case 6: return launch_step_single_D6; case 7: return launch_step_single_D7;
+        case 8: return launch_step_single_D8;
     }
     return nullptr;
 }
@@ -53,7 +54,6 @@ constexpr int kSingleMaxB = 64;
 constexpr int MEAN_JP = 16;          // partitions of the training set in the mean kernel
 constexpr int MEAN_THREADS = 128;
 
-struct StepDims { int B, Bpad, D, E, m, G, n, ld; };
 
 // ---------------------------------------------------------------------------------------------
 // prep_step: one thread per (rollout, lambda-group)
@@ -171,122 +171,11 @@ __global__ void __launch_bounds__(MEAN_THREADS) mean_sums_kernel(const MeanArgs 
     }
 }
 
-// Few rollouts: lanes <-> training points.  grid (MEAN_JP, B); fixed-order block reduction.
-template <int D>
-__global__ void __launch_bounds__(256) mean_single_kernel(const MeanArgs a)
-{
-    constexpr int NA = 1 + 2 * D;
-    __shared__ double etab[16];
-    __shared__ double cs[2 * D];
-    __shared__ double red[8][kGroupMax * NA];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int jp = blockIdx.x, b = blockIdx.y;
-    if (tid < 16) etab[tid] = kExp2Tab[tid];
-    if (tid < 2 * D) cs[tid] = a.cst[(size_t)(2 * D + tid) * a.d.Bpad + b];      // cm_k, cm_k u_k
-    __syncthreads();
-    const int per = (a.d.ld / 64 + MEAN_JP - 1) / MEAN_JP * 64;
-    const int j_begin = jp * per;
-    const int j_end = min(a.d.ld, j_begin + per);
-    double m0[kGroupMax], m1[kGroupMax][D], m2[kGroupMax][D];
-#pragma unroll
-    for (int g = 0; g < kGroupMax; ++g) {
-        m0[g] = 0.0;
-#pragma unroll
-        for (int k = 0; k < D; ++k) m1[g][k] = m2[g][k] = 0.0;
-    }
-    for (int j = j_begin + tid; j < j_end; j += 256) {
-        double p[D], pp[D], S = 0.0;
-#pragma unroll
-        for (int k = 0; k < D; ++k) { p[k] = fma(-cs[k], a.X[(size_t)j * D + k], cs[D + k]); pp[k] = p[k] * p[k]; S += pp[k]; }
-        const double l = exp_neg(S, etab);
-#pragma unroll
-        for (int g = 0; g < kGroupMax; ++g) {
-            if (g < a.EG) {
-                const double w = a.beta[g][j] * l;
-                m0[g] += w;
-#pragma unroll
-                for (int k = 0; k < D; ++k) { m1[g][k] = fma(w, p[k], m1[g][k]); m2[g][k] = fma(w, pp[k], m2[g][k]); }
-            }
-        }
-    }
-    auto warp_sum = [](double v) {
-#pragma unroll
-        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        return v;
-    };
-#pragma unroll
-    for (int g = 0; g < kGroupMax; ++g) {
-        const double v0 = warp_sum(m0[g]);
-        if (lane == 0) red[wid][g * NA] = v0;
-#pragma unroll
-        for (int k = 0; k < D; ++k) {
-            const double v1 = warp_sum(m1[g][k]), v2 = warp_sum(m2[g][k]);
-            if (lane == 0) { red[wid][g * NA + 1 + k] = v1; red[wid][g * NA + 1 + D + k] = v2; }
-        }
-    }
-    __syncthreads();
-    if (tid < a.EG * NA) {
-        double sacc = 0.0;
-        for (int w = 0; w < 8; ++w) sacc += red[w][tid];
-        const int g = tid / NA, e = tid % NA;
-        a.mpart[(((size_t)jp * a.d.E + a.out_idx[g]) * NA + e) * a.d.Bpad + b] = sacc;
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // finalize_step: sums the partials of (rollout, output) in a fixed order (deterministic), applies the
 // determinant prefactors and writes mean/var of step t plus the tape entry.
 //   tape[((t-1)*E + a) * (2+4D) + e][Bpad]:  e = 0 mean, 1 var, 2.. dm/du, dm/ds, dv/du, dv/ds
 // ---------------------------------------------------------------------------------------------
-// Shared tail of the finalize kernels: prefactors, mean/var of step t and the tape entry of (b, a).
-__device__ void finalize_math(const StepDims &d, int t, int a, int b, const double *accN, const double *accM,
-                              const double *__restrict__ us, const double *__restrict__ hyp,
-                              double *__restrict__ mu, double *__restrict__ var, double *__restrict__ tape,
-                              int want_grad)
-{
-    const int D = d.D;
-    const double *lam = hyp + (size_t)a * D;
-    const double sf = hyp[(size_t)d.E * D + a];
-    double detm = 1.0, detv = 1.0;
-    double s[kMaxD];
-    for (int k = 0; k < D; ++k) {
-        s[k] = us[(size_t)(D + k) * d.Bpad + b];
-        detm *= 1.0 + s[k] / lam[k];            // |Lam^-1 S + I|      uncertainty_prop.py:335
-        detv *= 1.0 + 2.0 * s[k] / lam[k];      // |2 Lam^-1 S + I|    uncertainty_prop.py:377
-    }
-    const double sf2 = sf * sf;
-    const double cmf = sf2 / sqrt(detm);
-    const double cvf = sf2 * sf2 / sqrt(detv);
-    const double M0 = cmf * accM[0];
-    const double N0 = cvf * accN[0];
-    const double mean = M0;
-    const double v = sf2 - N0 - mean * mean;     // latent variance, uncertainty_prop.py:399
-    mu[((size_t)t * d.E + a) * d.Bpad + b] = mean;
-    var[((size_t)t * d.E + a) * d.Bpad + b] = v;
-    if (!want_grad) return;
-    const int NT = 2 + 4 * D;
-    double *tp = tape + (((size_t)(t - 1) * d.E + a) * NT) * d.Bpad + b;
-    tp[0] = mean;
-    tp[(size_t)d.Bpad] = v;
-    for (int k = 0; k < D; ++k) {
-        const double ak = 1.0 / (0.5 * lam[k] + s[k]);
-        const double bk = 1.0 / (s[k] + lam[k]);
-        const double c = sqrt(0.125 * ak), cm = sqrt(0.5 * bk);
-        const double M1 = cmf * accM[1 + k] / cm;               // sum beta l v_k
-        const double M2 = cmf * accM[1 + D + k] / (cm * cm);    // sum beta l v_k^2
-        const double N1 = cvf * accN[1 + k] / c;                // sum w (v_ik + v_jk)
-        const double N2 = cvf * accN[1 + D + k] / (c * c);      // sum w (v_ik + v_jk)^2
-        const double dmu = -bk * M1;
-        const double dms = 0.5 * bk * bk * M2 - 0.5 * bk * M0;
-        const double dTu = -0.5 * ak * N1;
-        const double dTs = 0.125 * ak * ak * N2 - N0 / (lam[k] + 2.0 * s[k]);
-        tp[(size_t)(2 + k) * d.Bpad] = dmu;
-        tp[(size_t)(2 + D + k) * d.Bpad] = dms;
-        tp[(size_t)(2 + 2 * D + k) * d.Bpad] = -dTu - 2.0 * mean * dmu;
-        tp[(size_t)(2 + 3 * D + k) * d.Bpad] = -dTs - 2.0 * mean * dms;
-    }
-}
-
 constexpr int FIN_WARPS = 4;
 __global__ void __launch_bounds__(32 * FIN_WARPS)
 finalize_step_kernel(StepDims d, int t, int P, const double *__restrict__ part,
@@ -319,27 +208,6 @@ finalize_step_kernel(StepDims d, int t, int P, const double *__restrict__ part,
         accN[e] = s; accM[e] = sm;
     }
     finalize_math(d, t, a, b, accN, accM, us, hyp, mu, var, tape, want_grad);
-}
-
-// Few rollouts: one block per (rollout, output); warp e sums statistic e over the partial list (lanes stride the
-// list, xor-tree combine: fixed order), thread 0 finishes.
-__global__ void __launch_bounds__(32 * (1 + 2 * kMaxD))
-finalize_small_kernel(StepDims d, int t, int P, const double *__restrict__ part,
-                      const double *__restrict__ mpart, const double *__restrict__ us,
-                      const double *__restrict__ hyp, double *__restrict__ mu,
-                      double *__restrict__ var, double *__restrict__ tape, int want_grad)
-{
-    __shared__ double accN[1 + 2 * kMaxD], accM[1 + 2 * kMaxD];
-    const int lane = threadIdx.x & 31, e = threadIdx.x >> 5;
-    const int b = blockIdx.x, a = blockIdx.y;
-    const int NA = 1 + 2 * d.D;
-    double s = 0.0, sm = 0.0;
-    for (int p = lane; p < P; p += 32) s += part[(((size_t)p * d.E + a) * NA + e) * d.Bpad + b];
-    for (int p = lane; p < MEAN_JP; p += 32) sm += mpart[(((size_t)p * d.E + a) * NA + e) * d.Bpad + b];
-    for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); sm += __shfl_xor_sync(0xffffffffu, sm, o); }
-    if (lane == 0) { accN[e] = s; accM[e] = sm; }
-    __syncthreads();
-    if (threadIdx.x == 0) finalize_math(d, t, a, b, accN, accM, us, hyp, mu, var, tape, want_grad);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -666,8 +534,7 @@ static void pair_geometry(gpmpc_ctx *h, int B, long long total_tiles, int &ctas_
 
 template <int D> static void launch_mean(const MeanArgs &ma, dim3 grid, cudaStream_t st)
 {
-    if (ma.d.B < kSingleMaxB) mean_single_kernel<D><<<dim3(MEAN_JP, ma.d.B), 256, 0, st>>>(ma);
-    else mean_sums_kernel<D><<<grid, MEAN_THREADS, 0, st>>>(ma);
+    mean_sums_kernel<D><<<grid, MEAN_THREADS, 0, st>>>(ma);
 }
 static void launch_mean_d(int D, const MeanArgs &ma, dim3 grid, cudaStream_t st)
 {
@@ -679,22 +546,46 @@ static void launch_mean_d(int D, const MeanArgs &ma, dim3 grid, cudaStream_t st)
     }
 }
 
+// Constants of the following step, written by the fused few-rollouts kernel (one lambda group only).
+struct NextPrep { bool on = false; const double *Uint = nullptr; const double *lam_group = nullptr; double act_var = 0.0; };
+
 // One moment-matching step for all rollouts: us/cst must have been prepared.  Writes mean/var of step t
 // (slot t of mu/var) and, if want_grad, the tape entry t-1.
+//   B <  kSingleMaxB: one launch of mm_step_single per lambda group does everything (pairs, mean, finalize)
+//   B >= kSingleMaxB: mm_pairs_batch + mean_sums per group, then finalize_step
 static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int ctas, int P, long long total_tiles, bool want_grad,
-                    double *us, double *cst, double *mu, double *var, double *tape)
+                    double *us, double *cst, double *mu, double *var, double *tape, const NextPrep &next = NextPrep())
 {
     const size_t mat = (size_t)h->ld * h->ld;
-    const int NA = nacc(d.D);
-    if (d.B < kSingleMaxB) {
-        GP_CUDA(h, h->zall.reserve((size_t)d.G * d.B * h->ld * d.D * sizeof(double)));
-        zprep_kernel<<<dim3((h->ld * d.D + 255) / 256, d.B, d.G), 256, 0, h->stream>>>(h->X.as<double>(), h->ld, d.D, d.B,
-                                                                                      d.Bpad, d.G, cst, h->zall.as<double>());
-        GP_LAUNCH_CHECK(h);
-    }
+    const bool few = d.B < kSingleMaxB;
     if (h->time_pairs) cudaEventRecord(h->ev0, h->stream);
     for (int g = 0; g < d.G; ++g) {
         const LambdaGroup &grp = h->groups[g];
+        PairTma tm;
+        for (int i = 0; i < kGroupMax; ++i) tm.map[i] = h->wt_map[grp.outputs[i < grp.count ? i : 0]];
+        cudaError_t e;
+        if (few) {
+            SingleStepArgs sa;
+            for (int i = 0; i < kGroupMax; ++i) {
+                const int o = grp.outputs[i < grp.count ? i : 0];
+                sa.Wt[i] = h->Wt.as<double>() + (size_t)o * mat;
+                sa.beta[i] = h->beta.as<double>() + (size_t)o * h->ld;
+                sa.out_idx[i] = o;
+            }
+            sa.X = h->X.as<double>();
+            sa.cst = cst + (size_t)g * 4 * d.D * d.Bpad;
+            sa.spart = h->part.as<double>();
+            sa.tickets = h->tickets.as<int>();
+            sa.ld = h->ld; sa.ntile = h->ld / PT; sa.total_tiles = (int)total_tiles;
+            sa.d = d; sa.t = t; sa.us = us; sa.hyp = h->hyp.as<double>(); sa.mu = mu; sa.var = var; sa.tape = tape;
+            sa.want_grad = want_grad ? 1 : 0;
+            sa.prep_next = (next.on && d.G == 1) ? 1 : 0;
+            sa.Uint = next.Uint; sa.lam_group = next.lam_group; sa.us_w = us; sa.cst_w = cst; sa.act_var = next.act_var;
+            e = single_launcher(d.D)(grp.count, want_grad, sa, tm, dim3(ctas, d.B), h->stream);
+            h->launches++;
+            if (e != cudaSuccess) return fail(h, GPMPC_ERR_CUDA, std::string("mm_step_single: ") + cudaGetErrorString(e));
+            continue;
+        }
         PairArgs pa;
         MeanArgs ma;
         for (int i = 0; i < kGroupMax; ++i) {
@@ -711,16 +602,8 @@ static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int ctas, int P, lon
         pa.total_tiles = (int)total_tiles; pa.chunks = (d.B + PAIR_THREADS - 1) / PAIR_THREADS;
         const int chunks = (d.B + PAIR_THREADS - 1) / PAIR_THREADS;
         pa.counters = h->tickets.as<int>();
-        cudaError_t e;
-        if (d.B < kSingleMaxB) {
-            pa.zall = h->zall.as<double>() + (size_t)g * d.B * h->ld * d.D;
-            e = single_launcher(d.D)(grp.count, want_grad, pa, dim3(ctas, d.B), h->stream);
-        } else {
-            GP_CUDA(h, cudaMemsetAsync(pa.counters, 0, chunks * sizeof(int), h->stream));
-            PairTma tm;
-            for (int i = 0; i < kGroupMax; ++i) tm.map[i] = h->wt_map[grp.outputs[i < grp.count ? i : 0]];
-            e = pair_launcher(d.D)(grp.count, want_grad, pa, tm, dim3(ctas * chunks), h->stream);
-        }
+        GP_CUDA(h, cudaMemsetAsync(pa.counters, 0, chunks * sizeof(int), h->stream));
+        e = pair_launcher(d.D)(grp.count, want_grad, pa, tm, dim3(ctas * chunks), h->stream);
         h->launches++;
         if (e != cudaSuccess) return fail(h, GPMPC_ERR_CUDA, std::string("mm_pairs_batch: ") + cudaGetErrorString(e));
 
@@ -730,18 +613,13 @@ static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int ctas, int P, lon
         GP_LAUNCH_CHECK(h);
     }
     if (h->time_pairs) cudaEventRecord(h->ev1, h->stream);
-    if (d.B < kSingleMaxB) {
-        finalize_small_kernel<<<dim3(d.B, d.E), 32 * nacc(d.D), 0, h->stream>>>(d, t, P, h->part.as<double>(),
-                                                                                h->mpart.as<double>(), us, h->hyp.as<double>(),
-                                                                                mu, var, tape, want_grad ? 1 : 0);
-    } else {
+    if (!few) {
         dim3 fgrid((d.B + 31) / 32, d.E);
         finalize_step_kernel<<<fgrid, 32 * FIN_WARPS, 0, h->stream>>>(d, t, P, h->part.as<double>(), h->mpart.as<double>(),
                                                                       us, h->hyp.as<double>(), mu, var, tape,
                                                                       want_grad ? 1 : 0);
+        GP_LAUNCH_CHECK(h);
     }
-    GP_LAUNCH_CHECK(h);
-    (void)NA;
     return GPMPC_OK;
 }
 
@@ -757,13 +635,18 @@ static int reserve_rollout(gpmpc_ctx *h, int B, int H, RolloutWork &w)
     const long long nt = h->ld / PT;
     w.total_tiles = (B < kSingleMaxB) ? nt * (nt + 1) / 2 : pair_batch_tiles(h->ld);
     pair_geometry(h, B, w.total_tiles, w.ctas, w.P);
-    GP_CUDA(h, h->tickets.reserve(((B + PAIR_THREADS - 1) / PAIR_THREADS) * sizeof(int)));
+    const bool few = B < kSingleMaxB;
+    const size_t n_tickets = few ? (size_t)B : (size_t)((B + PAIR_THREADS - 1) / PAIR_THREADS);
+    GP_CUDA(h, h->tickets.reserve(n_tickets * sizeof(int)));
+    if (few) GP_CUDA(h, cudaMemsetAsync(h->tickets.as<int>(), 0, n_tickets * sizeof(int), h->stream));
     const size_t Bp = d.Bpad;
     const int Hs = H > 0 ? H : 1;
     GP_CUDA(h, h->mu.reserve((size_t)(H + 1) * d.E * Bp * sizeof(double)));
     GP_CUDA(h, h->var.reserve((size_t)(H + 1) * d.E * Bp * sizeof(double)));
     GP_CUDA(h, h->tape.reserve((size_t)Hs * d.E * ntape(d.D) * Bp * sizeof(double)));
-    GP_CUDA(h, h->part.reserve((size_t)w.P * d.E * nacc(d.D) * Bp * sizeof(double)));
+    // few rollouts: [B][P][2 * 4 * nacc] (pair + mean partials of one lambda group); else [P][E][nacc][Bp]
+    GP_CUDA(h, h->part.reserve(few ? (size_t)B * w.P * 2 * kGroupMax * nacc(d.D) * sizeof(double)
+                                   : (size_t)w.P * d.E * nacc(d.D) * Bp * sizeof(double)));
     GP_CUDA(h, h->mpart.reserve((size_t)MEAN_JP * d.E * nacc(d.D) * Bp * sizeof(double)));
     // cst: x0int [E][Bp] | Uint [H*m][Bp] | us [2D][Bp] | cst [G][4D][Bp]
     const size_t cnt = (size_t)d.E * Bp + (size_t)Hs * (d.m > 0 ? d.m : 1) * Bp + 2 * (size_t)d.D * Bp +
@@ -807,12 +690,18 @@ static int forward(gpmpc_ctx *h, int B, int H, const double *x0_dev, const doubl
     GP_LAUNCH_CHECK(h);
     const double act_var = (double)1e-3f;          // fp32 eye in the action block, src/dynamics.py:162
     h->last_pair_ms = 0.0; h->last_pair_evals = 0;
+    // few rollouts and one lambda group: the step kernel itself prepares the constants of the following step
+    const bool fused_prep = B < kSingleMaxB && d.G == 1;
     for (int t = 1; t <= H; ++t) {
-        prep_step_kernel<<<dim3((B + 127) / 128, d.G), blk, 0, h->stream>>>(d, t, h->mu.as<double>(), h->var.as<double>(),
-                                                                             w.Uint, w.lamg, w.us, w.cst, act_var);
-        GP_LAUNCH_CHECK(h);
+        if (!fused_prep || t == 1) {
+            prep_step_kernel<<<dim3((B + 127) / 128, d.G), blk, 0, h->stream>>>(d, t, h->mu.as<double>(), h->var.as<double>(),
+                                                                                 w.Uint, w.lamg, w.us, w.cst, act_var);
+            GP_LAUNCH_CHECK(h);
+        }
+        NextPrep next;
+        next.on = fused_prep && t < H; next.Uint = w.Uint; next.lam_group = w.lamg; next.act_var = act_var;
         rc = run_step(h, d, t, w.ctas, w.P, w.total_tiles, want_grad, w.us, w.cst, h->mu.as<double>(),
-                      h->var.as<double>(), h->tape.as<double>());
+                      h->var.as<double>(), h->tape.as<double>(), next);
         if (rc) return rc;
         if (h->time_pairs) {
             GP_CUDA(h, cudaEventSynchronize(h->ev1));

@@ -75,7 +75,7 @@ int main(int argc, char **argv)
     cudaMalloc(&dlat, 128 * 8);
     PairArgs a;
     for (int g = 0; g < EG; ++g) { a.Wt[g] = dW[g]; a.out_idx[g] = g; }
-    a.X = dX; a.cst = dc; a.part = dpart; a.ld = ld; a.ntile = (int)nt; a.B = B; a.Bpad = Bpad; a.E = EG; a.n_items = P; a.counters = dcnt; a.total_tiles = (int)total; a.chunks = chunks; a.zall = nullptr;
+    a.X = dX; a.cst = dc; a.part = dpart; a.ld = ld; a.ntile = (int)nt; a.B = B; a.Bpad = Bpad; a.E = EG; a.n_items = P; a.counters = dcnt; a.total_tiles = (int)total; a.chunks = chunks;
 #ifdef GPMPC_PAIR_TIMING
     unsigned long long *dtimes; cudaMalloc(&dtimes, (size_t)ctas * chunks * 3 * 8); a.cta_times = dtimes;
 #endif
