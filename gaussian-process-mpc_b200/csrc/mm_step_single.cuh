@@ -24,9 +24,11 @@ namespace gpmpc {
 constexpr int SINGLE_THREADS = 128;    // 2 CTAs per SM
 constexpr int SINGLE_WARPS = SINGLE_THREADS / 32;
 constexpr int SINGLE_ROWS = PT / SINGLE_WARPS;       // rows of a tile handled by one thread (8)
+constexpr int SINGLE_GROUP = 16;       // CTAs per first-level reduction group
 constexpr int SINGLE_STAGES = 3;       // ring slots per CTA: 2-3 tiles in flight (x2 CTAs per SM = ~200 KB per SM)
 
 static_assert(kPairTileJ == kPairTile, "mm_step_single uses the 32x32 TMA box of the Wt maps");
+static_assert(kGroupMax <= SINGLE_WARPS, "the finalize maps one warp to each output of the group");
 
 struct SingleStepArgs {
     const double *Wt[kGroupMax];   // only used to keep the argument list self-describing (tiles come through the maps)
@@ -34,8 +36,8 @@ struct SingleStepArgs {
     int out_idx[kGroupMax];
     const double *X;               // [ld, D]
     const double *cst;             // this group's per-rollout constants [4D][Bpad]: c, c*u, cm, cm*u
-    double *spart;                 // [B][P][2*EG*NA] partial sums: pair sums (EG*NA) then mean sums (EG*NA)
-    int *tickets;                  // [B] arrival counters, zero before the launch; the last CTA re-zeroes its own
+    double *spart;                 // [B][P][NV] partial sums (NV = 2*EG*NA: pair sums, then mean sums), then [B][NG][NV] group sums
+    int *tickets;                  // [B][1 + NG] arrival counters (NG = ceil(P/16)), zero before the launch and after it
     int ld, ntile, total_tiles;
     // finalize (last CTA of each rollout)
     StepDims d;
@@ -265,33 +267,55 @@ mm_step_single(const SingleStepArgs a, const __grid_constant__ PairTma tm)
         }
     }
 
-    // ---- last CTA of this rollout: deterministic reduction over the P partials, finalize, next-step constants ----
+    // ---- two-level "last one done" reduction (fixed order => deterministic): the last CTA of each group of
+    // SINGLE_GROUP consecutive CTAs sums the group's partials, the last group to finish sums the group sums and
+    // finalizes.  Only ~SINGLE_GROUP + P/SINGLE_GROUP loads per value sit on the critical path, all in flight at once.
+    const int NG = (P + SINGLE_GROUP - 1) / SINGLE_GROUP;
+    const int gidx = blockIdx.x / SINGLE_GROUP;
+    const int g0 = gidx * SINGLE_GROUP;
+    const int gsize = min(SINGLE_GROUP, P - g0);
+    int *tk = a.tickets + (size_t)b * (1 + NG);         // [0]: groups done, [1 + g]: CTAs of group g done
+    double *gsum = a.spart + (size_t)a.d.B * P * NV + ((size_t)b * NG) * NV;   // [NG][NV] group sums of rollout b
     __threadfence();
     __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(&a.tickets[b], 1) == P - 1);
+    if (tid == 0) s_last = (atomicAdd(&tk[1 + gidx], 1) == gsize - 1);
     __syncthreads();
     if (!s_last) return;
     __threadfence();
     {
-        const double *src = a.spart + (size_t)b * P * NV;
+        const double *src = a.spart + ((size_t)b * P + g0) * NV;
         for (int v = tid; v < NV; v += SINGLE_THREADS) {
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            int p = 0;
-            for (; p + 4 <= P; p += 4) {
-                s0 += __ldcg(src + (size_t)(p + 0) * NV + v);
-                s1 += __ldcg(src + (size_t)(p + 1) * NV + v);
-                s2 += __ldcg(src + (size_t)(p + 2) * NV + v);
-                s3 += __ldcg(src + (size_t)(p + 3) * NV + v);
-            }
-            for (; p < P; ++p) s0 += __ldcg(src + (size_t)p * NV + v);
-            fin[v] = (s0 + s1) + (s2 + s3);
+            double x[SINGLE_GROUP];
+#pragma unroll
+            for (int q = 0; q < SINGLE_GROUP; ++q) x[q] = q < gsize ? __ldcg(src + (size_t)q * NV + v) : 0.0;
+            double sacc = 0.0;
+#pragma unroll
+            for (int q = 0; q < SINGLE_GROUP; ++q) sacc += x[q];
+            gsum[(size_t)gidx * NV + v] = sacc;
         }
     }
+    __threadfence();
     __syncthreads();
-    if (tid < EG)
-        finalize_math(a.d, a.t, a.out_idx[tid], b, &fin[tid * NA], &fin[EG * NA + tid * NA], a.us, a.hyp, a.mu, a.var,
-                      a.tape, a.want_grad);
-    if (tid == 0) a.tickets[b] = 0;                      // ready for the next launch on this stream
+    if (tid == 0) { tk[1 + gidx] = 0; s_last = (atomicAdd(&tk[0], 1) == NG - 1); }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int v = tid; v < NV; v += SINGLE_THREADS) {
+        double sacc = 0.0;
+        for (int q0 = 0; q0 < NG; q0 += SINGLE_GROUP) {
+            double x[SINGLE_GROUP];
+#pragma unroll
+            for (int q = 0; q < SINGLE_GROUP; ++q) x[q] = q0 + q < NG ? __ldcg(gsum + (size_t)(q0 + q) * NV + v) : 0.0;
+#pragma unroll
+            for (int q = 0; q < SINGLE_GROUP; ++q) sacc += x[q];
+        }
+        fin[v] = sacc;
+    }
+    __syncthreads();
+    if (wid < EG)                                        // warp <-> output, lane <-> input dimension
+        finalize_math_lanes(a.d, a.t, a.out_idx[wid], b, lane, &fin[wid * NA], &fin[EG * NA + wid * NA], a.us, a.hyp,
+                            a.mu, a.var, a.tape, a.want_grad);
+    if (tid == 0) tk[0] = 0;                             // counters are zero again for the next launch on this stream
     if (a.prep_next) {
         __syncthreads();                                 // mean_t / var_t of all outputs are written
         if (tid < D) {

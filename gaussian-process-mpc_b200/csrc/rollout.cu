@@ -237,38 +237,65 @@ __global__ void init_state_kernel(const double *__restrict__ x0int, int B, int B
 // Small dense LU (partial pivoting) in local memory: determinant and inverse of an E x E matrix.
 // Same algorithm as the LAPACK getrf/getri behind torch.linalg.det / inv (src/mpc.py:179-185).
 // ---------------------------------------------------------------------------------------------
-__device__ double lu_det_inv(int E, const double *Ain, double *inv)
+// E is a compile-time constant so that the matrix lives in registers (a run-time E puts it in local memory and
+// every access on the dependency chain pays an L1 round trip); row swaps use predicated moves, no dynamic index.
+template <int E>
+__device__ __forceinline__ double lu_det_inv_t(const double *Ain, double *inv)
 {
-    double A[kMaxE * kMaxE];
-    int piv[kMaxE];
+    double A[E][E];
+    int piv[E];
     double det = 1.0;
-    for (int i = 0; i < E * E; ++i) A[i] = Ain[i];
+#pragma unroll
+    for (int r = 0; r < E; ++r)
+#pragma unroll
+        for (int k = 0; k < E; ++k) A[r][k] = Ain[r * E + k];
+#pragma unroll
     for (int c = 0; c < E; ++c) {
         int p = c;
-        for (int r = c + 1; r < E; ++r) if (fabs(A[r * E + c]) > fabs(A[p * E + c])) p = r;
+        double best = fabs(A[c][c]);
+#pragma unroll
+        for (int r = c + 1; r < E; ++r) { const double v = fabs(A[r][c]); if (v > best) { best = v; p = r; } }
         piv[c] = p;
-        if (p != c) {
-            for (int k = 0; k < E; ++k) { const double tmp = A[c * E + k]; A[c * E + k] = A[p * E + k]; A[p * E + k] = tmp; }
-            det = -det;
-        }
-        det *= A[c * E + c];
-        const double dinv = 1.0 / A[c * E + c];
+#pragma unroll
+        for (int r = c + 1; r < E; ++r)
+            if (r == p) {
+#pragma unroll
+                for (int k = 0; k < E; ++k) { const double tmp = A[c][k]; A[c][k] = A[r][k]; A[r][k] = tmp; }
+            }
+        if (p != c) det = -det;
+        det *= A[c][c];
+        const double dinv = 1.0 / A[c][c];
+#pragma unroll
         for (int r = c + 1; r < E; ++r) {
-            const double f = A[r * E + c] * dinv;
-            A[r * E + c] = f;
-            for (int k = c + 1; k < E; ++k) A[r * E + k] -= f * A[c * E + k];
+            const double f = A[r][c] * dinv;
+            A[r][c] = f;
+#pragma unroll
+            for (int k = c + 1; k < E; ++k) A[r][k] -= f * A[c][k];
         }
     }
     if (inv) {
+#pragma unroll
         for (int col = 0; col < E; ++col) {
-            double x[kMaxE];
+            double x[E];
+#pragma unroll
             for (int r = 0; r < E; ++r) x[r] = (r == col) ? 1.0 : 0.0;
-            for (int c = 0; c < E; ++c) { const int p = piv[c]; if (p != c) { const double tmp = x[c]; x[c] = x[p]; x[p] = tmp; } }
-            for (int r = 0; r < E; ++r) for (int k = 0; k < r; ++k) x[r] -= A[r * E + k] * x[k];
-            for (int r = E - 1; r >= 0; --r) {
-                for (int k = r + 1; k < E; ++k) x[r] -= A[r * E + k] * x[k];
-                x[r] /= A[r * E + r];
+#pragma unroll
+            for (int c = 0; c < E; ++c) {
+#pragma unroll
+                for (int r = c + 1; r < E; ++r)
+                    if (r == piv[c]) { const double tmp = x[c]; x[c] = x[r]; x[r] = tmp; }
             }
+#pragma unroll
+            for (int r = 0; r < E; ++r)
+#pragma unroll
+                for (int k = 0; k < r; ++k) x[r] -= A[r][k] * x[k];
+#pragma unroll
+            for (int r = E - 1; r >= 0; --r) {
+#pragma unroll
+                for (int k = r + 1; k < E; ++k) x[r] -= A[r][k] * x[k];
+                x[r] /= A[r][r];
+            }
+#pragma unroll
             for (int r = 0; r < E; ++r) inv[r * E + col] = x[r];
         }
     }
@@ -297,38 +324,60 @@ struct CostArgs {
 // State cost of time t and its partials (src/mpc.py:179-185):
 //   c_t = 1/gamma log det(I + gamma Q Sigma_t) + e^T (Q^-1 + gamma Sigma_t)^-1 e,  e = mu_t - x_ref
 // d c_t / d mu = (G + G^T) e,  d c_t / d sigma_k^2 = (M^-1 Q)_kk - gamma (G^T e)_k (G e)_k
-__device__ double state_cost_terms(const CostArgs &a, int b, int t, double gamma, double *dmu, double *dvar)
+template <int E>
+__device__ __forceinline__ double state_cost_terms_t(const CostArgs &a, int b, int t, double gamma, double *dmu, double *dvar)
 {
-    const int E = a.d.E, Bp = a.d.Bpad;
-    double M[kMaxE * kMaxE], Minv[kMaxE * kMaxE], Gm[kMaxE * kMaxE], G[kMaxE * kMaxE], e[kMaxE], sg[kMaxE];
+    const int Bp = a.d.Bpad;
+    double M[E * E], Minv[E * E], Gm[E * E], G[E * E], e[E], sg[E];
+#pragma unroll
     for (int k = 0; k < E; ++k) {
         sg[k] = a.var[((size_t)t * E + k) * Bp + b];
         e[k] = a.mu[((size_t)t * E + k) * Bp + b] - a.xref[k];
     }
+#pragma unroll
     for (int r = 0; r < E; ++r)
+#pragma unroll
         for (int k = 0; k < E; ++k) {
             M[r * E + k] = (r == k ? 1.0 : 0.0) + gamma * a.Q[r * E + k] * sg[k];     // I + gamma Q Sigma
             Gm[r * E + k] = a.Qi[r * E + k] + (r == k ? gamma * sg[k] : 0.0);         // Q^-1 + gamma Sigma
         }
-    const double det = lu_det_inv(E, M, a.want_grad ? Minv : nullptr);
-    lu_det_inv(E, Gm, G);
+    const double det = lu_det_inv_t<E>(M, a.want_grad ? Minv : nullptr);
+    lu_det_inv_t<E>(Gm, G);
     double cost = (1.0 / gamma) * log(det);            // log of the determinant (NaN if det < 0), mpc.py:183
-    double Ge[kMaxE], Gte[kMaxE];
+    double Ge[E], Gte[E];
+#pragma unroll
     for (int r = 0; r < E; ++r) {
         double s1 = 0.0, s2 = 0.0;
+#pragma unroll
         for (int k = 0; k < E; ++k) { s1 += G[r * E + k] * e[k]; s2 += G[k * E + r] * e[k]; }
         Ge[r] = s1; Gte[r] = s2;
     }
+#pragma unroll
     for (int k = 0; k < E; ++k) cost += e[k] * Ge[k];
     if (a.want_grad) {
+#pragma unroll
         for (int k = 0; k < E; ++k) {
             double mq = 0.0;
+#pragma unroll
             for (int r = 0; r < E; ++r) mq += Minv[k * E + r] * a.Q[r * E + k];
             dmu[k] = Ge[k] + Gte[k];
             dvar[k] = mq - gamma * Gte[k] * Ge[k];
         }
     }
     return cost;
+}
+__device__ __noinline__ double state_cost_terms(const CostArgs &a, int b, int t, double gamma, double *dmu, double *dvar)
+{
+    switch (a.d.E) {
+        case 1: return state_cost_terms_t<1>(a, b, t, gamma, dmu, dvar);
+        case 2: return state_cost_terms_t<2>(a, b, t, gamma, dmu, dvar);
+        case 3: return state_cost_terms_t<3>(a, b, t, gamma, dmu, dvar);
+        case 4: return state_cost_terms_t<4>(a, b, t, gamma, dmu, dvar);
+        case 5: return state_cost_terms_t<5>(a, b, t, gamma, dmu, dvar);
+        case 6: return state_cost_terms_t<6>(a, b, t, gamma, dmu, dvar);
+        case 7: return state_cost_terms_t<7>(a, b, t, gamma, dmu, dvar);
+        default: return state_cost_terms_t<8>(a, b, t, gamma, dmu, dvar);
+    }
 }
 
 // Direct cost of action j (src/mpc.py:188-198): (u_j-u_ref)^T R (u_j-u_ref) + delta_j^T Rd delta_j, and the
@@ -421,7 +470,13 @@ __global__ void __launch_bounds__(128) cost_adjoint_small_kernel(const CostArgs 
     double *gact = seed_var + (size_t)(H + 1) * E; // [H * m]
     double *cpart = gact + (size_t)H * (m > 0 ? m : 1);   // [2H + 1]
     double *carry = cpart + 2 * H + 1;             // [2E]: mb, vb
+    double *tps = carry + 2 * E;                   // [H * E * 4D]: the partial derivatives of this rollout's tape
     const double gamma = (a.mode == 0) ? a.gamma[b] : 0.0;
+    if (a.want_grad)                               // all loads in flight at once instead of one latency per step
+        for (int i = tid; i < H * E * 4 * D; i += blockDim.x) {
+            const int e = i % (4 * D), to = i / (4 * D);
+            tps[i] = a.tape[((size_t)to * NT + 2 + e) * Bp + b];
+        }
     for (int t = tid; t <= H; t += blockDim.x) {
         double dmu[kMaxE], dvar[kMaxE];
         for (int k = 0; k < E; ++k) dmu[k] = dvar[k] = 0.0;
@@ -460,10 +515,10 @@ __global__ void __launch_bounds__(128) cost_adjoint_small_kernel(const CostArgs 
         double ub = 0.0, sb = 0.0;
         if (k < D) {
             for (int o = 0; o < E; ++o) {
-                const double *tp = a.tape + (((size_t)(t - 1) * E + o) * NT) * Bp + b;
+                const double *tp = tps + ((size_t)(t - 1) * E + o) * 4 * D;    // dm/du, dm/ds, dv/du, dv/ds
                 const double mo = carry[o], vo = carry[E + o];
-                ub += mo * tp[(size_t)(2 + k) * Bp] + vo * tp[(size_t)(2 + 2 * D + k) * Bp];
-                sb += mo * tp[(size_t)(2 + D + k) * Bp] + vo * tp[(size_t)(2 + 3 * D + k) * Bp];
+                ub += mo * tp[k] + vo * tp[2 * D + k];
+                sb += mo * tp[D + k] + vo * tp[3 * D + k];
             }
         }
         __syncwarp();
@@ -480,8 +535,14 @@ __global__ void __launch_bounds__(128) cost_adjoint_small_kernel(const CostArgs 
 static void launch_cost_adjoint(gpmpc_ctx *h, const CostArgs &ca, int B, int H)
 {
     if (B < kSingleMaxB) {
-        const size_t smem = ((size_t)2 * (H + 1) * ca.d.E + (size_t)H * (ca.d.m > 0 ? ca.d.m : 1) + 2 * H + 1 + 2 * ca.d.E) * sizeof(double);
-        if (smem <= 40 * 1024) {
+        const size_t smem = ((size_t)2 * (H + 1) * ca.d.E + (size_t)H * (ca.d.m > 0 ? ca.d.m : 1) + 2 * H + 1 + 2 * ca.d.E +
+                             (size_t)H * ca.d.E * 4 * ca.d.D) * sizeof(double);
+        if (smem <= 160 * 1024) {
+            static bool configured = false;
+            if (!configured) {
+                cudaFuncSetAttribute(cost_adjoint_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+                configured = true;
+            }
             cost_adjoint_small_kernel<<<B, 128, smem, h->stream>>>(ca);
             return;
         }
@@ -636,7 +697,8 @@ static int reserve_rollout(gpmpc_ctx *h, int B, int H, RolloutWork &w)
     w.total_tiles = (B < kSingleMaxB) ? nt * (nt + 1) / 2 : pair_batch_tiles(h->ld);
     pair_geometry(h, B, w.total_tiles, w.ctas, w.P);
     const bool few = B < kSingleMaxB;
-    const size_t n_tickets = few ? (size_t)B : (size_t)((B + PAIR_THREADS - 1) / PAIR_THREADS);
+    const size_t n_groups = (size_t)(w.P + SINGLE_GROUP - 1) / SINGLE_GROUP;
+    const size_t n_tickets = few ? (size_t)B * (1 + n_groups) : (size_t)((B + PAIR_THREADS - 1) / PAIR_THREADS);
     GP_CUDA(h, h->tickets.reserve(n_tickets * sizeof(int)));
     if (few) GP_CUDA(h, cudaMemsetAsync(h->tickets.as<int>(), 0, n_tickets * sizeof(int), h->stream));
     const size_t Bp = d.Bpad;
@@ -644,8 +706,8 @@ static int reserve_rollout(gpmpc_ctx *h, int B, int H, RolloutWork &w)
     GP_CUDA(h, h->mu.reserve((size_t)(H + 1) * d.E * Bp * sizeof(double)));
     GP_CUDA(h, h->var.reserve((size_t)(H + 1) * d.E * Bp * sizeof(double)));
     GP_CUDA(h, h->tape.reserve((size_t)Hs * d.E * ntape(d.D) * Bp * sizeof(double)));
-    // few rollouts: [B][P][2 * 4 * nacc] (pair + mean partials of one lambda group); else [P][E][nacc][Bp]
-    GP_CUDA(h, h->part.reserve(few ? (size_t)B * w.P * 2 * kGroupMax * nacc(d.D) * sizeof(double)
+    // few rollouts: [B][P + groups][2 * 4 * nacc] (pair + mean partials of one lambda group); else [P][E][nacc][Bp]
+    GP_CUDA(h, h->part.reserve(few ? (size_t)B * (w.P + n_groups) * 2 * kGroupMax * nacc(d.D) * sizeof(double)
                                    : (size_t)w.P * d.E * nacc(d.D) * Bp * sizeof(double)));
     GP_CUDA(h, h->mpart.reserve((size_t)MEAN_JP * d.E * nacc(d.D) * Bp * sizeof(double)));
     // cst: x0int [E][Bp] | Uint [H*m][Bp] | us [2D][Bp] | cst [G][4D][Bp]
