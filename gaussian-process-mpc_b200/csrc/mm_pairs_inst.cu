@@ -51,8 +51,15 @@ static cudaError_t launch_single_one(const SingleStepArgs &a, const PairTma &tm,
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    mm_step_single<D, EG, GRAD><<<grid, SINGLE_THREADS, smem, st>>>(a, tm);
-    return cudaGetLastError();
+    // programmatic dependent launch: consecutive step kernels overlap this grid's prologue (barrier setup, first
+    // TMA tile loads) with the previous grid's tail; the kernel orders itself with griddepcontrol.wait
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(SINGLE_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, mm_step_single<D, EG, GRAD>, a, tm);
 }
 
 template <int D>

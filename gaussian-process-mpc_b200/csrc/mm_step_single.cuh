@@ -83,8 +83,10 @@ mm_step_single(const SingleStepArgs a, const __grid_constant__ PairTma tm)
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int b = blockIdx.y;                            // rollout
     const int P = gridDim.x;
+    // Programmatic dependent launch: the next step's grid may be scheduled while this one drains; everything up
+    // to griddepcontrol.wait touches only data no step kernel writes (the exp table, Wt, X).
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     if (tid < 16) tab[tid] = kExp2Tab[tid];
-    if (tid < 4 * D) cs[tid] = a.cst[(size_t)tid * a.d.Bpad + b];
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < SINGLE_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], SINGLE_WARPS); }
@@ -126,6 +128,67 @@ mm_step_single(const SingleStepArgs a, const __grid_constant__ PairTma tm)
 #pragma unroll
         for (int s = 0; s < SINGLE_STAGES - 1; ++s)
             if (issued < t_end) issue_next();
+    }
+
+    // the first tiles are in flight; now wait until the previous kernel on the stream (the preceding step) is
+    // complete and its writes (this step's constants, the ticket counters, the partial buffers) are visible
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    if (tid < 4 * D) cs[tid] = a.cst[(size_t)tid * a.d.Bpad + b];
+    __syncthreads();
+    double *mine = a.spart + ((size_t)b * P + blockIdx.x) * NV;
+
+    // ---- mean sums over this CTA's slice of the training set (lanes <-> training points), done while the first
+    // tiles land.  Scratch = the last ring slot (the prologue fills slots 0 .. STAGES-2 only).
+    // p_k = cm_k (u_k - x_jk),  l_j = exp(-sum p_k^2),  M0 += beta_j l_j, M1_k += beta_j l_j p_k, M2_k += .. p_k^2
+    {
+        constexpr int RCAP = (int)(STAGE / (EG * NA)) < SINGLE_THREADS ? (int)(STAGE / (EG * NA)) : SINGLE_THREADS;
+        const int per = (a.ld + P - 1) / P;
+        const int j_begin = blockIdx.x * per;
+        const int j_end = min(a.ld, j_begin + per);
+        const int rows = min(max(j_end - j_begin, 0), RCAP);             // threads that own >= 1 point
+        double *scratch = smem + (size_t)(SINGLE_STAGES - 1) * STAGE;    // [thread][EG*NA]
+        if (tid < rows) {
+            double m0[EG], m1[EG][D], m2[EG][D];
+#pragma unroll
+            for (int g = 0; g < EG; ++g) {
+                m0[g] = 0.0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) m1[g][k] = m2[g][k] = 0.0;
+            }
+            for (int j = j_begin + tid; j < j_end; j += rows) {
+                double p[D], pp[D], S = 0.0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    p[k] = fma(-cs[2 * D + k], a.X[(size_t)j * D + k], cs[3 * D + k]);
+                    pp[k] = p[k] * p[k];
+                    S += pp[k];
+                }
+                const double l = exp_neg(S, tab);
+#pragma unroll
+                for (int g = 0; g < EG; ++g) {
+                    const double w = a.beta[g][j] * l;
+                    m0[g] += w;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) { m1[g][k] = fma(w, p[k], m1[g][k]); m2[g][k] = fma(w, pp[k], m2[g][k]); }
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < EG; ++g) {
+                scratch[(size_t)tid * (EG * NA) + g * NA] = m0[g];
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    scratch[(size_t)tid * (EG * NA) + g * NA + 1 + k] = m1[g][k];
+                    scratch[(size_t)tid * (EG * NA) + g * NA + 1 + D + k] = m2[g][k];
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < EG * NA) {
+            double sacc = 0.0;
+            for (int r = 0; r < rows; ++r) sacc += scratch[(size_t)r * (EG * NA) + tid];
+            mine[EG * NA + tid] = sacc;
+        }
+        __syncthreads();                                 // the slot is free again before tile STAGES-1 is issued into it
     }
 
     int curI = -1;
@@ -207,64 +270,12 @@ mm_step_single(const SingleStepArgs a, const __grid_constant__ PairTma tm)
             if (lane == 0) { red[wid][g * NA + 1 + k] = v1; red[wid][g * NA + 1 + D + k] = v2; }
         }
     }
-    __syncthreads();                                     // also: every warp has left the tile ring
-    double *mine = a.spart + ((size_t)b * P + blockIdx.x) * NV;
+    __syncthreads();
     if (tid < EG * NA) {
         double s = 0.0;
 #pragma unroll
         for (int w = 0; w < SINGLE_WARPS; ++w) s += red[w][tid];
         mine[tid] = s;
-    }
-
-    // ---- mean sums over this CTA's slice of the training set (lanes <-> training points) ----
-    // p_k = cm_k (u_k - x_jk),  l_j = exp(-sum p_k^2),  M0 += beta_j l_j, M1_k += beta_j l_j p_k, M2_k += .. p_k^2
-    {
-        const int per = (a.ld + P - 1) / P;
-        const int j_begin = blockIdx.x * per;
-        const int j_end = min(a.ld, j_begin + per);
-        const int rows = min(max(j_end - j_begin, 0), SINGLE_THREADS);   // threads that own >= 1 point
-        double *scratch = smem;                          // [thread][EG*NA] (the ring is idle now)
-        if (tid < rows) {
-            double m0[EG], m1[EG][D], m2[EG][D];
-#pragma unroll
-            for (int g = 0; g < EG; ++g) {
-                m0[g] = 0.0;
-#pragma unroll
-                for (int k = 0; k < D; ++k) m1[g][k] = m2[g][k] = 0.0;
-            }
-            for (int j = j_begin + tid; j < j_end; j += SINGLE_THREADS) {
-                double p[D], pp[D], S = 0.0;
-#pragma unroll
-                for (int k = 0; k < D; ++k) {
-                    p[k] = fma(-cs[2 * D + k], a.X[(size_t)j * D + k], cs[3 * D + k]);
-                    pp[k] = p[k] * p[k];
-                    S += pp[k];
-                }
-                const double l = exp_neg(S, tab);
-#pragma unroll
-                for (int g = 0; g < EG; ++g) {
-                    const double w = a.beta[g][j] * l;
-                    m0[g] += w;
-#pragma unroll
-                    for (int k = 0; k < D; ++k) { m1[g][k] = fma(w, p[k], m1[g][k]); m2[g][k] = fma(w, pp[k], m2[g][k]); }
-                }
-            }
-#pragma unroll
-            for (int g = 0; g < EG; ++g) {
-                scratch[(size_t)tid * (EG * NA) + g * NA] = m0[g];
-#pragma unroll
-                for (int k = 0; k < D; ++k) {
-                    scratch[(size_t)tid * (EG * NA) + g * NA + 1 + k] = m1[g][k];
-                    scratch[(size_t)tid * (EG * NA) + g * NA + 1 + D + k] = m2[g][k];
-                }
-            }
-        }
-        __syncthreads();
-        if (tid < EG * NA) {
-            double s = 0.0;
-            for (int r = 0; r < rows; ++r) s += scratch[(size_t)r * (EG * NA) + tid];
-            mine[EG * NA + tid] = s;
-        }
     }
 
     // ---- two-level "last one done" reduction (fixed order => deterministic): the last CTA of each group of
