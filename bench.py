@@ -248,7 +248,8 @@ def run_ours(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     roofline = {
         "bound": "fp64_pipe", "kernel": "mm_pairs_batch<5,4,grad>", "achieved": achieved_tflops, "peak": fma_tflops,
-        "unit": "TFLOP/s", "frac": achieved_tflops / fma_tflops if fma_tflops else None, "traffic": None,
+        "unit": "TFLOP/s", "frac": achieved_tflops / fma_tflops if fma_tflops else None,
+        "traffic": 460.4e6,       # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/r01b_*)
         "note": "FP64-pipe instructions (x2 flop) per launch / CUDA-event duration of the pair kernel; peak = DFMA rate "
                 "measured live by gpmpc_measure_fp64_peak (MEASURED_PEAKS.json has no fp64 figure); this kernel is "
                 "neither HBM- nor tensor-bound (see DESIGN.md)",
@@ -295,6 +296,19 @@ def run_ours(args):
             solver = "cyipopt"
         except ImportError:
             solver = "scipy L-BFGS-B over the same callbacks (cyipopt is not installed)"
+        # the B = 1 step kernel streams the Wt upper triangles once per horizon step: it is the HBM-bound kernel of the path
+        bundle.pair_kernel_timing()
+        x1 = torch.tensor(x0[None, :], device=dev); U1 = torch.tensor(U_all[:1], device=dev); g1 = torch.tensor([-1.0], device=dev, dtype=torch.float64)
+        bundle.cost_grad(x1, U1, g1, Q, R, want_grad=True, host_out=False); torch.cuda.synchronize()
+        single_ms, _ = bundle.pair_kernel_timing()
+        line["roofline_single"] = {
+            "bound": "hbm", "kernel": "mm_step_single<5,4,grad> (B=1: one fused launch per horizon step)",
+            "achieved": bytes_algo / (single_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+            "frac": bytes_algo / (single_ms * 1e-3) / 1e9 / hbm_peak, "traffic": 271.0e6,
+            "ms_per_launch": single_ms / H,
+            "note": "algorithmic bytes = H*E*n(n+1)/2*8 (Wt upper triangle once per step) / CUDA-event time of the H "
+                    "launches of one B=1 evaluation (events on the library stream, programmatic dependent launch off "
+                    "between timed launches); traffic = dram__bytes_read+write per launch from profiles/r01c_*"}
         line["single_solve"] = {"objective_plus_gradient_ms": 1e3 * float(np.median(lat)),
                                 "solve_p50_ms": 1e3 * float(np.median([t for t, _ in solves])),
                                 "evals_per_solve": [k for _, k in solves], "solver": solver,

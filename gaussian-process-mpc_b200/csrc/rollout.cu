@@ -176,35 +176,51 @@ __global__ void __launch_bounds__(MEAN_THREADS) mean_sums_kernel(const MeanArgs 
 // determinant prefactors and writes mean/var of step t plus the tape entry.
 //   tape[((t-1)*E + a) * (2+4D) + e][Bpad]:  e = 0 mean, 1 var, 2.. dm/du, dm/ds, dv/du, dv/ds
 // ---------------------------------------------------------------------------------------------
-constexpr int FIN_WARPS = 4;
+constexpr int FIN_WARPS = 16;
+static_assert(MEAN_JP <= FIN_WARPS, "one warp per mean partition");
+__host__ __device__ inline size_t finalize_smem_bytes(int D) { return (size_t)FIN_WARPS * 2 * nacc(D) * 32 * sizeof(double); }
 __global__ void __launch_bounds__(32 * FIN_WARPS)
 finalize_step_kernel(StepDims d, int t, int P, const double *__restrict__ part,
                      const double *__restrict__ mpart, const double *__restrict__ us,
                      const double *__restrict__ hyp, double *__restrict__ mu,
                      double *__restrict__ var, double *__restrict__ tape, int want_grad)
 {
-    // block = 32 rollouts (lanes) x FIN_WARPS slices of the partial-sum list; fixed summation order
-    __shared__ double red[FIN_WARPS][2 * (1 + 2 * kMaxD)][32];
+    // block = 32 rollouts (lanes) x FIN_WARPS interleaved slices of the partial-sum list.  The list can be long
+    // (16 work items per pair-kernel CTA), so every thread keeps 4 independent loads in flight per statistic; the
+    // summation order is fixed: 4 strided chains per warp, then the warps in index order.
+    extern __shared__ double red[];                  // [FIN_WARPS][2 * NA][32]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int b = blockIdx.x * 32 + lane;
     const int a = blockIdx.y;
     const int D = d.D, NA = 1 + 2 * D;
     const bool live = b < d.B;
+    const size_t stride = (size_t)d.E * NA * d.Bpad;     // one work item
     for (int e = 0; e < NA; ++e) {
-        double s = 0.0, sm = 0.0;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, sm = 0.0;
         if (live) {
-            for (int p = wid; p < P; p += FIN_WARPS) s += part[(((size_t)p * d.E + a) * NA + e) * d.Bpad + b];
-            for (int p = wid; p < MEAN_JP; p += FIN_WARPS) sm += mpart[(((size_t)p * d.E + a) * NA + e) * d.Bpad + b];
+            const double *src = part + ((size_t)a * NA + e) * d.Bpad + b;
+            int p = wid;
+            for (; p + 3 * FIN_WARPS < P; p += 4 * FIN_WARPS) {
+                s0 += src[(size_t)p * stride];
+                s1 += src[(size_t)(p + FIN_WARPS) * stride];
+                s2 += src[(size_t)(p + 2 * FIN_WARPS) * stride];
+                s3 += src[(size_t)(p + 3 * FIN_WARPS) * stride];
+            }
+            for (; p < P; p += FIN_WARPS) s0 += src[(size_t)p * stride];
+            if (wid < MEAN_JP) sm = mpart[(((size_t)wid * d.E + a) * NA + e) * d.Bpad + b];
         }
-        red[wid][e][lane] = s;
-        red[wid][NA + e][lane] = sm;
+        red[((size_t)wid * 2 * NA + e) * 32 + lane] = (s0 + s1) + (s2 + s3);
+        red[((size_t)wid * 2 * NA + NA + e) * 32 + lane] = sm;
     }
     __syncthreads();
     if (wid != 0 || !live) return;
     double accN[1 + 2 * kMaxD], accM[1 + 2 * kMaxD];
     for (int e = 0; e < NA; ++e) {
         double s = 0.0, sm = 0.0;
-        for (int w = 0; w < FIN_WARPS; ++w) { s += red[w][e][lane]; sm += red[w][NA + e][lane]; }
+        for (int w = 0; w < FIN_WARPS; ++w) {
+            s += red[((size_t)w * 2 * NA + e) * 32 + lane];
+            sm += red[((size_t)w * 2 * NA + NA + e) * 32 + lane];
+        }
         accN[e] = s; accM[e] = sm;
     }
     finalize_math(d, t, a, b, accN, accM, us, hyp, mu, var, tape, want_grad);
@@ -676,7 +692,13 @@ static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int ctas, int P, lon
     if (h->time_pairs) cudaEventRecord(h->ev1, h->stream);
     if (!few) {
         dim3 fgrid((d.B + 31) / 32, d.E);
-        finalize_step_kernel<<<fgrid, 32 * FIN_WARPS, 0, h->stream>>>(d, t, P, h->part.as<double>(), h->mpart.as<double>(),
+        static bool fin_configured = false;
+        if (!fin_configured) {
+            GP_CUDA(h, cudaFuncSetAttribute(finalize_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)finalize_smem_bytes(kMaxD)));
+            fin_configured = true;
+        }
+        finalize_step_kernel<<<fgrid, 32 * FIN_WARPS, finalize_smem_bytes(d.D), h->stream>>>(d, t, P, h->part.as<double>(), h->mpart.as<double>(),
                                                                       us, h->hyp.as<double>(), mu, var, tape,
                                                                       want_grad ? 1 : 0);
         GP_LAUNCH_CHECK(h);

@@ -55,6 +55,19 @@ class RiskSensitiveMPC:
         self.lb = [-1e16 for _ in range(self.input_dim)]
         self.train_empty = True
         self.n_evals = 0
+        self._host_cache = {}
+
+    def _host(self, name, v):
+        """Host fp64 copy of an attribute; device tensors are copied once per (tensor, in-place version) instead
+        of once per callback (each copy is a device synchronisation on the IPOPT critical path)."""
+        if not isinstance(v, torch.Tensor):
+            return np.asarray(v, dtype=np.float64)
+        key = (id(v), v._version)
+        hit = self._host_cache.get(name)
+        if hit is None or hit[0] != key:
+            hit = (key, v, _to_numpy(v))                 # keeps `v` alive so that its id cannot be reused
+            self._host_cache[name] = hit
+        return hit[2]
 
     # ---- setters (src/mpc.py:72-116) ---------------------------------------------------------------
     def set_ub(self, ub):
@@ -112,17 +125,17 @@ class RiskSensitiveMPC:
     def _evaluate(self, x):
         H, m = self.horizon, self.input_dim
         U = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(1, H, m))
-        x0 = _to_numpy(self.curr_state).reshape(1, self.state_dim)
+        x0 = self._host("curr_state", self.curr_state).reshape(1, self.state_dim)
         dyn = self.dynamics
         dyn._require_data()
         dyn._sync_propagation_hypers()
         last_u = None
         if self.R_delta is not None:
             last_u = np.asarray(self.last_traj[0:m], dtype=np.float64).reshape(1, m)
-        cost, grad, _, _ = dyn._bundle.cost_grad(x0, U, np.array([float(self.gamma)]), _to_numpy(self.Q),
-                                                 _to_numpy(self.R),
-                                                 None if self.R_delta is None else _to_numpy(self.R_delta), last_u,
-                                                 _to_numpy(self.x_ref), _to_numpy(self.u_ref))
+        cost, grad, _, _ = dyn._bundle.cost_grad(x0, U, np.array([float(self.gamma)]), self._host("Q", self.Q),
+                                                 self._host("R", self.R),
+                                                 None if self.R_delta is None else self._host("R_delta", self.R_delta),
+                                                 last_u, self._host("x_ref", self.x_ref), self._host("u_ref", self.u_ref))
         dyn._tape_serial += 1
         self.n_evals += 1
         self.curr_cost = float(cost[0])
