@@ -594,7 +594,10 @@ __global__ void __launch_bounds__(256) pairs_full_kernel(const double *__restric
             for (int k = 0; k < D; ++k) t = fma(fa.A[r * D + k], s[k], t);
             q = fma(s[r], t, q);
         }
-        double w = Wm[(size_t)i * ldw + j];
+        // RAW: Wm is a row-major [.., ldw] matrix; else the tile-major upper-triangular Wt (ldw = padded n)
+        double w = RAW ? Wm[(size_t)i * ldw + j]
+                       : Wm[wt_tile_index(i / kPairTile, j / kPairTile, ldw / kPairTile) * kPairTile * kPairTile +
+                            (i % kPairTile) * kPairTile + (j % kPairTile)];
         if (RAW) w = (w - beta[i] * beta[j]) * exp(-0.25 * el);
         acc = fma(w, exp(fa.scale * q), acc);
     }
@@ -758,7 +761,7 @@ static int moment_match_impl(gpmpc_handle h, int B, const double *U, const doubl
             sum_kernel<<<1, 1024, 0, h->stream>>>(bl, n, scal);
             GP_LAUNCH_CHECK(h);
             pairs_full_kernel<false><<<(n + 7) / 8, 256, 0, h->stream>>>(h->X.as<double>(), n, fs.var_arg,
-                                                                         h->Wt.as<double>() + a * mat, ld, nullptr, rows);
+                                                                         h->Wt.as<double>() + a * wt_doubles(ld), ld, nullptr, rows);
             GP_LAUNCH_CHECK(h);
             sum_kernel<<<1, 1024, 0, h->stream>>>(rows, n, scal + 1);
             GP_LAUNCH_CHECK(h);

@@ -13,13 +13,16 @@ namespace gpmpc {
 
 constexpr int kTile = 64;          // padding granule of n (fit GEMM tiles are 64x64)
 constexpr int kPairTile = 32;      // pair-space tile rows of the moment-matching kernels
-#ifndef GPMPC_PTJ
-#define GPMPC_PTJ 32
-#endif
-constexpr int kPairTileJ = GPMPC_PTJ;   // tile columns of mm_pairs_batch (must match mm_pairs.cuh)
 constexpr int kMaxD = GPMPC_MAX_D;
 constexpr int kMaxE = GPMPC_MAX_E;
 constexpr int kGroupMax = 4;       // outputs evaluated per pair-kernel pass (sharing one exp)
+
+// Wt storage: only the upper-triangular 32x32 tiles, each tile contiguous (8 KB, row-major inside), tiles in
+// row-major order of (I, J >= I).  A contiguous range of the tile list is a contiguous range of memory, which is
+// what the per-step kernels stream (bulk copies of whole tiles instead of 32 strided 256-byte rows).
+__host__ __device__ inline size_t wt_tiles(int ld) { const size_t nt = (size_t)ld / kPairTile; return nt * (nt + 1) / 2; }
+__host__ __device__ inline size_t wt_tile_index(int I, int J, int nt) { return (size_t)I * nt - (size_t)I * (I - 1) / 2 + (size_t)(J - I); }
+__host__ __device__ inline size_t wt_doubles(int ld) { return wt_tiles(ld) * kPairTile * kPairTile; }
 
 // number of accumulated statistics per (rollout, output) in q-space: T, N1[D], N2[D]
 __host__ __device__ constexpr int nacc(int D) { return 1 + 2 * D; }
@@ -66,13 +69,12 @@ struct gpmpc_ctx {
     gpmpc::DevBuf X;               // [ld, D]  (rows >= n are zero)
     gpmpc::DevBuf Y;               // [E, ld]
     gpmpc::DevBuf Kinv;            // [E, ld, ld]
-    gpmpc::DevBuf Wt;              // [E, ld, ld]  moment-matching weights (see fit.cu: derive_weights)
+    gpmpc::DevBuf Wt;              // [E][upper tiles][32*32]  moment-matching weights, tile-major (fit.cu: derive_weights)
     gpmpc::DevBuf beta;            // [E, ld]
     gpmpc::DevBuf chol, zt, tt;    // fit workspaces: L [ld,ld], L^-T [ld,ld], panel [ld,64]
     gpmpc::DevBuf linv;            // [64,64] inverse of the current diagonal block
     gpmpc::DevBuf info;            // int: index of first bad pivot + 1, 0 = ok
     gpmpc::DevBuf hyp;             // device copy of propagation hypers: lam[E,D], sf[E]
-    CUtensorMap wt_map[gpmpc::kMaxE];   // TMA descriptors of the Wt matrices (2-D, box 32x32), see fit.cu
 
     // rollout workspaces (grow-only)
     gpmpc::DevBuf mu, var, tape, cst, part, mpart, stage_in, stage_out, gbuf, tickets;
@@ -130,7 +132,6 @@ int derive_weights(gpmpc_ctx *h, int a);                // Wt[a] from Kinv[a], b
 int gram_into(gpmpc_ctx *h, int a, double *dst, int ldd, bool add_noise);   // Kf / Ky of output a
 void rebuild_groups(gpmpc_ctx *h);
 int upload_prop_hypers(gpmpc_ctx *h);
-int encode_wt_maps(gpmpc_ctx *h);                       // (re)build the TMA descriptors after Wt was (re)allocated
 
 // ---- gemm.cu ------------------------------------------------------------------------------
 // C[M,N] = alpha * A[M,K] * B[N,K]^T + beta * C   (all row-major, fp64, DMMA m8n8k4)

@@ -172,34 +172,42 @@ __global__ void gemv_kernel(const double *__restrict__ A, int ld, int n, const d
 //     Wt_ij = w(i,j) (Ky^-1 - beta beta^T)_ij exp(-1/4 ...),   w = 2 for j > i, 1 for j == i, 0 for j < i
 // so that the per-step kernels sweep only the upper triangle (the [u,S] part is symmetric in i,j).
 // ---------------------------------------------------------------------------------------------
-__global__ void derive_weights_kernel(const double *__restrict__ X, int n, int np, int D, HyperArg hp,
+__global__ void derive_weights_kernel(const double *__restrict__ X, int n, int D, HyperArg hp,
                                       const double *__restrict__ Kinv, const double *__restrict__ beta,
                                       double *__restrict__ Wt, int ld)
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y * blockDim.y + threadIdx.y;
-    if (i >= np || j >= np) return;
-    double v = 0.0;
-    if (i < n && j < n && j >= i) {
-        double q = 0.0;
-        for (int k = 0; k < D; ++k) {
-            const double d = X[(size_t)i * D + k] - X[(size_t)j * D + k];
-            q = fma(d * d, hp.inv_lam[k], q);
+    // one block per upper tile (I = blockIdx.y, J = blockIdx.x >= I); writes the tile-major layout of common.cuh
+    const int I = blockIdx.y, J = blockIdx.x;
+    if (J < I) return;
+    const int nt = ld / kPairTile;
+    double *tile = Wt + wt_tile_index(I, J, nt) * kPairTile * kPairTile;
+    const int c = threadIdx.x;
+    const int j = J * kPairTile + c;
+    for (int r = threadIdx.y; r < kPairTile; r += blockDim.y) {
+        const int i = I * kPairTile + r;
+        double v = 0.0;
+        if (i < n && j < n && j >= i) {
+            double q = 0.0;
+            for (int k = 0; k < D; ++k) {
+                const double d = X[(size_t)i * D + k] - X[(size_t)j * D + k];
+                q = fma(d * d, hp.inv_lam[k], q);
+            }
+            const double w = Kinv[(size_t)i * ld + j] - beta[i] * beta[j];
+            v = (j > i ? 2.0 : 1.0) * w * exp(-0.25 * q);
         }
-        const double w = Kinv[(size_t)i * ld + j] - beta[i] * beta[j];
-        v = (j > i ? 2.0 : 1.0) * w * exp(-0.25 * q);
+        tile[r * kPairTile + c] = v;
     }
-    Wt[(size_t)i * ld + j] = v;
 }
 
 int derive_weights(gpmpc_ctx *h, int a)
 {
     const size_t mat = (size_t)h->ld * h->ld;
-    dim3 blk(32, 8), grid((h->ld + 31) / 32, (h->ld + 7) / 8);
-    derive_weights_kernel<<<grid, blk, 0, h->stream>>>(h->X.as<double>(), h->n, h->ld, h->D, make_hyper(h, a, true),
+    const int nt = h->ld / kPairTile;
+    dim3 blk(32, 8), grid(nt, nt);
+    derive_weights_kernel<<<grid, blk, 0, h->stream>>>(h->X.as<double>(), h->n, h->D, make_hyper(h, a, true),
                                                        h->Kinv.as<double>() + a * mat,
                                                        h->beta.as<double>() + (size_t)a * h->ld,
-                                                       h->Wt.as<double>() + a * mat, h->ld);
+                                                       h->Wt.as<double>() + a * wt_doubles(h->ld), h->ld);
     GP_LAUNCH_CHECK(h);
     return GPMPC_OK;
 }
@@ -324,53 +332,18 @@ static int invert_factor(gpmpc_ctx *h, const double *L, double *ZT, int np)
     return GPMPC_OK;
 }
 
-// TMA descriptors for the per-step pair kernel: Wt[a] as a 2-D fp64 tensor {ld, ld}, 32x32 boxes, no swizzle.
-// cuTensorMapEncodeTiled is a driver entry point; it is resolved through the runtime so that libgpmpc.so
-// does not link libcuda directly.
-int encode_wt_maps(gpmpc_ctx *h)
-{
-    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static encode_fn encode = nullptr;
-    if (!encode) {
-        void *fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        GP_CUDA(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-        if (!fn || qres != cudaDriverEntryPointSuccess)
-            return fail(h, GPMPC_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
-        encode = reinterpret_cast<encode_fn>(fn);
-    }
-    const size_t mat = (size_t)h->ld * h->ld;
-    for (int a = 0; a < h->E; ++a) {
-        const cuuint64_t dims[2] = {(cuuint64_t)h->ld, (cuuint64_t)h->ld};
-        const cuuint64_t strides[1] = {(cuuint64_t)h->ld * sizeof(double)};
-        const cuuint32_t box[2] = {(cuuint32_t)kPairTileJ, (cuuint32_t)kPairTile};   // {columns, rows}
-        const cuuint32_t estr[2] = {1, 1};
-        CUresult r = encode(&h->wt_map[a], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, h->Wt.as<double>() + a * mat, dims, strides,
-                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(h, GPMPC_ERR_CUDA, "cuTensorMapEncodeTiled failed for a Wt matrix");
-    }
-    return GPMPC_OK;
-}
-
 int fit_all(gpmpc_ctx *h, const bool *which)
 {
     const int ld = h->ld, np = h->ld, n = h->n, E = h->E;
     const size_t mat = (size_t)ld * ld;
     GP_CUDA(h, h->Kinv.reserve(mat * E * sizeof(double)));
-    GP_CUDA(h, h->Wt.reserve(mat * E * sizeof(double)));
+    GP_CUDA(h, h->Wt.reserve(wt_doubles(ld) * E * sizeof(double)));
     GP_CUDA(h, h->beta.reserve((size_t)ld * E * sizeof(double)));
     GP_CUDA(h, h->chol.reserve(mat * sizeof(double)));
     GP_CUDA(h, h->zt.reserve(mat * sizeof(double)));
     GP_CUDA(h, h->tt.reserve((size_t)ld * NB * sizeof(double)));
     GP_CUDA(h, h->linv.reserve((size_t)NB * NB * sizeof(double)));
     GP_CUDA(h, h->info.reserve(sizeof(int)));
-    {
-        int rc_maps = encode_wt_maps(h);
-        if (rc_maps) return rc_maps;
-    }
 
     for (int a = 0; a < E; ++a) {
         if (!which[a]) continue;

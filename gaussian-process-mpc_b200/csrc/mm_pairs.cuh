@@ -14,8 +14,9 @@
 // mm_pairs_batch: lanes <-> rollouts.  Every lane of a warp owns one rollout b and keeps its
 // accumulators in registers for the whole kernel; the pair data (x_i, x_j, Wt_ij of up to 4 outputs that
 // share lambda and hence the exp) is warp-uniform and read from shared memory by broadcast, so the inner
-// loop has no cross-lane traffic at all.  Shared memory is filled by cp.async double buffering of 32x32
-// Wt tiles.  The kernel is bound by the FP64 pipe (one exp + ~14 + 12*EG DFMA-class ops per pair).
+// loop has no cross-lane traffic at all.  Shared memory is filled by the TMA engine: Wt is stored tile-major
+// (common.cuh), so a 32x32 tile is ONE contiguous 8 KB bulk copy (cp.async.bulk + mbarrier, SASS UBLKCP), double
+// buffered.  The kernel is bound by the FP64 pipe (one exp + ~14 + 12*EG DFMA-class ops per pair).
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
@@ -40,12 +41,6 @@ namespace gpmpc {
 #endif
 #ifndef GPMPC_ACC_ORDER
 #define GPMPC_ACC_ORDER 0        // accumulation loop nest: 0 output-major, 1 dimension-major, 2 e-scaled features
-#endif
-#ifndef GPMPC_USE_TMA
-#define GPMPC_USE_TMA 1          // 1: Wt tiles by TMA (cp.async.bulk.tensor.2d + mbarrier), 0: cp.async (LDGSTS)
-#endif
-#ifndef GPMPC_PTJ
-#define GPMPC_PTJ 32             // columns of a Wt tile of mm_pairs_batch (rows are always 32)
 #endif
 #ifndef GPMPC_PIPELINE
 #define GPMPC_PIPELINE 1         // 1: software-pipelined pair loop (exp chain of pair p+1 overlaps the sums of pair p)
@@ -168,8 +163,7 @@ __device__ __forceinline__ void cpa16(void *smem, const void *gmem)
 __device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// ---- TMA / mbarrier primitives (sm_90+ PTX; SASS: UTMALDG / UBLKCP / SYNCS) ----
-struct alignas(64) PairTma { CUtensorMap map[kGroupMax]; };   // one 2-D map per Wt matrix: dims {ld, ld}, box {32, 32}
+// ---- TMA (bulk copy) / mbarrier primitives (sm_90+ PTX; SASS: UBLKCP / SYNCS) ----
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(void *bar, unsigned count)
@@ -193,11 +187,6 @@ __device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
         "GPMPC_DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, void *bar)
-{
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
-                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, unsigned bytes, void *bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
@@ -205,7 +194,7 @@ __device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, unsigne
 }
 
 struct PairArgs {
-    const double *Wt[kGroupMax];   // weight matrices of the group's outputs (ld x ld, upper-tri weights)
+    const double *Wt[kGroupMax];   // weights of the group's outputs, tile-major upper-triangular tiles (common.cuh)
     int out_idx[kGroupMax];        // global output index of each member
     const double *X;               // [ld, D]
     const double *cst;             // this group's per-rollout constants [4D][Bpad]: c, c*u, cm, cm*u
@@ -218,21 +207,13 @@ struct PairArgs {
 #endif
 };
 
-constexpr int PT = kPairTile;      // 32: tile rows (and tile columns of mm_pairs_single)
-constexpr int PTJ = GPMPC_PTJ;     // tile columns of mm_pairs_batch
+constexpr int PT = kPairTile;      // 32: tile edge
+constexpr int PTJ = PT;
 constexpr int PAIR_THREADS = 128;
 constexpr int RI = GPMPC_RI;       // rows of the register micro-tile
 
 template <int D, int EG>
 __host__ __device__ constexpr size_t pair_stage_doubles() { return (size_t)EG * PT * PTJ + (PT + PTJ) * D; }
-// number of PT x PTJ tiles that intersect the upper triangle (row block I owns column blocks J >= I*PT/PTJ)
-__host__ __device__ inline long long pair_batch_tiles(int ld)
-{
-    const long long nr = ld / PT, nc = ld / PTJ;
-    long long t = 0;
-    for (long long i = 0; i < nr; ++i) t += nc - i * PT / PTJ;
-    return t;
-}
 // dynamic shared memory of mm_pairs_batch: two stages + the 16-entry exp table
 template <int D, int EG>
 __host__ __device__ constexpr size_t pair_smem_bytes()
@@ -242,7 +223,7 @@ __host__ __device__ constexpr size_t pair_smem_bytes()
 
 template <int D, int EG, bool GRAD>
 __global__ void __launch_bounds__(PAIR_THREADS, GPMPC_MINBLOCKS)
-mm_pairs_batch(const PairArgs a, const __grid_constant__ PairTma tm)
+mm_pairs_batch(const PairArgs a)
 {
     extern __shared__ __align__(128) double smem[];
     constexpr size_t STAGE = pair_stage_doubles<D, EG>();
@@ -280,48 +261,29 @@ mm_pairs_batch(const PairArgs a, const __grid_constant__ PairTma tm)
 #define GP_CU(k) cu[k]
 #endif
 
-#if GPMPC_USE_TMA
     // full[stage] completes when the TMA engine has written the stage's bytes; one thread arms and issues.
     __shared__ __align__(8) unsigned long long full[2];
     if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
     __syncthreads();
     unsigned uses0 = 0, uses1 = 0;               // completed uses of each stage -> wait parity
     constexpr unsigned STAGE_BYTES = (unsigned)(STAGE * sizeof(double));
-    auto issue = [&](int stage, int ti, int tj) {
+    auto issue = [&](int stage, int t, int ti, int tj) {       // t = index of tile (ti, tj) in the tile-major list
         if (tid == 0) {
             double *base = smem + (size_t)stage * STAGE;
             void *bar = &full[stage];
             mbar_expect_tx(bar, STAGE_BYTES);
 #pragma unroll
-            for (int g = 0; g < EG; ++g) tma_load_2d(base + (size_t)g * PT * PTJ, &tm.map[g], tj * PTJ, ti * PT, bar);
-            double *xi = base + (size_t)EG * PT * PTJ;
+            for (int g = 0; g < EG; ++g)
+                bulk_load_1d(base + (size_t)g * PT * PT, a.Wt[g] + (size_t)t * PT * PT, PT * PT * sizeof(double), bar);
+            double *xi = base + (size_t)EG * PT * PT;
             bulk_load_1d(xi, a.X + (size_t)ti * PT * D, PT * D * sizeof(double), bar);
-            bulk_load_1d(xi + PT * D, a.X + (size_t)tj * PTJ * D, PTJ * D * sizeof(double), bar);
+            bulk_load_1d(xi + PT * D, a.X + (size_t)tj * PT * D, PT * D * sizeof(double), bar);
         }
     };
     auto wait_stage = [&](int stage) {
         if (stage == 0) { mbar_wait(&full[0], uses0 & 1); ++uses0; }
         else { mbar_wait(&full[1], uses1 & 1); ++uses1; }
     };
-#else
-    auto issue = [&](int stage, int ti, int tj) {
-        double *base = smem + (size_t)stage * STAGE;
-#pragma unroll
-        for (int g = 0; g < EG; ++g) {
-            const double *src = a.Wt[g] + (size_t)ti * PT * a.ld + (size_t)tj * PTJ;
-            double *dst = base + (size_t)g * PT * PTJ;
-            for (int chunk = tid; chunk < PT * PTJ / 2; chunk += PAIR_THREADS) {   // 16-byte chunks, PTJ/2 per row
-                const int r = chunk / (PTJ / 2), cc = (chunk % (PTJ / 2)) * 2;
-                cpa16(dst + r * PTJ + cc, src + (size_t)r * a.ld + cc);
-            }
-        }
-        double *xi = base + (size_t)EG * PT * PTJ;
-        double *xj = xi + PT * D;
-        for (int chunk = tid; chunk < PT * D / 2; chunk += PAIR_THREADS) cpa16(xi + chunk * 2, a.X + (size_t)ti * PT * D + chunk * 2);
-        for (int chunk = tid; chunk < PTJ * D / 2; chunk += PAIR_THREADS) cpa16(xj + chunk * 2, a.X + (size_t)tj * PTJ * D + chunk * 2);
-        cpa_commit();
-    };
-#endif
 
     // Work items = fixed contiguous ranges of the upper-triangular tile list.  CTAs draw items from a ticket
     // counter (the two CTAs of an SM do not progress at the same rate: the warp scheduler favours one of
@@ -351,27 +313,20 @@ mm_pairs_batch(const PairArgs a, const __grid_constant__ PairTma tm)
 
         const int t_begin = (int)((long long)a.total_tiles * item / a.n_items);
         const int t_end = (int)((long long)a.total_tiles * (item + 1) / a.n_items);
-        const int ncol = a.ld / PTJ;                 // column blocks; row block I starts at column block I*PT/PTJ
         int I = 0, J = 0;
         {
             int rem = t_begin;
             int row = 0;
-            while (rem >= ncol - row * PT / PTJ) { rem -= ncol - row * PT / PTJ; ++row; }
-            I = row; J = row * PT / PTJ + rem;
+            while (rem >= a.ntile - row) { rem -= a.ntile - row; ++row; }
+            I = row; J = row + rem;
         }
-        if (t_begin < t_end) issue(0, I, J);
+        if (t_begin < t_end) issue(0, t_begin, I, J);
         int stage = 0;
         for (int t = t_begin; t < t_end; ++t) {
             int In = I, Jn = J + 1;
-            if (Jn == ncol) { ++In; Jn = In * PT / PTJ; }
-#if GPMPC_USE_TMA
-            if (t + 1 < t_end) issue(stage ^ 1, In, Jn);
+            if (Jn == a.ntile) { ++In; Jn = In; }
+            if (t + 1 < t_end) issue(stage ^ 1, t + 1, In, Jn);
             wait_stage(stage);
-#else
-            if (t + 1 < t_end) { issue(stage ^ 1, In, Jn); cpa_wait<1>(); }
-            else cpa_wait<0>();
-            __syncthreads();
-#endif
 
             const double *Ws = smem + (size_t)stage * STAGE;
             const double *xi = Ws + (size_t)EG * PT * PTJ;

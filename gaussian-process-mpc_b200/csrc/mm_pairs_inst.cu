@@ -10,7 +10,7 @@
 namespace gpmpc {
 
 template <int D, int EG, bool GRAD>
-static cudaError_t launch_one(const PairArgs &a, const PairTma &tm, dim3 grid, cudaStream_t st)
+static cudaError_t launch_one(const PairArgs &a, dim3 grid, cudaStream_t st)
 {
     const size_t smem = pair_smem_bytes<D, EG>();
     static bool configured = false;
@@ -20,28 +20,28 @@ static cudaError_t launch_one(const PairArgs &a, const PairTma &tm, dim3 grid, c
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    mm_pairs_batch<D, EG, GRAD><<<grid, PAIR_THREADS, smem, st>>>(a, tm);
+    mm_pairs_batch<D, EG, GRAD><<<grid, PAIR_THREADS, smem, st>>>(a);
     return cudaGetLastError();
 }
 
 template <int D>
-static cudaError_t launch_d(int EG, bool grad, const PairArgs &a, const PairTma &tm, dim3 grid, cudaStream_t st)
+static cudaError_t launch_d(int EG, bool grad, const PairArgs &a, dim3 grid, cudaStream_t st)
 {
     switch (EG * 2 + (grad ? 1 : 0)) {
-        case 2: return launch_one<D, 1, false>(a, tm, grid, st);
-        case 3: return launch_one<D, 1, true>(a, tm, grid, st);
-        case 4: return launch_one<D, 2, false>(a, tm, grid, st);
-        case 5: return launch_one<D, 2, true>(a, tm, grid, st);
-        case 6: return launch_one<D, 3, false>(a, tm, grid, st);
-        case 7: return launch_one<D, 3, true>(a, tm, grid, st);
-        case 8: return launch_one<D, 4, false>(a, tm, grid, st);
-        case 9: return launch_one<D, 4, true>(a, tm, grid, st);
+        case 2: return launch_one<D, 1, false>(a, grid, st);
+        case 3: return launch_one<D, 1, true>(a, grid, st);
+        case 4: return launch_one<D, 2, false>(a, grid, st);
+        case 5: return launch_one<D, 2, true>(a, grid, st);
+        case 6: return launch_one<D, 3, false>(a, grid, st);
+        case 7: return launch_one<D, 3, true>(a, grid, st);
+        case 8: return launch_one<D, 4, false>(a, grid, st);
+        case 9: return launch_one<D, 4, true>(a, grid, st);
     }
     return cudaErrorInvalidValue;
 }
 
 template <int D, int EG, bool GRAD>
-static cudaError_t launch_single_one(const SingleStepArgs &a, const PairTma &tm, dim3 grid, cudaStream_t st)
+static cudaError_t launch_single_one(const SingleStepArgs &a, dim3 grid, cudaStream_t st)
 {
     const size_t smem = single_smem_bytes<D, EG>();
     static bool configured = false;
@@ -59,36 +59,36 @@ static cudaError_t launch_single_one(const SingleStepArgs &a, const PairTma &tm,
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, mm_step_single<D, EG, GRAD>, a, tm);
+    return cudaLaunchKernelEx(&cfg, mm_step_single<D, EG, GRAD>, a);
 }
 
 template <int D>
-static cudaError_t launch_single_d(int EG, bool grad, const SingleStepArgs &a, const PairTma &tm, dim3 grid, cudaStream_t st)
+static cudaError_t launch_single_d(int EG, bool grad, const SingleStepArgs &a, dim3 grid, cudaStream_t st)
 {
     switch (EG * 2 + (grad ? 1 : 0)) {
-        case 2: return launch_single_one<D, 1, false>(a, tm, grid, st);
-        case 3: return launch_single_one<D, 1, true>(a, tm, grid, st);
-        case 4: return launch_single_one<D, 2, false>(a, tm, grid, st);
-        case 5: return launch_single_one<D, 2, true>(a, tm, grid, st);
-        case 6: return launch_single_one<D, 3, false>(a, tm, grid, st);
-        case 7: return launch_single_one<D, 3, true>(a, tm, grid, st);
-        case 8: return launch_single_one<D, 4, false>(a, tm, grid, st);
-        case 9: return launch_single_one<D, 4, true>(a, tm, grid, st);
+        case 2: return launch_single_one<D, 1, false>(a, grid, st);
+        case 3: return launch_single_one<D, 1, true>(a, grid, st);
+        case 4: return launch_single_one<D, 2, false>(a, grid, st);
+        case 5: return launch_single_one<D, 2, true>(a, grid, st);
+        case 6: return launch_single_one<D, 3, false>(a, grid, st);
+        case 7: return launch_single_one<D, 3, true>(a, grid, st);
+        case 8: return launch_single_one<D, 4, false>(a, grid, st);
+        case 9: return launch_single_one<D, 4, true>(a, grid, st);
     }
     return cudaErrorInvalidValue;
 }
 
 #define GPMPC_CAT2(a, b) a##b
 #define GPMPC_CAT(a, b) GPMPC_CAT2(a, b)
-cudaError_t GPMPC_CAT(launch_pairs_batch_D, GPMPC_INST_D)(int EG, bool grad, const PairArgs &a, const PairTma &tm,
+cudaError_t GPMPC_CAT(launch_pairs_batch_D, GPMPC_INST_D)(int EG, bool grad, const PairArgs &a,
                                                           dim3 grid, cudaStream_t st)
 {
-    return launch_d<GPMPC_INST_D>(EG, grad, a, tm, grid, st);
+    return launch_d<GPMPC_INST_D>(EG, grad, a, grid, st);
 }
-cudaError_t GPMPC_CAT(launch_step_single_D, GPMPC_INST_D)(int EG, bool grad, const SingleStepArgs &a, const PairTma &tm,
+cudaError_t GPMPC_CAT(launch_step_single_D, GPMPC_INST_D)(int EG, bool grad, const SingleStepArgs &a,
                                                           dim3 grid, cudaStream_t st)
 {
-    return launch_single_d<GPMPC_INST_D>(EG, grad, a, tm, grid, st);
+    return launch_single_d<GPMPC_INST_D>(EG, grad, a, grid, st);
 }
 
 }  // namespace gpmpc

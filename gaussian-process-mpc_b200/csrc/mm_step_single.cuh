@@ -2,8 +2,9 @@
 // sequence at a time: B = 1, src/mpc.py:202-255).
 //
 // mm_pairs_batch maps lanes to rollouts and needs >= 32 of them per warp.  Here lanes map to PAIRS: grid
-// (P, B); CTA (x, b) streams its contiguous share of the upper-triangular 32x32 tiles of Wt through a TMA +
-// mbarrier ring (full/empty barriers, no CTA-wide barrier in the loop), lane <-> column j of the tile,
+// (P, B); CTA (x, b) streams its contiguous share of the upper-triangular 32x32 tiles of Wt (tile-major storage:
+// one contiguous range of memory) through a TMA bulk-copy + mbarrier ring (full/empty barriers, no CTA-wide
+// barrier in the loop), lane <-> column j of the tile,
 // warp <-> 8 rows, and every thread keeps the (1+2D)*EG accumulators of rollout b.  Per rollout and step the
 // kernel reads EG * n(n+1)/2 * 8 bytes of Wt exactly once (268 MB at n=4096, E=4): with one rollout it is bound
 // by HBM, not by the FP64 pipe (41 us vs 34 us per step at n=4096).
@@ -27,11 +28,10 @@ constexpr int SINGLE_ROWS = PT / SINGLE_WARPS;       // rows of a tile handled b
 constexpr int SINGLE_GROUP = 16;       // CTAs per first-level reduction group
 constexpr int SINGLE_STAGES = 3;       // ring slots per CTA: 2-3 tiles in flight (x2 CTAs per SM = ~200 KB per SM)
 
-static_assert(kPairTileJ == kPairTile, "mm_step_single uses the 32x32 TMA box of the Wt maps");
 static_assert(kGroupMax <= SINGLE_WARPS, "the finalize maps one warp to each output of the group");
 
 struct SingleStepArgs {
-    const double *Wt[kGroupMax];   // only used to keep the argument list self-describing (tiles come through the maps)
+    const double *Wt[kGroupMax];   // tile-major upper-triangular tiles of the group's outputs (common.cuh)
     const double *beta[kGroupMax];
     int out_idx[kGroupMax];
     const double *X;               // [ld, D]
@@ -66,7 +66,7 @@ __device__ __forceinline__ void mbar_arrive(void *bar)
 
 template <int D, int EG, bool GRAD>
 __global__ void __launch_bounds__(SINGLE_THREADS, 2)
-mm_step_single(const SingleStepArgs a, const __grid_constant__ PairTma tm)
+mm_step_single(const SingleStepArgs a)
 {
     constexpr int NA = 1 + 2 * D;
     constexpr int NV = 2 * EG * NA;
@@ -112,14 +112,16 @@ mm_step_single(const SingleStepArgs a, const __grid_constant__ PairTma tm)
         while (rem >= a.ntile - row) { rem -= a.ntile - row; ++row; }
         I = row; J = row + rem;
     }
-    int Ii = I, Ji = J, issued = t_begin;                // next tile to issue (thread 0 only)
+    int Ii = I, Ji = J, issued = t_begin;                // next tile to issue (thread 0 only); Ii is not needed for Wt
+    (void)Ii;
     auto issue_next = [&]() {                            // thread 0: tile `issued` -> slot (issued - t_begin) % STAGES
         const int slot = (issued - t_begin) % SINGLE_STAGES;
         double *base = smem + (size_t)slot * STAGE;
         void *bar = &full[slot];
         mbar_expect_tx(bar, STAGE_BYTES);
 #pragma unroll
-        for (int g = 0; g < EG; ++g) tma_load_2d(base + (size_t)g * PT * PT, &tm.map[g], Ji * PT, Ii * PT, bar);
+        for (int g = 0; g < EG; ++g)             // tile-major Wt: tile number `issued` is one contiguous 8 KB block
+            bulk_load_1d(base + (size_t)g * PT * PT, a.Wt[g] + (size_t)issued * PT * PT, PT * PT * sizeof(double), bar);
         bulk_load_1d(base + (size_t)EG * PT * PT, a.X + (size_t)Ji * PT * D, PT * D * sizeof(double), bar);
         ++issued; ++Ji;
         if (Ji == a.ntile) { ++Ii; Ji = Ii; }

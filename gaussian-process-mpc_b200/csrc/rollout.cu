@@ -20,13 +20,13 @@
 
 namespace gpmpc {
 
-#define DECL_LAUNCH(D) cudaError_t launch_pairs_batch_D##D(int, bool, const PairArgs &, const PairTma &, dim3, cudaStream_t); \
-                       cudaError_t launch_step_single_D##D(int, bool, const SingleStepArgs &, const PairTma &, dim3, cudaStream_t);
+#define DECL_LAUNCH(D) cudaError_t launch_pairs_batch_D##D(int, bool, const PairArgs &, dim3, cudaStream_t); \
+                       cudaError_t launch_step_single_D##D(int, bool, const SingleStepArgs &, dim3, cudaStream_t);
 DECL_LAUNCH(2) DECL_LAUNCH(3) DECL_LAUNCH(4) DECL_LAUNCH(5) DECL_LAUNCH(6) DECL_LAUNCH(7) DECL_LAUNCH(8)
 #undef DECL_LAUNCH
 
-typedef cudaError_t (*pair_launch_fn)(int, bool, const SingleStepArgs &, const PairTma &, dim3, cudaStream_t);
-typedef cudaError_t (*pair_tma_launch_fn)(int, bool, const PairArgs &, const PairTma &, dim3, cudaStream_t);
+typedef cudaError_t (*pair_launch_fn)(int, bool, const SingleStepArgs &, dim3, cudaStream_t);
+typedef cudaError_t (*pair_tma_launch_fn)(int, bool, const PairArgs &, dim3, cudaStream_t);
 static pair_tma_launch_fn pair_launcher(int D)
 {
     switch (D) {
@@ -638,14 +638,12 @@ static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int ctas, int P, lon
     if (h->time_pairs) cudaEventRecord(h->ev0, h->stream);
     for (int g = 0; g < d.G; ++g) {
         const LambdaGroup &grp = h->groups[g];
-        PairTma tm;
-        for (int i = 0; i < kGroupMax; ++i) tm.map[i] = h->wt_map[grp.outputs[i < grp.count ? i : 0]];
         cudaError_t e;
         if (few) {
             SingleStepArgs sa;
             for (int i = 0; i < kGroupMax; ++i) {
                 const int o = grp.outputs[i < grp.count ? i : 0];
-                sa.Wt[i] = h->Wt.as<double>() + (size_t)o * mat;
+                sa.Wt[i] = h->Wt.as<double>() + (size_t)o * wt_doubles(h->ld);
                 sa.beta[i] = h->beta.as<double>() + (size_t)o * h->ld;
                 sa.out_idx[i] = o;
             }
@@ -658,7 +656,7 @@ static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int ctas, int P, lon
             sa.want_grad = want_grad ? 1 : 0;
             sa.prep_next = (next.on && d.G == 1) ? 1 : 0;
             sa.Uint = next.Uint; sa.lam_group = next.lam_group; sa.us_w = us; sa.cst_w = cst; sa.act_var = next.act_var;
-            e = single_launcher(d.D)(grp.count, want_grad, sa, tm, dim3(ctas, d.B), h->stream);
+            e = single_launcher(d.D)(grp.count, want_grad, sa, dim3(ctas, d.B), h->stream);
             h->launches++;
             if (e != cudaSuccess) return fail(h, GPMPC_ERR_CUDA, std::string("mm_step_single: ") + cudaGetErrorString(e));
             continue;
@@ -667,7 +665,7 @@ static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int ctas, int P, lon
         MeanArgs ma;
         for (int i = 0; i < kGroupMax; ++i) {
             const int o = grp.outputs[i < grp.count ? i : 0];
-            pa.Wt[i] = h->Wt.as<double>() + (size_t)o * mat;
+            pa.Wt[i] = h->Wt.as<double>() + (size_t)o * wt_doubles(h->ld);
             pa.out_idx[i] = o;
             ma.beta[i] = h->beta.as<double>() + (size_t)o * h->ld;
             ma.out_idx[i] = o;
@@ -680,7 +678,7 @@ static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int ctas, int P, lon
         const int chunks = (d.B + PAIR_THREADS - 1) / PAIR_THREADS;
         pa.counters = h->tickets.as<int>();
         GP_CUDA(h, cudaMemsetAsync(pa.counters, 0, chunks * sizeof(int), h->stream));
-        e = pair_launcher(d.D)(grp.count, want_grad, pa, tm, dim3(ctas * chunks), h->stream);
+        e = pair_launcher(d.D)(grp.count, want_grad, pa, dim3(ctas * chunks), h->stream);
         h->launches++;
         if (e != cudaSuccess) return fail(h, GPMPC_ERR_CUDA, std::string("mm_pairs_batch: ") + cudaGetErrorString(e));
 
@@ -716,7 +714,7 @@ static int reserve_rollout(gpmpc_ctx *h, int B, int H, RolloutWork &w)
     w.d = make_dims(h, B);
     const StepDims &d = w.d;
     const long long nt = h->ld / PT;
-    w.total_tiles = (B < kSingleMaxB) ? nt * (nt + 1) / 2 : pair_batch_tiles(h->ld);
+    w.total_tiles = nt * (nt + 1) / 2;
     pair_geometry(h, B, w.total_tiles, w.ctas, w.P);
     const bool few = B < kSingleMaxB;
     const size_t n_groups = (size_t)(w.P + SINGLE_GROUP - 1) / SINGLE_GROUP;

@@ -50,9 +50,10 @@ int main(int argc, char **argv)
     const int Bpad = (B + 31) / 32 * 32;
     std::mt19937_64 rng(1);
     std::uniform_real_distribution<double> U(-1, 1);
-    std::vector<double> hX((size_t)ld * D, 0.0), hW((size_t)ld * ld), hc((size_t)4 * D * Bpad);
+    std::vector<double> hX((size_t)ld * D, 0.0), hW(wt_doubles(ld)), hc((size_t)4 * D * Bpad);
     for (int i = 0; i < n * D; ++i) hX[i] = U(rng);
-    for (int i = 0; i < ld; ++i) for (int j = 0; j < ld; ++j) hW[(size_t)i * ld + j] = (i < n && j < n && j >= i) ? U(rng) : 0.0;
+    for (int i = 0; i < ld; ++i) for (int j = (i / 32) * 32; j < ld; ++j)      // tile-major upper-triangular tiles
+        hW[wt_tile_index(i / 32, j / 32, ld / 32) * 1024 + (i % 32) * 32 + (j % 32)] = (i < n && j < n && j >= i) ? U(rng) : 0.0;
     for (int k = 0; k < D; ++k) for (int b = 0; b < Bpad; ++b) { double c = 0.3 + 0.05 * U(rng), u = 0.5 * U(rng); hc[(size_t)k * Bpad + b] = c; hc[(size_t)(D + k) * Bpad + b] = c * u; }
     double *dX, *dW[EG], *dc, *dpart, *dlat;
     cudaMalloc(&dX, hX.size() * 8); cudaMemcpy(dX, hX.data(), hX.size() * 8, cudaMemcpyHostToDevice);
@@ -60,7 +61,7 @@ int main(int argc, char **argv)
     cudaMalloc(&dc, hc.size() * 8); cudaMemcpy(dc, hc.data(), hc.size() * 8, cudaMemcpyHostToDevice);
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     const int chunks = (B + PAIR_THREADS - 1) / PAIR_THREADS;
-    const long long nt = ld / PT, total = pair_batch_tiles(ld);
+    const long long nt = ld / PT, total = nt * (nt + 1) / 2;
 #ifndef GPMPC_CTAS_PER_SM
 #define GPMPC_CTAS_PER_SM 2
 #endif
@@ -79,24 +80,6 @@ int main(int argc, char **argv)
 #ifdef GPMPC_PAIR_TIMING
     unsigned long long *dtimes; cudaMalloc(&dtimes, (size_t)ctas * chunks * 3 * 8); a.cta_times = dtimes;
 #endif
-    PairTma tm;
-    {
-        typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-        void *fn = nullptr; cudaDriverEntryPointQueryResult qres;
-        cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-        encode_fn encode = reinterpret_cast<encode_fn>(fn);
-        for (int g = 0; g < EG; ++g) {
-            const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)ld};
-            const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
-            const cuuint32_t box[2] = {PTJ, PT}, estr[2] = {1, 1};
-            CUresult r = encode(&tm.map[g], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, dW[g], dims, strides, box, estr,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) { printf("tensor map encode failed %d\n", (int)r); return 1; }
-        }
-    }
     const size_t smem = pair_smem_bytes<D, EG>();
     cudaFuncSetAttribute(mm_pairs_batch<D, EG, GPMPC_BENCH_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(ctas * chunks);
@@ -105,7 +88,7 @@ int main(int argc, char **argv)
     for (int rep = 0; rep < 4; ++rep) {
         cudaMemset(dcnt, 0, chunks * sizeof(int));
         cudaEventRecord(e0);
-        mm_pairs_batch<D, EG, GPMPC_BENCH_GRAD><<<grid, PAIR_THREADS, smem>>>(a, tm);
+        mm_pairs_batch<D, EG, GPMPC_BENCH_GRAD><<<grid, PAIR_THREADS, smem>>>(a);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
     }

@@ -5,6 +5,12 @@
 #include "../gaussian-process-mpc_b200/csrc/mm_pairs.cuh"
 #include <vector>
 using namespace gpmpc;
+struct alignas(64) PairTma { CUtensorMap map[4]; };
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, void *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
 constexpr int EG = 4, STAGES = 3, THREADS = 128;
 constexpr size_t STAGE = (size_t)EG * 1024;
 __device__ __forceinline__ void mbar_arrive_l(void *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory"); }
