@@ -233,6 +233,7 @@ mm_pairs_batch(const PairArgs a)
     const int chunk_id = blockIdx.x % a.chunks;
     const int b = chunk_id * PAIR_THREADS + tid;
     const bool active = b < a.B;
+    const bool warp_active = chunk_id * PAIR_THREADS + (tid & ~31) < a.B;   // ragged last chunk: idle warps only keep the barriers
     double *tab = smem + 2 * STAGE;
     if (tid < 16) tab[tid] = kExp2Tab[tid];      // visible after the first __syncthreads of the tile loop
 #ifdef GPMPC_PAIR_TIMING
@@ -332,6 +333,7 @@ mm_pairs_batch(const PairArgs a)
             const double *xi = Ws + (size_t)EG * PT * PTJ;
             const double *xj = xi + PT * D;
 
+            if (warp_active) {
 #if GPMPC_PIPELINE
             // One pair = chain (q, q^2, S, exp: a ~15-deep dependency chain) + sums (4 + 44 independent FMAs).
             // ptxas does not software-pipeline loops, so the loop is rotated by hand: the chain of pair p+1 and the
@@ -478,6 +480,7 @@ mm_pairs_batch(const PairArgs a)
                 }
             }
 #endif
+            }
             __syncthreads();
             stage ^= 1; I = In; J = Jn;
         }

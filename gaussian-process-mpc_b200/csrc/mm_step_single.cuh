@@ -2,7 +2,7 @@
 // sequence at a time: B = 1, src/mpc.py:202-255).
 //
 // mm_pairs_batch maps lanes to rollouts and needs >= 32 of them per warp.  Here lanes map to PAIRS: grid
-// (P, B); CTA (x, b) streams its contiguous share of the upper-triangular 32x32 tiles of Wt (tile-major storage:
+// (B, P); CTA (b, x) streams its contiguous share of the upper-triangular 32x32 tiles of Wt (tile-major storage:
 // one contiguous range of memory) through a TMA bulk-copy + mbarrier ring (full/empty barriers, no CTA-wide
 // barrier in the loop), lane <-> column j of the tile,
 // warp <-> 8 rows, and every thread keeps the (1+2D)*EG accumulators of rollout b.  Per rollout and step the
@@ -81,8 +81,11 @@ mm_step_single(const SingleStepArgs a)
     __shared__ __align__(8) unsigned long long full[SINGLE_STAGES], empty[SINGLE_STAGES];
     __shared__ int s_last;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int b = blockIdx.y;                            // rollout
-    const int P = gridDim.x;
+    // grid (B, P): the rollout index is the FAST block index, so the CTAs that are resident together work on the
+    // same tile ranges for different rollouts and share the Wt tiles through L2 (2 <= B < 64)
+    const int b = blockIdx.x;                            // rollout
+    const int P = gridDim.y;
+    const int bx = blockIdx.y;                           // this CTA's slice of the tile list / training set
     // Programmatic dependent launch: the next step's grid may be scheduled while this one drains; everything up
     // to griddepcontrol.wait touches only data no step kernel writes (the exp table, Wt, X).
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
@@ -104,8 +107,8 @@ mm_step_single(const SingleStepArgs a)
             for (int k = 0; k < D; ++k) acc1[g][k] = acc2[g][k] = 0.0;
     }
 
-    const int t_begin = (int)((long long)a.total_tiles * blockIdx.x / P);
-    const int t_end = (int)((long long)a.total_tiles * (blockIdx.x + 1) / P);
+    const int t_begin = (int)((long long)a.total_tiles * bx / P);
+    const int t_end = (int)((long long)a.total_tiles * (bx + 1) / P);
     int I = 0, J = 0;                                    // tile being consumed
     {
         int rem = t_begin, row = 0;
@@ -137,7 +140,7 @@ mm_step_single(const SingleStepArgs a)
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
     if (tid < 4 * D) cs[tid] = a.cst[(size_t)tid * a.d.Bpad + b];
     __syncthreads();
-    double *mine = a.spart + ((size_t)b * P + blockIdx.x) * NV;
+    double *mine = a.spart + ((size_t)b * P + bx) * NV;
 
     // ---- mean sums over this CTA's slice of the training set (lanes <-> training points), done while the first
     // tiles land.  Scratch = the last ring slot (the prologue fills slots 0 .. STAGES-2 only).
@@ -145,7 +148,7 @@ mm_step_single(const SingleStepArgs a)
     {
         constexpr int RCAP = (int)(STAGE / (EG * NA)) < SINGLE_THREADS ? (int)(STAGE / (EG * NA)) : SINGLE_THREADS;
         const int per = (a.ld + P - 1) / P;
-        const int j_begin = blockIdx.x * per;
+        const int j_begin = bx * per;
         const int j_end = min(a.ld, j_begin + per);
         const int rows = min(max(j_end - j_begin, 0), RCAP);             // threads that own >= 1 point
         double *scratch = smem + (size_t)(SINGLE_STAGES - 1) * STAGE;    // [thread][EG*NA]
@@ -284,7 +287,7 @@ mm_step_single(const SingleStepArgs a)
     // SINGLE_GROUP consecutive CTAs sums the group's partials, the last group to finish sums the group sums and
     // finalizes.  Only ~SINGLE_GROUP + P/SINGLE_GROUP loads per value sit on the critical path, all in flight at once.
     const int NG = (P + SINGLE_GROUP - 1) / SINGLE_GROUP;
-    const int gidx = blockIdx.x / SINGLE_GROUP;
+    const int gidx = bx / SINGLE_GROUP;
     const int g0 = gidx * SINGLE_GROUP;
     const int gsize = min(SINGLE_GROUP, P - g0);
     int *tk = a.tickets + (size_t)b * (1 + NG);         // [0]: groups done, [1 + g]: CTAs of group g done

@@ -49,8 +49,10 @@ static pair_launch_fn single_launcher(int D)
     return nullptr;
 }
 
-// below this many rollouts the lanes<->pairs kernel (one rollout per CTA column) replaces the lanes<->rollouts one
-constexpr int kSingleMaxB = 64;
+// below this many rollouts the lanes<->pairs kernel (one rollout per CTA column) replaces the lanes<->rollouts one:
+// measured on B200 at n=4096 it costs 1.55 ms per rollout and evaluation, the batched kernel 174 ms per started
+// chunk of 128 rollouts, i.e. the crossover is at 112
+constexpr int kSingleMaxB = 112;
 constexpr int MEAN_JP = 16;          // partitions of the training set in the mean kernel
 constexpr int MEAN_THREADS = 128;
 
@@ -656,7 +658,7 @@ static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int ctas, int P, lon
             sa.want_grad = want_grad ? 1 : 0;
             sa.prep_next = (next.on && d.G == 1) ? 1 : 0;
             sa.Uint = next.Uint; sa.lam_group = next.lam_group; sa.us_w = us; sa.cst_w = cst; sa.act_var = next.act_var;
-            e = single_launcher(d.D)(grp.count, want_grad, sa, dim3(ctas, d.B), h->stream);
+            e = single_launcher(d.D)(grp.count, want_grad, sa, dim3(d.B, ctas), h->stream);
             h->launches++;
             if (e != cudaSuccess) return fail(h, GPMPC_ERR_CUDA, std::string("mm_step_single: ") + cudaGetErrorString(e));
             continue;

@@ -285,7 +285,7 @@ def _synth_dynamics(gp, n, E, m, seed, lam=2.0, sn=0.1):
 
 def test_batched_rollouts_vs_c_oracle(gp):
     from oracle import oracle as orc
-    n, E, m, H, B = 700, 4, 1, 6, 70           # n not a multiple of 64, B not a multiple of 32
+    n, E, m, H, B = 700, 4, 1, 6, 150          # n not a multiple of 64; B = one full 128-lane chunk + a ragged one
     dyn, S, A, nxt, rng = _synth_dynamics(gp, n, E, m, seed=2)
     X = np.concatenate([S, A], 1)
     lam = np.full((E, E + m), 2.0); sf = np.ones(E)
@@ -295,7 +295,7 @@ def test_batched_rollouts_vs_c_oracle(gp):
     Q = 2 * np.eye(E); R = 0.01 * np.eye(m)
     br = gp.BatchedRollouts(dyn, Q, R)
     cost, grad = br.cost_and_grad(x0, U, gamma, host_out=True)
-    for b in (0, 1, 33, 69):
+    for b in (0, 1, 33, 127, 128, 149):
         c, gr, _, _ = orc.c_rollout_cost_grad(X, [f["Ky_inv"] for f in fits], [f["beta"] for f in fits], lam, sf,
                                               x0[b], U[b], gamma[b], Q, R)
         close(cost[b], c, RTOL)
@@ -306,7 +306,10 @@ def test_batched_rollouts_vs_c_oracle(gp):
     close(cost_p, cost[perm], 1e-12)
     norm_close(grad_p, grad[perm], 1e-11)
     c1, g1 = br.cost_and_grad(x0[5:6], U[5:6], gamma[5:6], host_out=True)
-    close(c1, cost[5:6], 1e-9)      # B < 64 runs the lanes<->pairs kernel: different (fixed) summation order
+    close(c1, cost[5:6], 1e-9)      # few rollouts run the lanes<->pairs kernel: different (fixed) summation order
+    c70, g70 = br.cost_and_grad(x0[:70], U[:70], gamma[:70], host_out=True)     # 70 rollouts: still the lanes<->pairs kernel
+    close(c70, cost[:70], 1e-9)
+    norm_close(g70, grad[:70], 1e-8)
 
 
 def test_mid_size_vs_c_oracle_and_finite_differences(gp):
@@ -340,6 +343,11 @@ def test_determinism(gp):
     dyn, S, A, nxt, rng = _synth_dynamics(gp, 512, 4, 1, seed=4)
     br = gp.BatchedRollouts(dyn, 2 * np.eye(4), 0.01 * np.eye(1))
     x0 = rng.uniform(-0.5, 0.5, 4); U = rng.uniform(-0.3, 0.3, (40, 4, 1))
+    a = br.cost_and_grad(x0, U, -1.0, host_out=True)
+    b = br.cost_and_grad(x0, U, -1.0, host_out=True)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    # batched kernel: work items are handed out dynamically, the result must still be bit-identical
+    U = rng.uniform(-0.3, 0.3, (200, 4, 1))
     a = br.cost_and_grad(x0, U, -1.0, host_out=True)
     b = br.cost_and_grad(x0, U, -1.0, host_out=True)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])

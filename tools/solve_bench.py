@@ -35,8 +35,9 @@ for i in range(5):
     t0 = time.perf_counter(); traj = mpc.get_optimal_trajectory(x0); st.append((time.perf_counter() - t0, mpc.n_evals - n0))
 print("solve (L-BFGS-B fallback unless cyipopt present): " + ", ".join(f"{1e3*t:.1f} ms/{k} evals" for t, k in st),
       f"p50 {1e3*np.median([t for t, _ in st]):.1f} ms")
-B = 16
-U = rng.uniform(-0.3, 0.3, (B, H, m))
 br = gp.BatchedRollouts(mpc.dynamics, 2 * np.eye(E), 0.01 * np.eye(m))
-for _ in range(2): br.cost_and_grad(np.zeros(E), U, -1.0, host_out=True)
-t0 = time.perf_counter(); br.cost_and_grad(np.zeros(E), U, -1.0, host_out=True); print(f"B={B}: {1e3*(time.perf_counter()-t0):.3f} ms")
+for B in (1, 4, 16, 48, 64, 128):
+    U = rng.uniform(-0.3, 0.3, (B, H, m))
+    for _ in range(2): br.cost_and_grad(np.zeros(E), U, -1.0, host_out=True)
+    t0 = time.perf_counter(); br.cost_and_grad(np.zeros(E), U, -1.0, host_out=True); dt = time.perf_counter() - t0
+    print(f"B={B}: {1e3*dt:.3f} ms  ({1e3*dt/B:.3f} ms per rollout)")
