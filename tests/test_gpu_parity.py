@@ -483,3 +483,72 @@ def test_full_covariance_propagation_vs_numpy_oracle(gp):
         mu, Sig = np.array(ms), Sig_new
         norm_close(means[t], mu, 1e-8)
         assert np.max(np.abs(covs[t] - Sig)) <= RTOL * max(np.max(np.abs(Sig)), 1e-3)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configurations at their full sizes: oracle spot checks + size-independent properties
+# ------------------------------------------------------------------------------------------------
+def test_config2_full_size_batched_moment_matching(gp):
+    """configs[1]: n=2048, D=5, E=4, 8192 uncertain test inputs (mean + variance, no gradient).  The C oracle
+    checks a sample of the inputs; the rest is covered by properties: permutation invariance (a result does not
+    depend on its batch neighbours), agreement of the batched (lanes<->rollouts) and few-input (lanes<->pairs)
+    kernels, and bit-identical repeats."""
+    from oracle import oracle as orc
+    n, E, m, B = 2048, 4, 1, 8192
+    D = E + m
+    dyn, S, A, nxt, rng = _synth_dynamics(gp, n, E, m, seed=0)
+    X = np.concatenate([S, A], 1)
+    lam = np.full((E, D), 2.0)
+    fits = [orc.fit(X, nxt[:, a], lam[a], 1.0, float(np.float32(0.1 ** 2)) ** 0.5) for a in range(E)]
+    U = rng.uniform(-0.5, 0.5, (B, D)); Sd = rng.uniform(1e-3, 5e-2, (B, D))
+    mean, var = dyn._bundle.moment_match(U, Sd, out_device=False)
+    assert mean.shape == (B, E) and var.shape == (B, E) and np.all(np.isfinite(mean)) and np.all(var > 0)
+    for b in (0, 4097, B - 1):
+        for a in range(E):
+            mo, vo, _ = orc.c_moment_match_diag(X, fits[a]["Ky_inv"], fits[a]["beta"], lam[a], 1.0, U[b], Sd[b])
+            close(mean[b, a], mo, 1e-8)
+            assert abs(var[b, a] - vo) <= RTOL * max(abs(vo), 1e-3)
+    perm = rng.permutation(B)
+    mean_p, var_p = dyn._bundle.moment_match(U[perm], Sd[perm], out_device=False)
+    assert np.array_equal(mean_p, mean[perm]) and np.array_equal(var_p, var[perm])
+    mean_s, var_s = dyn._bundle.moment_match(U[:5], Sd[:5], out_device=False)      # 5 inputs: the lanes<->pairs kernel
+    close(mean_s, mean[:5], 1e-10)
+    assert np.max(np.abs(var_s - var[:5])) <= 1e-9
+
+
+def test_config3_full_size_rollout_cost_gradient(gp):
+    """configs[2], the headline: n=4096, E=4, m=1, H=30, gamma=-1, multi-start control sequences from one x0.
+    One rollout is checked against the C oracle (O(n^2) restatement pinned to the reference's autograd at small n);
+    the batch is covered by properties: the batched kernel and the few-rollouts kernel agree on the same control
+    sequences, the gradient matches a central difference along a random direction, repeats are bit-identical."""
+    from oracle import oracle as orc
+    n, E, m, H, B = 4096, 4, 1, 30, 256
+    dyn, S, A, nxt, rng = _synth_dynamics(gp, n, E, m, seed=0)
+    Q = 2 * np.eye(E); R = 0.01 * np.eye(m)
+    br = gp.BatchedRollouts(dyn, Q, R)
+    x0 = rng.uniform(-0.5, 0.5, E); U = rng.uniform(-0.3, 0.3, (B, H, m))
+    cost, grad = br.cost_and_grad(x0, U, -1.0, host_out=True)
+    assert np.all(np.isfinite(cost)) and np.all(np.isfinite(grad))
+    # (1) oracle, one rollout at the full size
+    X = np.concatenate([S, A], 1)
+    lam = np.full((E, E + m), 2.0)
+    fits = [orc.fit(X, nxt[:, a], lam[a], 1.0, float(np.float32(0.1 ** 2)) ** 0.5) for a in range(E)]
+    c, gr, _, _ = orc.c_rollout_cost_grad(X, [f["Ky_inv"] for f in fits], [f["beta"] for f in fits], lam, np.ones(E),
+                                          x0, U[7], -1.0, Q, R)
+    close(cost[7], c, RTOL)
+    norm_close(grad[7], gr, RTOL)
+    # (2) the two kernels agree
+    # (different fixed summation orders; SURVEY 7 measured 1e-9..6e-9 from re-association alone at this n)
+    cs, gs = br.cost_and_grad(x0, U[:3], -1.0, host_out=True)
+    close(cs, cost[:3], 1e-7)
+    norm_close(gs, grad[:3], 1e-7)
+    # (3) directional derivative
+    d = rng.normal(size=(H, m)); d /= np.linalg.norm(d)
+    h = 1e-5
+    cpm, _ = br.cost_and_grad(x0, np.stack([U[0] + h * d, U[0] - h * d]), -1.0, host_out=True)
+    fd = (cpm[0] - cpm[1]) / (2 * h)
+    an = float(np.sum(grad[0] * d))
+    assert abs(fd - an) <= 1e-5 * max(1.0, abs(an)), (fd, an)
+    # (4) determinism
+    cost2, grad2 = br.cost_and_grad(x0, U, -1.0, host_out=True)
+    assert np.array_equal(cost, cost2) and np.array_equal(grad, grad2)
