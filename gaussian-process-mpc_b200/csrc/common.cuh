@@ -140,6 +140,10 @@ int upload_prop_hypers(gpmpc_ctx *h);
 //   kmode: 0 = k in [0,K); 1 = k >= tile row0 (A upper triangular); 2 = k >= max(row0, col0)
 int dgemm_nt(gpmpc_ctx *h, int M, int N, int K, double alpha, const double *A, int lda, const double *B,
              int ldb, double beta, double *C, int ldc, bool tri_lower, int kmode);
+// batched over `batch` problems (element strides sA/sB/sC); b_nn: B is [K][N]; kmode 3/4: see gemm.cu
+int dgemm_batched(gpmpc_ctx *h, bool b_nn, int batch, int M, int N, int K, double alpha, const double *A, int lda,
+                  long long sA, const double *B, int ldb, long long sB, double beta, double *C, int ldc, long long sC,
+                  bool tri_lower, int kmode);
 
 // ---- predict.cu ---------------------------------------------------------------------------
 int kernel_matrix_dev(gpmpc_ctx *h, int a, int p, const double *Xs_dev, double *out_dev, int ldo);

@@ -59,75 +59,66 @@ int gram_into(gpmpc_ctx *h, int a, double *dst, int ldd, bool add_noise)
     return GPMPC_OK;
 }
 
-// Inverse of the lower-triangular 64x64 matrix held in the lower part of S (pitch 65).  The inverse is
-// built column by column (thread j owns column j, forward substitution) and kept in the unused upper part:
-// Xinv[i][j] (i >= j) lives at S[j][i + 1].  Result is written dense (zeros above the diagonal) to Linv.
-__device__ void tri_inverse_packed(double (*S)[NB + 1], int tid, int nthreads, double *__restrict__ Linv)
-{
-    if (tid < NB) {
-        const int j = tid;
-        S[j][j + 1] = 1.0 / S[j][j];
-        for (int i = j + 1; i < NB; ++i) {
-            double s = 0.0;
-            for (int k = j; k < i; ++k) s = fma(S[i][k], S[j][k + 1], s);
-            S[j][i + 1] = -s / S[i][i];
-        }
-    }
-    __syncthreads();
-    for (int e = tid; e < NB * NB; e += nthreads) {
-        const int i = e / NB, j = e % NB;
-        Linv[e] = (i >= j) ? S[j][i + 1] : 0.0;
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
-// Diagonal block: unblocked Cholesky of a 64x64 block in shared memory + inverse of the factor.
+// Diagonal block: unblocked Cholesky of a 64x64 block in shared memory, then the inverse of the factor by a
+// right-looking column sweep (both 64 steps of <= 16 FMAs per thread).  Writes
+//   A    : L_kk in place (upper part of the block zeroed),
+//   Linv : L_kk^-1 dense row-major (the panel solve A[i,k] L_kk^-T is then a tensor-core GEMM),
+//   ZT   : (L_kk^-1)^T into the diagonal block of L^-T (leaf of the recursive triangular inverse).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-potrf_diag_kernel(double *__restrict__ A, int ld, int k0, double *__restrict__ Linv, int *info)
+potrf_diag_kernel(double *__restrict__ A, int ld, int k0, double *__restrict__ Linv, double *__restrict__ ZT,
+                  int ldz, int *info)
 {
+    // L in the lower triangle (c <= r); X = L^-1 (also lower triangular) transposed into the unused upper part,
+    // shifted by one column: X[i][j] (i >= j) lives at S[j][i + 1]
     __shared__ double S[NB][NB + 1];
+#define XS(i, j) S[j][(i) + 1]
     __shared__ int bad;
     const int tid = threadIdx.x;
+    const int r = tid & 63, q = tid >> 6;  // row / one of 4 column phases
     if (tid == 0) bad = 0;
     for (int e = tid; e < NB * NB; e += 256) {
-        const int r = e / NB, c = e % NB;
-        S[r][c] = (c <= r) ? A[(size_t)(k0 + r) * ld + k0 + c] : 0.0;
+        const int rr = e / NB, c = e % NB;
+        if (c <= rr) { S[rr][c] = A[(size_t)(k0 + rr) * ld + k0 + c]; XS(rr, c) = 0.0; }
     }
     __syncthreads();
     for (int c = 0; c < NB; ++c) {
-        if (tid == 0) {
-            const double d = S[c][c];
-            if (!(d > 0.0)) { if (!bad) bad = k0 + c + 1; S[c][c] = 1.0; }
-            else S[c][c] = sqrt(d);
+        double d = S[c][c];
+        const bool ok = d > 0.0;
+        if (!ok) { d = 1.0; if (tid == 0 && !bad) bad = k0 + c + 1; }
+        const double rs = rsqrt(d);
+        const double lrc = S[r][c] * rs;   // column c scaled (row r), valid for r > c
+        __syncthreads();                   // everyone has read column c / the pivot
+        if (q == 0) {
+            if (r == c) S[c][c] = ok ? d * rs : 1.0;
+            else if (r > c) S[r][c] = lrc;
         }
         __syncthreads();
-        const double dinv = 1.0 / S[c][c];
-        if (tid > c && tid < NB) S[tid][c] *= dinv;
+        // trailing update of the lower triangle: S[r][j] -= L[r][c] L[j][c], c < j <= r
+        if (r > c)
+            for (int jj = c + 1 + q; jj <= r; jj += 4) S[r][jj] = fma(-lrc, S[jj][c], S[r][jj]);
+        __syncthreads();                   // column c + 1 is final before the next step reads it
+    }
+    // X = L^-1:  X[k][j] = (delta_kj - sum_{p<k} L[k][p] X[p][j]) / L[k][k]; the sums are kept in Xs and updated
+    // as soon as row k is final
+    for (int k = 0; k < NB; ++k) {
+        if (tid <= k) XS(k, tid) = ((tid == k ? 1.0 : 0.0) - XS(k, tid)) / S[k][k];
         __syncthreads();
-        // trailing update of the lower triangle: S[r][j] -= S[r][c] S[j][c], c < j <= r
-        for (int e = tid; e < NB * NB; e += 256) {
-            const int r = e / NB, j = e % NB;
-            if (j > c && j <= r) S[r][j] = fma(-S[r][c], S[j][c], S[r][j]);
+        if (r <= k) {
+            const double xk = XS(k, r);
+            for (int i = k + 1 + q; i < NB; i += 4) XS(i, r) = fma(S[i][k], xk, XS(i, r));
         }
         __syncthreads();
     }
     for (int e = tid; e < NB * NB; e += 256) {
-        const int r = e / NB, c = e % NB;
-        A[(size_t)(k0 + r) * ld + k0 + c] = (c <= r) ? S[r][c] : 0.0;      // upper part of the block is zero
+        const int rr = e / NB, c = e % NB;
+        A[(size_t)(k0 + rr) * ld + k0 + c] = (c <= rr) ? S[rr][c] : 0.0;      // upper part of the block is zero
+        Linv[e] = (c <= rr) ? XS(rr, c) : 0.0;
+        ZT[(size_t)(k0 + rr) * ldz + k0 + c] = (c >= rr) ? XS(c, rr) : 0.0;   // transposed
     }
     if (tid == 0 && bad) atomicCAS(info, 0, bad);
-    __syncthreads();
-    tri_inverse_packed(S, tid, blockDim.x, Linv);
-}
-
-// dst[c][r] = src[r][c] for a 64x64 block
-__global__ void transpose_block_kernel(const double *__restrict__ src, int lds, double *__restrict__ dst, int ldd)
-{
-    __shared__ double T[NB][NB + 1];
-    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) T[e / NB][e % NB] = src[(size_t)(e / NB) * lds + e % NB];
-    __syncthreads();
-    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) dst[(size_t)(e / NB) * ldd + e % NB] = T[e % NB][e / NB];
+#undef XS
 }
 
 // copy the lower triangle (tiles computed by the tri_lower GEMM) into the upper triangle
@@ -143,12 +134,6 @@ __global__ void mirror_lower_kernel(double *__restrict__ A, int np, int ld)
         const int i = bj * 32 + r, j = bi * 32 + tx;       // transposed position
         if (j > i) A[(size_t)i * ld + j] = T[tx][r];
     }
-}
-
-__global__ void zero_kernel(double *p, size_t count)
-{
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
-        p[i] = 0.0;
 }
 
 // y = A[0:n,0:n] x   (row per warp, coalesced, warp-shuffle reduction)
@@ -250,43 +235,42 @@ int upload_prop_hypers(gpmpc_ctx *h)
     return GPMPC_OK;
 }
 
-// Ky (padded, in `L`) -> L in place; returns GPMPC_ERR_NOT_PD through info
-static int cholesky_inplace(gpmpc_ctx *h, double *L, int np)
+// Ky (padded, in `L`) -> L in place; returns GPMPC_ERR_NOT_PD through info.  Also leaves (L_kk^-1)^T in the
+// diagonal blocks of ZT.  Two-level right-looking algorithm: inside an outer panel of NB2 columns the 64-wide
+// rank updates touch only the panel, the rest of the matrix gets ONE rank-NB2 update per outer step (4x fewer
+// passes over the trailing matrix, 16 k-steps per tensor-core tile instead of 4).
+constexpr int NB2 = 256;
+static int cholesky_inplace(gpmpc_ctx *h, double *L, double *ZT, int np)
 {
     const int ld = h->ld;
     double *linv = h->linv.as<double>();
-    double *panel = h->tt.as<double>();
-    const int nblk = np / NB;
-    for (int k = 0; k < nblk; ++k) {
-        potrf_diag_kernel<<<1, 256, 0, h->stream>>>(L, ld, k * NB, linv, h->info.as<int>());
-        GP_LAUNCH_CHECK(h);
-        const int rem = np - (k + 1) * NB;
-        if (rem <= 0) break;
-        double *Apan = L + (size_t)(k + 1) * NB * ld + (size_t)k * NB;
-        // panel = A[i,k] * Lkk^-T      (then copied back over A[i,k])
-        int rc = dgemm_nt(h, rem, NB, NB, 1.0, Apan, ld, linv, NB, 0.0, panel, NB, false, 0);
-        if (rc) return rc;
-        GP_CUDA(h, cudaMemcpy2DAsync(Apan, (size_t)ld * sizeof(double), panel, NB * sizeof(double),
-                                     NB * sizeof(double), rem, cudaMemcpyDeviceToDevice, h->stream));
-        // trailing update: A[i,j] -= L[i,k] L[j,k]^T, lower tiles only
-        double *Atr = L + (size_t)(k + 1) * NB * ld + (size_t)(k + 1) * NB;
-        rc = dgemm_nt(h, rem, rem, NB, -1.0, Apan, ld, Apan, ld, 1.0, Atr, ld, true, 0);
-        if (rc) return rc;
+    for (int K0 = 0; K0 < np; K0 += NB2) {
+        const int w = np - K0 < NB2 ? np - K0 : NB2;
+        for (int k = K0; k < K0 + w; k += NB) {
+            potrf_diag_kernel<<<1, 256, 0, h->stream>>>(L, ld, k, linv, ZT, ld, h->info.as<int>());
+            GP_LAUNCH_CHECK(h);
+            const int rem = np - (k + NB);
+            if (rem <= 0) break;
+            double *Apan = L + (size_t)(k + NB) * ld + k;
+            // panel: A[i,k] <- A[i,k] * Lkk^-T, in place (a CTA reads exactly the 64x64 tile it overwrites, K = 64)
+            int rc = dgemm_nt(h, rem, NB, NB, 1.0, Apan, ld, linv, NB, 0.0, Apan, ld, false, 0);
+            if (rc) return rc;
+            // rank-64 update of the remaining columns of this outer panel (lower tiles only)
+            const int wc = K0 + w - (k + NB);
+            if (wc > 0) {
+                rc = dgemm_nt(h, rem, wc, NB, -1.0, Apan, ld, Apan, ld, 1.0, L + (size_t)(k + NB) * ld + (k + NB), ld, true, 0);
+                if (rc) return rc;
+            }
+        }
+        const int rem2 = np - (K0 + w);
+        if (rem2 > 0) {
+            // trailing update with the whole outer panel: A[i,j] -= sum_p L[i,K0+p] L[j,K0+p], lower tiles only
+            double *P = L + (size_t)(K0 + w) * ld + K0;
+            int rc = dgemm_nt(h, rem2, rem2, w, -1.0, P, ld, P, ld, 1.0, L + (size_t)(K0 + w) * ld + (K0 + w), ld, true, 0);
+            if (rc) return rc;
+        }
     }
     return GPMPC_OK;
-}
-
-// inverse of one 64x64 lower-triangular diagonal block of L
-__global__ void trtri_diag_kernel(const double *__restrict__ L, int ld, int k0, double *__restrict__ Linv)
-{
-    __shared__ double S[NB][NB + 1];
-    const int tid = threadIdx.x;   // 64 threads
-    for (int e = tid; e < NB * (NB + 1); e += 64) {
-        const int r = e / (NB + 1), c = e % (NB + 1);
-        S[r][c] = (c <= r) ? L[(size_t)(k0 + r) * ld + k0 + c] : 0.0;
-    }
-    __syncthreads();
-    tri_inverse_packed(S, tid, 64, Linv);
 }
 
 // out[0] = 2 * sum_{i<n} log L[i][i]  (single block, fixed reduction order)
@@ -304,30 +288,37 @@ __global__ void __launch_bounds__(1024) logdet_kernel(const double *__restrict__
     if (threadIdx.x == 0) out[0] = 2.0 * sm[0];
 }
 
-// ZT = L^-T (upper triangular, row-major) by blocked forward substitution
-static int invert_factor(gpmpc_ctx *h, const double *L, double *ZT, int np)
+// ZT = L^-T (upper triangular, row-major) by recursive doubling.  The diagonal 64x64 blocks are already there
+// (potrf_diag_kernel).  At block size s the pairs of neighbouring diagonal blocks are independent:
+//     L = [L11 0; L21 L22]  =>  ZT12 = -ZT11 * L21^T * ZT22
+// i.e. two tensor-core GEMMs per pair, batched over all pairs of the level (blockIdx.z); `work` holds the
+// intermediate products (needs np*np/4 doubles).
+static int invert_factor(gpmpc_ctx *h, const double *L, double *ZT, double *work, int np)
 {
     const int ld = h->ld;
-    double *linv = h->linv.as<double>();
-    double *TT = h->tt.as<double>();
-    const int nblk = np / NB;
-    zero_kernel<<<296, 256, 0, h->stream>>>(ZT, (size_t)np * ld);
-    GP_LAUNCH_CHECK(h);
-    for (int r = 0; r < nblk; ++r) {
-        // inverse of the diagonal block of L
-        trtri_diag_kernel<<<1, 64, 0, h->stream>>>(L, ld, r * NB, linv);
-        GP_LAUNCH_CHECK(h);
-        // ZT[r,r] = (Lrr^-1)^T
-        transpose_block_kernel<<<1, 256, 0, h->stream>>>(linv, NB, ZT + (size_t)r * NB * ld + (size_t)r * NB, ld);
-        GP_LAUNCH_CHECK(h);
-        if (r == 0) continue;
-        const int Mr = r * NB;
-        // TT[c, p] = sum_k ZT[c, k] L[r*NB + p, k],  k < r*NB   (ZT upper triangular: k >= c)
-        int rc = dgemm_nt(h, Mr, NB, Mr, 1.0, ZT, ld, L + (size_t)r * NB * ld, ld, 0.0, TT, NB, false, 1);
-        if (rc) return rc;
-        // ZT[c, r*NB + p] = - sum_s TT[c, s] Lrr^-1[p, s]
-        rc = dgemm_nt(h, Mr, NB, NB, -1.0, TT, NB, linv, NB, 0.0, ZT + (size_t)r * NB, ld, false, 0);
-        if (rc) return rc;
+    for (int s = NB; s < np; s *= 2) {
+        const int nfull = np / (2 * s);                       // pairs with two full blocks
+        const int tail0 = nfull * 2 * s;                      // start of a possible ragged pair
+        const int s2 = np - tail0 - s;                        // size of its second block (<= 0: none)
+        const long long sbig = (long long)2 * s * (ld + 1);
+        for (int pass = 0; pass < 2; ++pass) {
+            const int batch = pass == 0 ? nfull : (s2 > 0 ? 1 : 0);
+            if (batch == 0) continue;
+            const int base = pass == 0 ? 0 : tail0;
+            const int n2 = pass == 0 ? s : s2;
+            const double *ZT11 = ZT + (size_t)base * (ld + 1);
+            const double *L21 = L + (size_t)(base + s) * ld + base;
+            const double *ZT22 = ZT + (size_t)(base + s) * (ld + 1);
+            double *ZT12 = ZT + (size_t)base * ld + base + s;
+            // P[i][j] = sum_k ZT11[i][k] L21[j][k]      (ZT11 upper triangular: k >= row0)
+            int rc = dgemm_batched(h, false, batch, s, n2, s, 1.0, ZT11, ld, sbig, L21, ld, sbig, 0.0, work, n2,
+                                   (long long)s * n2, false, 1);
+            if (rc) return rc;
+            // ZT12[i][j] = - sum_k P[i][k] ZT22[k][j]   (ZT22 upper triangular: k < col0 + 64)
+            rc = dgemm_batched(h, true, batch, s, n2, n2, -1.0, work, n2, (long long)s * n2, ZT22, ld, sbig, 0.0,
+                               ZT12, ld, sbig, false, 3);
+            if (rc) return rc;
+        }
     }
     return GPMPC_OK;
 }
@@ -341,7 +332,6 @@ int fit_all(gpmpc_ctx *h, const bool *which)
     GP_CUDA(h, h->beta.reserve((size_t)ld * E * sizeof(double)));
     GP_CUDA(h, h->chol.reserve(mat * sizeof(double)));
     GP_CUDA(h, h->zt.reserve(mat * sizeof(double)));
-    GP_CUDA(h, h->tt.reserve((size_t)ld * NB * sizeof(double)));
     GP_CUDA(h, h->linv.reserve((size_t)NB * NB * sizeof(double)));
     GP_CUDA(h, h->info.reserve(sizeof(int)));
 
@@ -352,7 +342,8 @@ int fit_all(gpmpc_ctx *h, const bool *which)
         dim3 blk(32, 8), grid((np + 31) / 32, (np + 7) / 8);
         gram_kernel<<<grid, blk, 0, h->stream>>>(h->X.as<double>(), n, np, h->D, make_hyper(h, a, false), L, ld, 1);
         GP_LAUNCH_CHECK(h);
-        int rc = cholesky_inplace(h, L, np);
+        double *ZT = h->zt.as<double>();
+        int rc = cholesky_inplace(h, L, ZT, np);
         if (rc) return rc;
         logdet_kernel<<<1, 1024, 0, h->stream>>>(L, ld, n, h->linv.as<double>());   // linv is free after the loop
         GP_LAUNCH_CHECK(h);
@@ -365,10 +356,9 @@ int fit_all(gpmpc_ctx *h, const bool *which)
             snprintf(msg, sizeof msg, "gpmpc_fit: Ky of output %d is not positive definite (pivot %d)", a, info - 1);
             return fail(h, GPMPC_ERR_NOT_PD, msg);
         }
-        double *ZT = h->zt.as<double>();
-        rc = invert_factor(h, L, ZT, np);
-        if (rc) return rc;
         double *Kinv = h->Kinv.as<double>() + a * mat;
+        rc = invert_factor(h, L, ZT, Kinv, np);          // Kinv doubles as workspace until the next line
+        if (rc) return rc;
         // Ky^-1[i][j] = sum_{k >= max(i,j)} ZT[i][k] ZT[j][k]; lower tiles, then mirrored
         rc = dgemm_nt(h, np, np, np, 1.0, ZT, ld, ZT, ld, 0.0, Kinv, ld, true, 2);
         if (rc) return rc;

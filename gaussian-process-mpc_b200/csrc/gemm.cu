@@ -2,6 +2,7 @@
 // triangular-inverse panels, Ky^-1 = L^-T L^-1 and the posterior products K* Ky^-1 (src/gpr.py:171,306,325).
 //
 //   C[M,N] = alpha * A[M,K] * B[N,K]^T + beta * C        ("NT": both operands have K contiguous)
+//   C[M,N] = alpha * A[M,K] * B[K,N]   + beta * C        ("NN")
 //
 // 64x64 block tile, 4 warps (2x2), each warp 32x32 = 4x4 m8n8 accumulator tiles, K staged 16 at a time
 // through a cp.async double buffer.  The smem row pitch is 20 doubles so that the 32 lanes of a fragment
@@ -29,26 +30,37 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
                  : "d"(a), "d"(b));
 }
 
+// Generalised form used by the fit (all of it on the FP64 tensor pipe):
+//   * batched over blockIdx.z with element strides sA, sB, sC (independent diagonal blocks of the recursive
+//     triangular inverse),
+//   * B either [N][K] ("NT", BNN = false) or [K][N] ("NN", BNN = true), both row-major,
+//   * a per-tile k range that skips the structural zeros of triangular operands:
+//       kmode 0: [0, K)            1: k >= row0 (A upper triangular)      2: k >= max(row0, col0)
+//             3: k <  col0 + 64 (B = [K][N] upper triangular: B[k][n] = 0 for k > n)
+//             4: row0 <= k < col0 + 64 (A upper triangular and B as in 3)
+template <bool BNN>
 __global__ void __launch_bounds__(128)
-dgemm_nt_kernel(int M, int N, int K, double alpha, const double *__restrict__ A, int lda,
-                const double *__restrict__ B, int ldb, double beta, double *__restrict__ C, int ldc,
-                int tri_lower, int kmode)
+dgemm_kernel(int M, int N, int K, double alpha, const double *__restrict__ A, int lda, long long sA,
+             const double *__restrict__ B, int ldb, long long sB, double beta, double *__restrict__ C, int ldc,
+             long long sC, int tri_lower, int kmode)
 {
     const int row0 = blockIdx.y * GB, col0 = blockIdx.x * GB;
     if (tri_lower && col0 > row0) return;
+    A += (size_t)blockIdx.z * sA; B += (size_t)blockIdx.z * sB; C += (size_t)blockIdx.z * sC;
     __shared__ __align__(16) double As[2][GB * GP];
-    __shared__ __align__(16) double Bs[2][GB * GP];
+    __shared__ __align__(16) double Bs[2][BNN ? GK * (GB + 4) : GB * GP];     // NN: [k][n], pitch 68 (conflict-free fragment loads)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
     const int g = lane >> 2, t = lane & 3;
 
-    int k_lo = 0;
-    if (kmode == 1) k_lo = row0;
+    int k_lo = 0, k_hi = K;
+    if (kmode == 1 || kmode == 4) k_lo = row0;
     else if (kmode == 2) k_lo = row0 > col0 ? row0 : col0;
+    if (kmode == 3 || kmode == 4) k_hi = col0 + GB < K ? col0 + GB : K;
     k_lo = (k_lo / GK) * GK;
-    if (k_lo > K) k_lo = K;
-    const int nk = (K - k_lo) / GK;
+    if (k_lo > k_hi) k_lo = k_hi;
+    const int nk = (k_hi - k_lo) / GK;
 
     double acc[4][4][2];
 #pragma unroll
@@ -64,7 +76,12 @@ dgemm_nt_kernel(int M, int N, int K, double alpha, const double *__restrict__ A,
             const int chunk = tid + c * 128;
             const int r = chunk >> 3, kc = (chunk & 7) * 2;
             cp_async16(&As[s][r * GP + kc], A + (size_t)(row0 + r) * lda + kbase + kc);
-            cp_async16(&Bs[s][r * GP + kc], B + (size_t)(col0 + r) * ldb + kbase + kc);
+            if (!BNN) {
+                cp_async16(&Bs[s][r * GP + kc], B + (size_t)(col0 + r) * ldb + kbase + kc);
+            } else {                                     // 16 k-rows x 64 doubles
+                const int kr = chunk >> 5, nc = (chunk & 31) * 2;
+                cp_async16(&Bs[s][kr * (GB + 4) + nc], B + (size_t)(kbase + kr) * ldb + col0 + nc);
+            }
         }
         cp_async_commit();
     };
@@ -81,7 +98,8 @@ dgemm_nt_kernel(int M, int N, int K, double alpha, const double *__restrict__ A,
 #pragma unroll
             for (int i = 0; i < 4; ++i) a[i] = As[s][(wm + i * 8 + g) * GP + kk + t];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = Bs[s][(wn + j * 8 + g) * GP + kk + t];
+            for (int j = 0; j < 4; ++j)
+                b[j] = BNN ? Bs[s][(kk + t) * (GB + 4) + wn + j * 8 + g] : Bs[s][(wn + j * 8 + g) * GP + kk + t];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -110,17 +128,28 @@ dgemm_nt_kernel(int M, int N, int K, double alpha, const double *__restrict__ A,
         }
 }
 
+int dgemm_batched(gpmpc_ctx *h, bool b_nn, int batch, int M, int N, int K, double alpha, const double *A, int lda,
+                  long long sA, const double *B, int ldb, long long sB, double beta, double *C, int ldc, long long sC,
+                  bool tri_lower, int kmode)
+{
+    if (M <= 0 || N <= 0 || batch <= 0) return GPMPC_OK;
+    if (M % GB || N % GB || K % GK || (lda & 1) || (ldb & 1) || (ldc & 1) || batch > 65535)
+        return fail(h, GPMPC_ERR_INVALID, "dgemm: shape not tile aligned");
+    dim3 grid(N / GB, M / GB, batch);
+    if (b_nn)
+        dgemm_kernel<true><<<grid, 128, 0, h->stream>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC,
+                                                        tri_lower ? 1 : 0, kmode);
+    else
+        dgemm_kernel<false><<<grid, 128, 0, h->stream>>>(M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC,
+                                                         tri_lower ? 1 : 0, kmode);
+    GP_LAUNCH_CHECK(h);
+    return GPMPC_OK;
+}
+
 int dgemm_nt(gpmpc_ctx *h, int M, int N, int K, double alpha, const double *A, int lda, const double *B,
              int ldb, double beta, double *C, int ldc, bool tri_lower, int kmode)
 {
-    if (M <= 0 || N <= 0) return GPMPC_OK;
-    if (M % GB || N % GB || K % GK || (lda & 1) || (ldb & 1) || (ldc & 1))
-        return fail(h, GPMPC_ERR_INVALID, "dgemm_nt: shape not tile aligned");
-    dim3 grid(N / GB, M / GB);
-    dgemm_nt_kernel<<<grid, 128, 0, h->stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc,
-                                                  tri_lower ? 1 : 0, kmode);
-    GP_LAUNCH_CHECK(h);
-    return GPMPC_OK;
+    return dgemm_batched(h, false, 1, M, N, K, alpha, A, lda, 0, B, ldb, 0, beta, C, ldc, 0, tri_lower, kmode);
 }
 
 }  // namespace gpmpc

@@ -544,11 +544,11 @@ def test_config3_full_size_rollout_cost_gradient(gp):
     norm_close(gs, grad[:3], 1e-7)
     # (3) directional derivative
     d = rng.normal(size=(H, m)); d /= np.linalg.norm(d)
-    h = 1e-5
+    h = 1e-3                      # the cost itself carries ~1e-9 of summation noise: a smaller step amplifies it
     cpm, _ = br.cost_and_grad(x0, np.stack([U[0] + h * d, U[0] - h * d]), -1.0, host_out=True)
     fd = (cpm[0] - cpm[1]) / (2 * h)
     an = float(np.sum(grad[0] * d))
-    assert abs(fd - an) <= 1e-5 * max(1.0, abs(an)), (fd, an)
+    assert abs(fd - an) <= 2e-5 * max(1.0, abs(an)), (fd, an)
     # (4) determinism
     cost2, grad2 = br.cost_and_grad(x0, U, -1.0, host_out=True)
     assert np.array_equal(cost, cost2) and np.array_equal(grad, grad2)
