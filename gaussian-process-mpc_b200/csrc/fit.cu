@@ -74,6 +74,7 @@ potrf_diag_kernel(double *__restrict__ A, int ld, int k0, double *__restrict__ L
     // shifted by one column: X[i][j] (i >= j) lives at S[j][i + 1]
     __shared__ double S[NB][NB + 1];
 #define XS(i, j) S[j][(i) + 1]
+    __shared__ double rinv[NB];            // 1 / L_cc
     __shared__ int bad;
     const int tid = threadIdx.x;
     const int r = tid & 63, q = tid >> 6;  // row / one of 4 column phases
@@ -83,34 +84,65 @@ potrf_diag_kernel(double *__restrict__ A, int ld, int k0, double *__restrict__ L
         if (c <= rr) { S[rr][c] = A[(size_t)(k0 + rr) * ld + k0 + c]; XS(rr, c) = 0.0; }
     }
     __syncthreads();
+    // One barrier per step: the trailing update reads the UNSCALED column c (times 1/L_cc on the fly) and the
+    // scaled column is written after the barrier, when nobody reads column c any more.
     for (int c = 0; c < NB; ++c) {
         double d = S[c][c];
         const bool ok = d > 0.0;
         if (!ok) { d = 1.0; if (tid == 0 && !bad) bad = k0 + c + 1; }
-        const double rs = rsqrt(d);
-        const double lrc = S[r][c] * rs;   // column c scaled (row r), valid for r > c
-        __syncthreads();                   // everyone has read column c / the pivot
+        const double rs = rsqrt(d);        // 1 / L_cc
+        const double lrc = S[r][c] * rs;   // L[r][c], meaningful for r > c
+        // the <= 16 updates of a thread are independent: all loads first, then the arithmetic, then the stores
+        // (interleaved, the compiler must order every store before the next load and the step becomes one long
+        // LDS -> DMUL -> DFMA -> STS chain)
+        if (r > c) {
+            double lc[NB / 4], sv[NB / 4];
+#pragma unroll
+            for (int u = 0; u < NB / 4; ++u) {
+                const int jj = c + 1 + q + 4 * u;
+                lc[u] = jj <= r ? S[jj][c] : 0.0;
+                sv[u] = jj <= r ? S[r][jj] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < NB / 4; ++u) sv[u] = fma(-lrc, lc[u] * rs, sv[u]);
+#pragma unroll
+            for (int u = 0; u < NB / 4; ++u) {
+                const int jj = c + 1 + q + 4 * u;
+                if (jj <= r) S[r][jj] = sv[u];
+            }
+        }
+        __syncthreads();
         if (q == 0) {
-            if (r == c) S[c][c] = ok ? d * rs : 1.0;
+            if (r == c) { S[c][c] = ok ? d * rs : 1.0; rinv[c] = ok ? rs : 1.0; }
             else if (r > c) S[r][c] = lrc;
         }
-        __syncthreads();
-        // trailing update of the lower triangle: S[r][j] -= L[r][c] L[j][c], c < j <= r
-        if (r > c)
-            for (int jj = c + 1 + q; jj <= r; jj += 4) S[r][jj] = fma(-lrc, S[jj][c], S[r][jj]);
-        __syncthreads();                   // column c + 1 is final before the next step reads it
     }
-    // X = L^-1:  X[k][j] = (delta_kj - sum_{p<k} L[k][p] X[p][j]) / L[k][k]; the sums are kept in Xs and updated
-    // as soon as row k is final
+    __syncthreads();
+    // X = L^-1:  X[k][j] = (delta_kj - sum_{p<k} L[k][p] X[p][j]) / L[k][k]; the partial sums live where X[k][j] will
+    // be and are pushed forward as soon as row k is final (same one-barrier scheme)
     for (int k = 0; k < NB; ++k) {
-        if (tid <= k) XS(k, tid) = ((tid == k ? 1.0 : 0.0) - XS(k, tid)) / S[k][k];
-        __syncthreads();
+        double xk = 0.0;
         if (r <= k) {
-            const double xk = XS(k, r);
-            for (int i = k + 1 + q; i < NB; i += 4) XS(i, r) = fma(S[i][k], xk, XS(i, r));
+            xk = ((r == k ? 1.0 : 0.0) - XS(k, r)) * rinv[k];
+            double lk[NB / 4], xv[NB / 4];
+#pragma unroll
+            for (int u = 0; u < NB / 4; ++u) {
+                const int i = k + 1 + q + 4 * u;
+                lk[u] = i < NB ? S[i][k] : 0.0;
+                xv[u] = i < NB ? XS(i, r) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < NB / 4; ++u) xv[u] = fma(lk[u], xk, xv[u]);
+#pragma unroll
+            for (int u = 0; u < NB / 4; ++u) {
+                const int i = k + 1 + q + 4 * u;
+                if (i < NB) XS(i, r) = xv[u];
+            }
         }
         __syncthreads();
+        if (q == 0 && r <= k) XS(k, r) = xk;
     }
+    __syncthreads();
     for (int e = tid; e < NB * NB; e += 256) {
         const int rr = e / NB, c = e % NB;
         A[(size_t)(k0 + rr) * ld + k0 + c] = (c <= rr) ? S[rr][c] : 0.0;      // upper part of the block is zero
