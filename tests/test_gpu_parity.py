@@ -552,3 +552,54 @@ def test_config3_full_size_rollout_cost_gradient(gp):
     # (4) determinism
     cost2, grad2 = br.cost_and_grad(x0, U, -1.0, host_out=True)
     assert np.array_equal(cost, cost2) and np.array_equal(grad, grad2)
+
+
+def test_solver_iterates_match_oracle_driven_solver(gp):
+    """IPOPT is not installable here and the reference pins no iterates (its only real-IPOPT test asserts a shape).
+    SURVEY 8c's fallback: a deterministic bounded quasi-Newton (scipy L-BFGS-B) is driven once by the ORACLE's
+    callbacks and once by the device callbacks (RiskSensitiveMPC.objective / gradient, the cyipopt protocol);
+    every iterate visited, every cost and every gradient must agree to the parity tolerance."""
+    from scipy.optimize import minimize
+    from oracle import oracle as orc
+    n, E, m, H = 300, 2, 1, 6
+    rng = np.random.default_rng(11)
+    S = rng.uniform(-1, 1, (n, E)); A = rng.uniform(-1, 1, (n, m))
+    nxt = 0.9 * S + 0.2 * np.tanh(np.concatenate([S, A], 1) @ rng.normal(0, 0.3, (E + m, E)))
+    Q = 2 * np.eye(E); R = 0.01 * np.eye(m)
+    mpc = gp.RiskSensitiveMPC(-1.0, H, E, m, Q, R)
+    for a in range(E):
+        mpc.dynamics.gpr_err[a].set_lambdas(np.full(E + m, 2.0)); mpc.dynamics.gpr_err[a].set_sigma_n(np.float64(0.1))
+    mpc.dynamics.append_train_data(S, A, nxt)
+    x_init = np.array([0.4, -0.3])
+    mpc.curr_state = torch.tensor(x_init, device="cuda:0")
+    X = np.concatenate([S, A], 1)
+    lam = np.full((E, E + m), 2.0)
+    fits = [orc.fit(X, nxt[:, a], lam[a], 1.0, float(np.float32(0.1 ** 2)) ** 0.5) for a in range(E)]
+
+    def run(fun):
+        trace = []
+
+        def wrapped(z):
+            c, g = fun(z)
+            trace.append((z.copy(), c, np.asarray(g, dtype=np.float64).reshape(-1).copy()))
+            return c, trace[-1][2]
+        res = minimize(wrapped, np.zeros(H * m), jac=True, method="L-BFGS-B", bounds=[(-1.0, 1.0)] * (H * m),
+                       options={"maxiter": 40, "ftol": 1e-12, "gtol": 1e-6})
+        return res, trace
+
+    def device_fun(z):
+        return mpc.objective(z), mpc.gradient(z)
+
+    def oracle_fun(z):
+        c, g, _, _ = orc.c_rollout_cost_grad(X, [f["Ky_inv"] for f in fits], [f["beta"] for f in fits], lam, np.ones(E),
+                                             x_init, z.reshape(H, m), -1.0, Q, R)
+        return c, g
+
+    res_d, tr_d = run(device_fun)
+    res_o, tr_o = run(oracle_fun)
+    assert len(tr_d) == len(tr_o) and len(tr_d) >= 5, (len(tr_d), len(tr_o))
+    for (zd, cd, gd), (zo, co, go) in zip(tr_d, tr_o):
+        assert np.max(np.abs(zd - zo)) <= 1e-6
+        close(cd, co, RTOL)
+        norm_close(gd, go, 1e-5)
+    assert np.max(np.abs(res_d.x - res_o.x)) <= 1e-6
