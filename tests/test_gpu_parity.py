@@ -603,3 +603,26 @@ def test_solver_iterates_match_oracle_driven_solver(gp):
         close(cd, co, RTOL)
         norm_close(gd, go, 1e-5)
     assert np.max(np.abs(res_d.x - res_o.x)) <= 1e-6
+
+
+@pytest.mark.parametrize("E,m", [(1, 1), (3, 2), (5, 1), (6, 2)])
+def test_dimension_sweep_both_kernels_vs_c_oracle(gp, E, m):
+    """D = 2 .. 8 and E = 1 .. 6 (more than 4 outputs sharing lambda split into two kernel passes): the few-rollouts
+    kernel (B = 3) and the batched kernel (B = 130) against the C oracle."""
+    from oracle import oracle as orc
+    n, H = 256, 3
+    D = E + m
+    dyn, S, A, nxt, rng = _synth_dynamics(gp, n, E, m, seed=20 + D)
+    X = np.concatenate([S, A], 1)
+    lam = np.full((E, D), 2.0)
+    fits = [orc.fit(X, nxt[:, a], lam[a], 1.0, float(np.float32(0.1 ** 2)) ** 0.5) for a in range(E)]
+    Q = 2 * np.eye(E) + 0.1 * np.ones((E, E)); R = 0.01 * np.eye(m)
+    br = gp.BatchedRollouts(dyn, Q, R)
+    for B in (3, 130):
+        x0 = rng.uniform(-0.5, 0.5, (B, E)); U = rng.uniform(-0.3, 0.3, (B, H, m))
+        cost, grad = br.cost_and_grad(x0, U, -0.5, host_out=True)
+        for b in (0, B - 1):
+            c, gr, _, _ = orc.c_rollout_cost_grad(X, [f["Ky_inv"] for f in fits], [f["beta"] for f in fits], lam,
+                                                  np.ones(E), x0[b], U[b], -0.5, Q, R)
+            close(cost[b], c, RTOL)
+            norm_close(grad[b], gr, RTOL)
