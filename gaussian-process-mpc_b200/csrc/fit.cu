@@ -367,8 +367,28 @@ int fit_all(gpmpc_ctx *h, const bool *which)
     GP_CUDA(h, h->linv.reserve((size_t)NB * NB * sizeof(double)));
     GP_CUDA(h, h->info.reserve(sizeof(int)));
 
+    auto same_fit_hypers = [&](int a, int b) {
+        for (int k = 0; k < h->D; ++k) if (h->lam_fit[a][k] != h->lam_fit[b][k]) return false;
+        return h->sf_fit[a] == h->sf_fit[b] && h->noise[a] == h->noise[b];
+    };
     for (int a = 0; a < E; ++a) {
         if (!which[a]) continue;
+        // Outputs share X; with bit-identical kernel hyper-parameters they share Ky and hence Ky^-1 (the reference
+        // factorises each of them again, src/gpr.py:159-171): copy instead of recomputing the same numbers.
+        int twin = -1;
+        for (int b = 0; b < a && twin < 0; ++b) if (which[b] && same_fit_hypers(a, b)) twin = b;
+        if (twin >= 0) {
+            GP_CUDA(h, cudaMemcpyAsync(h->Kinv.as<double>() + a * mat, h->Kinv.as<double>() + twin * mat, mat * sizeof(double),
+                                       cudaMemcpyDeviceToDevice, h->stream));
+            h->logdet[a] = h->logdet[twin];
+            gemv_kernel<<<(np + 7) / 8, 256, 0, h->stream>>>(h->Kinv.as<double>() + a * mat, ld, n,
+                                                             h->Y.as<double>() + (size_t)a * ld,
+                                                             h->beta.as<double>() + (size_t)a * ld, np);
+            GP_LAUNCH_CHECK(h);
+            int rc = derive_weights(h, a);
+            if (rc) return rc;
+            continue;
+        }
         GP_CUDA(h, cudaMemsetAsync(h->info.p, 0, sizeof(int), h->stream));
         double *L = h->chol.as<double>();
         dim3 blk(32, 8), grid((np + 31) / 32, (np + 7) / 8);
