@@ -57,7 +57,7 @@ extern "C" int gpmpc_destroy(gpmpc_handle h)
     cudaStreamSynchronize(h->stream);
     for (DevBuf *b : {&h->X, &h->Y, &h->Kinv, &h->Wt, &h->beta, &h->chol, &h->zt, &h->tt, &h->linv, &h->info, &h->hyp,
                       &h->mu, &h->var, &h->tape, &h->cst, &h->part, &h->mpart, &h->stage_in, &h->stage_out, &h->gbuf,
-                      &h->tickets})
+                      &h->tickets, &h->dbg})
         b->release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);

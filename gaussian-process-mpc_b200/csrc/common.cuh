@@ -77,7 +77,7 @@ struct gpmpc_ctx {
     gpmpc::DevBuf hyp;             // device copy of propagation hypers: lam[E,D], sf[E]
 
     // rollout workspaces (grow-only)
-    gpmpc::DevBuf mu, var, tape, cst, part, mpart, stage_in, stage_out, gbuf, tickets;
+    gpmpc::DevBuf mu, var, tape, cst, part, mpart, stage_in, stage_out, gbuf, tickets, dbg;
     int tape_B = 0, tape_H = 0;    // shape of the tape held from the last rollout
 
     // timing of the last pair-kernel sequence

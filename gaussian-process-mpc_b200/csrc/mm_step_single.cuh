@@ -52,7 +52,16 @@ struct SingleStepArgs {
     const double *lam_group;       // [D] of group 0
     double *us_w, *cst_w;
     double act_var;
+    unsigned long long *dbg;       // optional [B*P][6] globaltimer stamps (GPMPC_STEP_DEBUG=1), else NULL
 };
+
+__device__ __forceinline__ unsigned long long gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define GP_STAMP(i) do { if (a.dbg && tid == 0) a.dbg[((size_t)b * P + bx) * 6 + (i)] = gtime(); } while (0)
 
 template <int D, int EG>
 __host__ __device__ constexpr size_t single_stage_doubles() { return (size_t)EG * PT * PT + PT * D; }
@@ -89,6 +98,7 @@ mm_step_single(const SingleStepArgs a)
     // Programmatic dependent launch: the next step's grid may be scheduled while this one drains; everything up
     // to griddepcontrol.wait touches only data no step kernel writes (the exp table, Wt, X).
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+    GP_STAMP(0);                                         // CTA start
     if (tid < 16) tab[tid] = kExp2Tab[tid];
     if (tid == 0) {
 #pragma unroll
@@ -135,9 +145,25 @@ mm_step_single(const SingleStepArgs a)
             if (issued < t_end) issue_next();
     }
 
+    // this thread's first training point of the mean sums (X and beta are constants of the fit: their global-load
+    // latency is paid here, before the dependency wait, instead of on the critical path after it)
+    constexpr int RCAP = (int)(STAGE / (EG * NA)) < SINGLE_THREADS ? (int)(STAGE / (EG * NA)) : SINGLE_THREADS;
+    const int per = (a.ld + P - 1) / P;
+    const int j_begin = bx * per;
+    const int j_end = min(a.ld, j_begin + per);
+    const int rows = min(max(j_end - j_begin, 0), RCAP);                 // threads that own >= 1 point
+    double xpre[D], bpre[EG];
+    if (tid < rows) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) xpre[k] = a.X[(size_t)(j_begin + tid) * D + k];
+#pragma unroll
+        for (int g = 0; g < EG; ++g) bpre[g] = a.beta[g][j_begin + tid];
+    }
+
     // the first tiles are in flight; now wait until the previous kernel on the stream (the preceding step) is
     // complete and its writes (this step's constants, the ticket counters, the partial buffers) are visible
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    GP_STAMP(1);                                         // previous grid complete
     if (tid < 4 * D) cs[tid] = a.cst[(size_t)tid * a.d.Bpad + b];
     __syncthreads();
     double *mine = a.spart + ((size_t)b * P + bx) * NV;
@@ -146,11 +172,6 @@ mm_step_single(const SingleStepArgs a)
     // tiles land.  Scratch = the last ring slot (the prologue fills slots 0 .. STAGES-2 only).
     // p_k = cm_k (u_k - x_jk),  l_j = exp(-sum p_k^2),  M0 += beta_j l_j, M1_k += beta_j l_j p_k, M2_k += .. p_k^2
     {
-        constexpr int RCAP = (int)(STAGE / (EG * NA)) < SINGLE_THREADS ? (int)(STAGE / (EG * NA)) : SINGLE_THREADS;
-        const int per = (a.ld + P - 1) / P;
-        const int j_begin = bx * per;
-        const int j_end = min(a.ld, j_begin + per);
-        const int rows = min(max(j_end - j_begin, 0), RCAP);             // threads that own >= 1 point
         double *scratch = smem + (size_t)(SINGLE_STAGES - 1) * STAGE;    // [thread][EG*NA]
         if (tid < rows) {
             double m0[EG], m1[EG][D], m2[EG][D];
@@ -161,17 +182,23 @@ mm_step_single(const SingleStepArgs a)
                 for (int k = 0; k < D; ++k) m1[g][k] = m2[g][k] = 0.0;
             }
             for (int j = j_begin + tid; j < j_end; j += rows) {
+                if (j != j_begin + tid) {                // only for training sets with more than P * RCAP points
+#pragma unroll
+                    for (int k = 0; k < D; ++k) xpre[k] = a.X[(size_t)j * D + k];
+#pragma unroll
+                    for (int g = 0; g < EG; ++g) bpre[g] = a.beta[g][j];
+                }
                 double p[D], pp[D], S = 0.0;
 #pragma unroll
                 for (int k = 0; k < D; ++k) {
-                    p[k] = fma(-cs[2 * D + k], a.X[(size_t)j * D + k], cs[3 * D + k]);
+                    p[k] = fma(-cs[2 * D + k], xpre[k], cs[3 * D + k]);
                     pp[k] = p[k] * p[k];
                     S += pp[k];
                 }
                 const double l = exp_neg(S, tab);
 #pragma unroll
                 for (int g = 0; g < EG; ++g) {
-                    const double w = a.beta[g][j] * l;
+                    const double w = bpre[g] * l;
                     m0[g] += w;
 #pragma unroll
                     for (int k = 0; k < D; ++k) { m1[g][k] = fma(w, p[k], m1[g][k]); m2[g][k] = fma(w, pp[k], m2[g][k]); }
@@ -196,6 +223,7 @@ mm_step_single(const SingleStepArgs a)
         __syncthreads();                                 // the slot is free again before tile STAGES-1 is issued into it
     }
 
+    GP_STAMP(2);                                         // mean sums done, tile loop starts
     int curI = -1;
     for (int t = t_begin; t < t_end; ++t) {
         const int it = t - t_begin;
@@ -258,6 +286,7 @@ mm_step_single(const SingleStepArgs a)
         if (J == a.ntile) { ++I; J = I; }
     }
 
+    GP_STAMP(3);                                         // tile loop done
     // ---- CTA reduction of the pair sums in a fixed order: lanes (xor tree), then warps in index order ----
     auto warp_sum = [](double v) {
 #pragma unroll
@@ -296,6 +325,7 @@ mm_step_single(const SingleStepArgs a)
     __syncthreads();
     if (tid == 0) s_last = (atomicAdd(&tk[1 + gidx], 1) == gsize - 1);
     __syncthreads();
+    GP_STAMP(4);                                         // partial written, first ticket drawn
     if (!s_last) return;
     __threadfence();
     {
@@ -354,6 +384,8 @@ mm_step_single(const SingleStepArgs a)
             a.cst_w[(size_t)(3 * D + k) * a.d.Bpad + b] = cmu;
         }
     }
+    GP_STAMP(5);                                         // last CTA: finalize and next-step constants done
 }
+#undef GP_STAMP
 
 }  // namespace gpmpc

@@ -658,9 +658,46 @@ static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int ctas, int P, lon
             sa.want_grad = want_grad ? 1 : 0;
             sa.prep_next = (next.on && d.G == 1) ? 1 : 0;
             sa.Uint = next.Uint; sa.lam_group = next.lam_group; sa.us_w = us; sa.cst_w = cst; sa.act_var = next.act_var;
+            sa.dbg = nullptr;
+            static const bool step_debug = getenv("GPMPC_STEP_DEBUG") != nullptr;
+            if (step_debug) {                            // development aid: per-CTA phase stamps of every launch
+                GP_CUDA(h, h->dbg.reserve((size_t)d.B * ctas * 6 * sizeof(unsigned long long)));
+                GP_CUDA(h, cudaMemsetAsync(h->dbg.p, 0, (size_t)d.B * ctas * 6 * sizeof(unsigned long long), h->stream));
+                sa.dbg = h->dbg.as<unsigned long long>();
+            }
             e = single_launcher(d.D)(grp.count, want_grad, sa, dim3(d.B, ctas), h->stream);
             h->launches++;
             if (e != cudaSuccess) return fail(h, GPMPC_ERR_CUDA, std::string("mm_step_single: ") + cudaGetErrorString(e));
+            if (step_debug) {
+                std::vector<unsigned long long> st((size_t)d.B * ctas * 6);
+                GP_CUDA(h, cudaMemcpyAsync(st.data(), h->dbg.p, st.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+                GP_CUDA(h, cudaStreamSynchronize(h->stream));
+                unsigned long long t0 = ~0ull, tend = 0;
+                for (size_t c = 0; c < st.size() / 6; ++c) { if (st[c * 6] && st[c * 6] < t0) t0 = st[c * 6]; }
+                double mx[6] = {0, 0, 0, 0, 0, 0}, av[6] = {0, 0, 0, 0, 0, 0};
+                for (size_t c = 0; c < st.size() / 6; ++c)
+                    for (int i = 0; i < 6; ++i) {
+                        if (!st[c * 6 + i]) continue;
+                        const double v = (double)(st[c * 6 + i] - t0) * 1e-3;
+                        if (v > mx[i]) mx[i] = v;
+                        av[i] += v / (st.size() / 6);
+                        if (st[c * 6 + i] > tend) tend = st[c * 6 + i];
+                    }
+                if (const char *path = getenv("GPMPC_STEP_DEBUG_FILE")) {
+                    if (FILE *f = fopen(path, "w")) {
+                        fprintf(f, "cta,start,depwait,loop_start,loop_end,ticket,done\n");
+                        for (size_t c = 0; c < st.size() / 6; ++c) {
+                            fprintf(f, "%zu", c);
+                            for (int i = 0; i < 6; ++i) fprintf(f, ",%.3f", st[c * 6 + i] ? (double)(st[c * 6 + i] - t0) * 1e-3 : -1.0);
+                            fprintf(f, "\n");
+                        }
+                        fclose(f);
+                    }
+                }
+                fprintf(stderr, "step %d us since first CTA start: start avg %.1f max %.1f | dep-wait done avg %.1f max %.1f | loop "
+                                "start avg %.1f max %.1f | loop end avg %.1f max %.1f | ticket avg %.1f max %.1f | last CTA done %.1f\n",
+                        t, av[0], mx[0], av[1], mx[1], av[2], mx[2], av[3], mx[3], av[4], mx[4], mx[5]);
+            }
             continue;
         }
         PairArgs pa;
