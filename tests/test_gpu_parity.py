@@ -626,3 +626,46 @@ def test_dimension_sweep_both_kernels_vs_c_oracle(gp, E, m):
                                                   np.ones(E), x0[b], U[b], -0.5, Q, R)
             close(cost[b], c, RTOL)
             norm_close(grad[b], gr, RTOL)
+
+
+@pytest.mark.parametrize("n", [1, 2, 10, 63, 65])
+def test_tiny_and_ragged_training_sets(gp, n):
+    """Edge sizes: a single training point, n below / just above one 64-row padding granule, the reference's own
+    rollout test size (n = 10, E = 2, m = 1, H = 2, sigma_n = 0.1; src/test/test_dynamics.py:134-196)."""
+    from oracle import oracle as orc
+    E, m, H = 2, 1, 2
+    dyn, S, A, nxt, rng = _synth_dynamics(gp, n, E, m, seed=40 + n)
+    X = np.concatenate([S, A], 1)
+    lam = np.full((E, E + m), 2.0)
+    fits = [orc.fit(X, nxt[:, a], lam[a], 1.0, float(np.float32(0.1 ** 2)) ** 0.5) for a in range(E)]
+    Q = 2 * np.eye(E); R = 0.01 * np.eye(m)
+    br = gp.BatchedRollouts(dyn, Q, R)
+    for B in (1, 113):                               # few-rollouts kernel and batched kernel
+        x0 = rng.uniform(-0.5, 0.5, (B, E)); U = rng.uniform(-0.3, 0.3, (B, H, m))
+        cost, grad = br.cost_and_grad(x0, U, -1.0, host_out=True)
+        c, gr, means, vars_ = orc.c_rollout_cost_grad(X, [f["Ky_inv"] for f in fits], [f["beta"] for f in fits], lam,
+                                                      np.ones(E), x0[B - 1], U[B - 1], -1.0, Q, R)
+        close(cost[B - 1], c, RTOL)
+        norm_close(grad[B - 1], gr, RTOL)
+    # NumPy-interface rollout of the same data (means and covariances like the reference's forward_propagate)
+    mu, cov = dyn.forward_propagate(H, x0[B - 1], U[B - 1])
+    close(mu, means, RTOL)
+    for t in range(H + 1):
+        assert np.max(np.abs(np.diag(cov[t]) - vars_[t])) <= RTOL * max(1.0, np.max(np.abs(vars_[t])))
+
+
+def test_zero_horizon_and_missing_data(gp):
+    from oracle import oracle as orc
+    E, m = 2, 1
+    dyn, S, A, nxt, rng = _synth_dynamics(gp, 50, E, m, seed=7)
+    Q = 2 * np.eye(E); R = 0.01 * np.eye(m)
+    br = gp.BatchedRollouts(dyn, Q, R)
+    x0 = rng.uniform(-0.5, 0.5, (4, E))
+    cost, grad = br.cost_and_grad(x0, np.zeros((4, 0, m)), -1.0, host_out=True)      # H = 0: the x_0 term only
+    for b in range(4):
+        ref = np.log(np.linalg.det(np.eye(E) - Q * 1e-3)) / -1.0 + x0[b] @ np.linalg.inv(np.linalg.inv(Q) - 1e-3 * np.eye(E)) @ x0[b]
+        close(cost[b], ref, RTOL)
+    assert grad.shape == (4, 0, m)
+    empty = gp.Dynamics(E, m)
+    with pytest.raises(Exception):
+        empty.forward_propagate(2, np.zeros(E), np.zeros((2, m)))
