@@ -669,3 +669,34 @@ def test_zero_horizon_and_missing_data(gp):
     empty = gp.Dynamics(E, m)
     with pytest.raises(Exception):
         empty.forward_propagate(2, np.zeros(E), np.zeros((2, m)))
+
+
+def test_config5_gamma_sweep_batched_solver_vs_scalar_solves(gp):
+    """configs[4] in miniature: a gamma sweep x several initial states solved in lock step by BatchedSolver (one
+    batched device evaluation per iteration) against one scalar solve per instance through the cyipopt-protocol
+    callbacks (L-BFGS-B here).  Different optimisers, same optimum: costs agree to 1e-5, controls to 1e-2."""
+    n, E, m, H = 400, 2, 1, 5
+    rng = np.random.default_rng(5)
+    S = rng.uniform(-1, 1, (n, E)); A = rng.uniform(-1, 1, (n, m))
+    nxt = 0.9 * S + 0.2 * np.tanh(np.concatenate([S, A], 1) @ rng.normal(0, 0.3, (E + m, E)))
+    Q = 2 * np.eye(E); R = 0.01 * np.eye(m)
+    mpc = gp.RiskSensitiveMPC(-1.0, H, E, m, Q, R)
+    for a in range(E):
+        mpc.dynamics.gpr_err[a].set_lambdas(np.full(E + m, 2.0)); mpc.dynamics.gpr_err[a].set_sigma_n(np.float64(0.1))
+    mpc.dynamics.append_train_data(S, A, nxt)
+    mpc.set_lb([-1.0]); mpc.set_ub([1.0])
+    gammas = np.array([-2.0, -1.0, -0.5, 0.5, 1.0])
+    starts = rng.uniform(-0.6, 0.6, (4, E))
+    G, X0 = np.meshgrid(gammas, np.arange(len(starts)), indexing="ij")
+    gam = G.reshape(-1); x0 = starts[X0.reshape(-1)]
+    B = gam.size
+    br = gp.BatchedRollouts(mpc.dynamics, Q, R)
+    sol = gp.BatchedSolver(br, H, m, lb=[-1.0], ub=[1.0], max_iter=200, gtol=1e-6).solve(x0, gam)
+    assert sol["U"].shape == (B, H, m) and np.all(np.isfinite(sol["cost"]))
+    for b in range(0, B, 3):
+        mpc.gamma = float(gam[b])
+        u = mpc.get_optimal_trajectory(x0[b])
+        c = mpc.objective(u.reshape(-1))
+        assert sol["cost"][b] <= c + 1e-5 * max(1.0, abs(c)), (b, sol["cost"][b], c)
+        assert abs(sol["cost"][b] - c) <= 1e-4 * max(1.0, abs(c)), (b, sol["cost"][b], c)
+        assert np.max(np.abs(sol["U"][b] - u)) <= 2e-2
