@@ -60,8 +60,12 @@ int gram_into(gpmpc_ctx *h, int a, double *dst, int ldd, bool add_noise)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Diagonal block: unblocked Cholesky of a 64x64 block in shared memory, then the inverse of the factor by a
-// right-looking column sweep (both 64 steps of <= 16 FMAs per thread).  Writes
+// Diagonal block: Cholesky of a 64x64 block and the inverse of its factor, one CTA, matrix in REGISTERS.
+// 256 threads form a 16x16 grid; thread (ty, tx) owns the 4x4 sub-block rows 4ty.., columns 4tx.. (threads above the
+// diagonal idle along).  Each of the 64 right-looking steps publishes one column (and, for the inverse, one row)
+// through a double-buffered 64-entry shared array: one barrier, 8 shared loads and 16 FMAs per thread and step.
+// (A shared-memory-resident version was bound by the shared-memory bandwidth of the one SM it runs on: 63 us.)
+// Writes
 //   A    : L_kk in place (upper part of the block zeroed),
 //   Linv : L_kk^-1 dense row-major (the panel solve A[i,k] L_kk^-T is then a tensor-core GEMM),
 //   ZT   : (L_kk^-1)^T into the diagonal block of L^-T (leaf of the recursive triangular inverse).
@@ -70,87 +74,130 @@ __global__ void __launch_bounds__(256)
 potrf_diag_kernel(double *__restrict__ A, int ld, int k0, double *__restrict__ Linv, double *__restrict__ ZT,
                   int ldz, int *info)
 {
-    // L in the lower triangle (c <= r); X = L^-1 (also lower triangular) transposed into the unused upper part,
-    // shifted by one column: X[i][j] (i >= j) lives at S[j][i + 1]
-    __shared__ double S[NB][NB + 1];
-#define XS(i, j) S[j][(i) + 1]
+    __shared__ __align__(32) double colb[2][NB];   // published column of the current step (double buffered)
+    __shared__ __align__(32) double rowb[2][NB];   // inverse: published row k of X
     __shared__ double rinv[NB];            // 1 / L_cc
     __shared__ int bad;
     const int tid = threadIdx.x;
-    const int r = tid & 63, q = tid >> 6;  // row / one of 4 column phases
+    const int tx = tid & 15, ty = tid >> 4;
     if (tid == 0) bad = 0;
-    for (int e = tid; e < NB * NB; e += 256) {
-        const int rr = e / NB, c = e % NB;
-        if (c <= rr) { S[rr][c] = A[(size_t)(k0 + rr) * ld + k0 + c]; XS(rr, c) = 0.0; }
-    }
+#ifdef GPMPC_POTRF_TIMING
+    long long tstamp[5]; tstamp[0] = clock64();
+#define POTRF_STAMP(i) tstamp[i] = clock64()
+#else
+#define POTRF_STAMP(i)
+#endif
+    double a[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = 4 * ty + i, c = 4 * tx + j;
+            a[i][j] = (c <= r) ? A[(size_t)(k0 + r) * ld + k0 + c] : 0.0;
+        }
     __syncthreads();
-    // One barrier per step: the trailing update reads the UNSCALED column c (times 1/L_cc on the fly) and the
-    // scaled column is written after the barrier, when nobody reads column c any more.
-    for (int c = 0; c < NB; ++c) {
-        double d = S[c][c];
-        const bool ok = d > 0.0;
-        if (!ok) { d = 1.0; if (tid == 0 && !bad) bad = k0 + c + 1; }
-        const double rs = rsqrt(d);        // 1 / L_cc
-        const double lrc = S[r][c] * rs;   // L[r][c], meaningful for r > c
-        // the <= 16 updates of a thread are independent: all loads first, then the arithmetic, then the stores
-        // (interleaved, the compiler must order every store before the next load and the step becomes one long
-        // LDS -> DMUL -> DFMA -> STS chain)
-        if (r > c) {
-            double lc[NB / 4], sv[NB / 4];
+    POTRF_STAMP(1);
+    // ---- Cholesky, right-looking by columns ----
+#pragma unroll 1
+    for (int tc = 0; tc < 16; ++tc) {
 #pragma unroll
-            for (int u = 0; u < NB / 4; ++u) {
-                const int jj = c + 1 + q + 4 * u;
-                lc[u] = jj <= r ? S[jj][c] : 0.0;
-                sv[u] = jj <= r ? S[r][jj] : 0.0;
+        for (int cc = 0; cc < 4; ++cc) {
+            const int c = 4 * tc + cc;
+            double *col = colb[c & 1];
+            if (tx == tc) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) col[4 * ty + i] = a[i][cc];
             }
+            __syncthreads();
+            double d = col[c];
+            const bool ok = d > 0.0;
+            if (!ok) { d = 1.0; if (tid == 0 && !bad) bad = k0 + c + 1; }
+            const double rs = rsqrt(d);        // 1 / L_cc
+            // 4 consecutive doubles per thread as two 16-byte loads (stride-4 scalar loads are 4-way bank conflicts)
+            const double2 r01 = *reinterpret_cast<const double2 *>(&col[4 * ty]), r23 = *reinterpret_cast<const double2 *>(&col[4 * ty + 2]);
+            const double2 c01 = *reinterpret_cast<const double2 *>(&col[4 * tx]), c23 = *reinterpret_cast<const double2 *>(&col[4 * tx + 2]);
+            const double lr[4] = {r01.x * rs, r01.y * rs, r23.x * rs, r23.y * rs};
+            const double lc[4] = {c01.x * rs, c01.y * rs, c23.x * rs, c23.y * rs};
+            if (tx == tc) {                    // the owners keep the scaled column
 #pragma unroll
-            for (int u = 0; u < NB / 4; ++u) sv[u] = fma(-lrc, lc[u] * rs, sv[u]);
+                for (int i = 0; i < 4; ++i) {
+                    const int r = 4 * ty + i;
+                    if (r > c) a[i][cc] = lr[i];
+                    else if (r == c) a[i][cc] = ok ? d * rs : 1.0;
+                }
+            }
+            if (tid == 0) rinv[c] = ok ? rs : 1.0;
+            // trailing update: a[r][j] -= L[r][c] L[j][c] for columns j > c (rows above the diagonal hold garbage that
+            // is never read)
+            if (tx >= tc) {
 #pragma unroll
-            for (int u = 0; u < NB / 4; ++u) {
-                const int jj = c + 1 + q + 4 * u;
-                if (jj <= r) S[r][jj] = sv[u];
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (4 * tx + j > c) a[i][j] = fma(-lr[i], lc[j], a[i][j]);
             }
         }
-        __syncthreads();
-        if (q == 0) {
-            if (r == c) { S[c][c] = ok ? d * rs : 1.0; rinv[c] = ok ? rs : 1.0; }
-            else if (r > c) S[r][c] = lrc;
-        }
     }
     __syncthreads();
-    // X = L^-1:  X[k][j] = (delta_kj - sum_{p<k} L[k][p] X[p][j]) / L[k][k]; the partial sums live where X[k][j] will
-    // be and are pushed forward as soon as row k is final (same one-barrier scheme)
-    for (int k = 0; k < NB; ++k) {
-        double xk = 0.0;
-        if (r <= k) {
-            xk = ((r == k ? 1.0 : 0.0) - XS(k, r)) * rinv[k];
-            double lk[NB / 4], xv[NB / 4];
+    POTRF_STAMP(2);
+    // ---- X = L^-1, right-looking by rows: once row k of X is final it is pushed into the sums of the rows below ----
+    double x[4][4];                            // running sums, then X
 #pragma unroll
-            for (int u = 0; u < NB / 4; ++u) {
-                const int i = k + 1 + q + 4 * u;
-                lk[u] = i < NB ? S[i][k] : 0.0;
-                xv[u] = i < NB ? XS(i, r) : 0.0;
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[i][j] = 0.0;
+#pragma unroll 1
+    for (int tk = 0; tk < 16; ++tk) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const int k = 4 * tk + kk;
+            double *row = rowb[k & 1], *col = colb[k & 1];
+            if (ty == tk) {                    // owners of row k: finalise and publish it
+                const double rk = rinv[k];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int c = 4 * tx + j;
+                    const double v = c <= k ? ((c == k ? 1.0 : 0.0) - x[kk][j]) * rk : 0.0;
+                    x[kk][j] = v;
+                    row[c] = v;
+                }
             }
+            if (tx == tk) {                    // owners of column k of L publish it
 #pragma unroll
-            for (int u = 0; u < NB / 4; ++u) xv[u] = fma(lk[u], xk, xv[u]);
+                for (int i = 0; i < 4; ++i) col[4 * ty + i] = a[i][kk];
+            }
+            __syncthreads();
+            if (ty >= tk) {
+                const double2 l01 = *reinterpret_cast<const double2 *>(&col[4 * ty]), l23 = *reinterpret_cast<const double2 *>(&col[4 * ty + 2]);
+                const double2 x01 = *reinterpret_cast<const double2 *>(&row[4 * tx]), x23 = *reinterpret_cast<const double2 *>(&row[4 * tx + 2]);
+                const double li[4] = {l01.x, l01.y, l23.x, l23.y};
+                const double xj[4] = {x01.x, x01.y, x23.x, x23.y};
 #pragma unroll
-            for (int u = 0; u < NB / 4; ++u) {
-                const int i = k + 1 + q + 4 * u;
-                if (i < NB) XS(i, r) = xv[u];
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (4 * ty + i > k) x[i][j] = fma(li[i], xj[j], x[i][j]);
             }
         }
-        __syncthreads();
-        if (q == 0 && r <= k) XS(k, r) = xk;
     }
-    __syncthreads();
-    for (int e = tid; e < NB * NB; e += 256) {
-        const int rr = e / NB, c = e % NB;
-        A[(size_t)(k0 + rr) * ld + k0 + c] = (c <= rr) ? S[rr][c] : 0.0;      // upper part of the block is zero
-        Linv[e] = (c <= rr) ? XS(rr, c) : 0.0;
-        ZT[(size_t)(k0 + rr) * ldz + k0 + c] = (c >= rr) ? XS(c, rr) : 0.0;   // transposed
-    }
+    POTRF_STAMP(3);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = 4 * ty + i, c = 4 * tx + j;
+            const bool low = c <= r;
+            A[(size_t)(k0 + r) * ld + k0 + c] = low ? a[i][j] : 0.0;          // upper part of the block is zero
+            Linv[r * NB + c] = low ? x[i][j] : 0.0;
+            ZT[(size_t)(k0 + c) * ldz + k0 + r] = low ? x[i][j] : 0.0;        // transposed
+        }
     if (tid == 0 && bad) atomicCAS(info, 0, bad);
-#undef XS
+#ifdef GPMPC_POTRF_TIMING
+    POTRF_STAMP(4);
+    if (tid == 0) printf("potrf_diag cycles: load %lld, cholesky %lld, inverse %lld, store %lld\n", tstamp[1] - tstamp[0],
+                         tstamp[2] - tstamp[1], tstamp[3] - tstamp[2], tstamp[4] - tstamp[3]);
+#endif
+#undef POTRF_STAMP
 }
 
 // copy the lower triangle (tiles computed by the tri_lower GEMM) into the upper triangle
