@@ -59,6 +59,9 @@ extern "C" int gpmpc_destroy(gpmpc_handle h)
                       &h->mu, &h->var, &h->tape, &h->cst, &h->part, &h->mpart, &h->stage_in, &h->stage_out, &h->gbuf,
                       &h->tickets, &h->dbg})
         b->release();
+    for (cudaStream_t st : h->aux_streams) cudaStreamDestroy(st);
+    for (cudaEvent_t ev : h->aux_events) cudaEventDestroy(ev);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     delete h;

@@ -80,6 +80,11 @@ struct gpmpc_ctx {
     gpmpc::DevBuf mu, var, tape, cst, part, mpart, stage_in, stage_out, gbuf, tickets, dbg;
     int tape_B = 0, tape_H = 0;    // shape of the tape held from the last rollout
 
+    // auxiliary streams / events: independent outputs are fitted concurrently (fit.cu)
+    std::vector<cudaStream_t> aux_streams;
+    std::vector<cudaEvent_t> aux_events;
+    cudaEvent_t ev_fork = nullptr;
+
     // timing of the last pair-kernel sequence
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_pair_ms = 0.0;

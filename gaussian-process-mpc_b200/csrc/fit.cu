@@ -319,14 +319,13 @@ int upload_prop_hypers(gpmpc_ctx *h)
 // rank updates touch only the panel, the rest of the matrix gets ONE rank-NB2 update per outer step (4x fewer
 // passes over the trailing matrix, 16 k-steps per tensor-core tile instead of 4).
 constexpr int NB2 = 256;
-static int cholesky_inplace(gpmpc_ctx *h, double *L, double *ZT, int np)
+static int cholesky_inplace(gpmpc_ctx *h, double *L, double *ZT, int np, double *linv, int *info)
 {
     const int ld = h->ld;
-    double *linv = h->linv.as<double>();
     for (int K0 = 0; K0 < np; K0 += NB2) {
         const int w = np - K0 < NB2 ? np - K0 : NB2;
         for (int k = K0; k < K0 + w; k += NB) {
-            potrf_diag_kernel<<<1, 256, 0, h->stream>>>(L, ld, k, linv, ZT, ld, h->info.as<int>());
+            potrf_diag_kernel<<<1, 256, 0, h->stream>>>(L, ld, k, linv, ZT, ld, info);
             GP_LAUNCH_CHECK(h);
             const int rem = np - (k + NB);
             if (rem <= 0) break;
@@ -406,70 +405,108 @@ int fit_all(gpmpc_ctx *h, const bool *which)
 {
     const int ld = h->ld, np = h->ld, n = h->n, E = h->E;
     const size_t mat = (size_t)ld * ld;
-    GP_CUDA(h, h->Kinv.reserve(mat * E * sizeof(double)));
-    GP_CUDA(h, h->Wt.reserve(wt_doubles(ld) * E * sizeof(double)));
-    GP_CUDA(h, h->beta.reserve((size_t)ld * E * sizeof(double)));
-    GP_CUDA(h, h->chol.reserve(mat * sizeof(double)));
-    GP_CUDA(h, h->zt.reserve(mat * sizeof(double)));
-    GP_CUDA(h, h->linv.reserve((size_t)NB * NB * sizeof(double)));
-    GP_CUDA(h, h->info.reserve(sizeof(int)));
-
     auto same_fit_hypers = [&](int a, int b) {
         for (int k = 0; k < h->D; ++k) if (h->lam_fit[a][k] != h->lam_fit[b][k]) return false;
         return h->sf_fit[a] == h->sf_fit[b] && h->noise[a] == h->noise[b];
     };
+    // Outputs share X; with bit-identical kernel hyper-parameters they share Ky and hence Ky^-1 (the reference
+    // factorises each of them again, src/gpr.py:159-171): one "leader" per distinct hyper-parameter set is
+    // factorised, its twins copy the result.  Leaders are independent problems: they run concurrently on auxiliary
+    // streams, so that one output's serial diagonal-block chain overlaps the other outputs' GEMMs.
+    int twin[kMaxE];
+    std::vector<int> leaders;
     for (int a = 0; a < E; ++a) {
+        twin[a] = -1;
         if (!which[a]) continue;
-        // Outputs share X; with bit-identical kernel hyper-parameters they share Ky and hence Ky^-1 (the reference
-        // factorises each of them again, src/gpr.py:159-171): copy instead of recomputing the same numbers.
-        int twin = -1;
-        for (int b = 0; b < a && twin < 0; ++b) if (which[b] && same_fit_hypers(a, b)) twin = b;
-        if (twin >= 0) {
-            GP_CUDA(h, cudaMemcpyAsync(h->Kinv.as<double>() + a * mat, h->Kinv.as<double>() + twin * mat, mat * sizeof(double),
-                                       cudaMemcpyDeviceToDevice, h->stream));
-            h->logdet[a] = h->logdet[twin];
-            gemv_kernel<<<(np + 7) / 8, 256, 0, h->stream>>>(h->Kinv.as<double>() + a * mat, ld, n,
-                                                             h->Y.as<double>() + (size_t)a * ld,
-                                                             h->beta.as<double>() + (size_t)a * ld, np);
-            GP_LAUNCH_CHECK(h);
-            int rc = derive_weights(h, a);
-            if (rc) return rc;
-            continue;
-        }
-        GP_CUDA(h, cudaMemsetAsync(h->info.p, 0, sizeof(int), h->stream));
-        double *L = h->chol.as<double>();
+        for (int b = 0; b < a && twin[a] < 0; ++b) if (which[b] && same_fit_hypers(a, b)) twin[a] = b;
+        if (twin[a] < 0) leaders.push_back(a);
+    }
+    const size_t nl = leaders.size();
+    GP_CUDA(h, h->Kinv.reserve(mat * E * sizeof(double)));
+    GP_CUDA(h, h->Wt.reserve(wt_doubles(ld) * E * sizeof(double)));
+    GP_CUDA(h, h->beta.reserve((size_t)ld * E * sizeof(double)));
+    GP_CUDA(h, h->chol.reserve(mat * (nl ? nl : 1) * sizeof(double)));
+    GP_CUDA(h, h->zt.reserve(mat * (nl ? nl : 1) * sizeof(double)));
+    GP_CUDA(h, h->linv.reserve(((size_t)NB * NB + 8) * kMaxE * sizeof(double)));     // per leader: Lkk^-1 | log det
+    GP_CUDA(h, h->info.reserve(kMaxE * sizeof(int)));
+    GP_CUDA(h, cudaMemsetAsync(h->info.p, 0, kMaxE * sizeof(int), h->stream));
+
+    cudaStream_t main_stream = h->stream;
+    while (h->aux_streams.size() + 1 < nl) {
+        cudaStream_t st; cudaEvent_t ev;
+        GP_CUDA(h, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        GP_CUDA(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        h->aux_streams.push_back(st); h->aux_events.push_back(ev);
+    }
+    if (!h->ev_fork) GP_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    if (nl > 1) GP_CUDA(h, cudaEventRecord(h->ev_fork, main_stream));
+
+    int rc = GPMPC_OK;
+    for (size_t s = 0; s < nl && rc == GPMPC_OK; ++s) {
+        const int a = leaders[s];
+        cudaStream_t st = s == 0 ? main_stream : h->aux_streams[s - 1];
+        if (s > 0) { cudaError_t e = cudaStreamWaitEvent(st, h->ev_fork, 0); if (e != cudaSuccess) { rc = fail(h, GPMPC_ERR_CUDA, cudaGetErrorString(e)); break; } }
+        h->stream = st;                          // the helpers below launch on h->stream
+        double *L = h->chol.as<double>() + s * mat;
+        double *ZT = h->zt.as<double>() + s * mat;
+        double *linv = h->linv.as<double>() + s * ((size_t)NB * NB + 8);
+        int *info = h->info.as<int>() + s;
+        double *Kinv = h->Kinv.as<double>() + a * mat;
         dim3 blk(32, 8), grid((np + 31) / 32, (np + 7) / 8);
-        gram_kernel<<<grid, blk, 0, h->stream>>>(h->X.as<double>(), n, np, h->D, make_hyper(h, a, false), L, ld, 1);
-        GP_LAUNCH_CHECK(h);
-        double *ZT = h->zt.as<double>();
-        int rc = cholesky_inplace(h, L, ZT, np);
-        if (rc) return rc;
-        logdet_kernel<<<1, 1024, 0, h->stream>>>(L, ld, n, h->linv.as<double>());   // linv is free after the loop
-        GP_LAUNCH_CHECK(h);
-        int info = 0;
-        GP_CUDA(h, cudaMemcpyAsync(&info, h->info.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        GP_CUDA(h, cudaMemcpyAsync(&h->logdet[a], h->linv.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        GP_CUDA(h, cudaStreamSynchronize(h->stream));
-        if (info != 0) {
+        gram_kernel<<<grid, blk, 0, st>>>(h->X.as<double>(), n, np, h->D, make_hyper(h, a, false), L, ld, 1);
+        h->launches++;
+        if ((rc = cholesky_inplace(h, L, ZT, np, linv, info))) break;
+        logdet_kernel<<<1, 1024, 0, st>>>(L, ld, n, linv + (size_t)NB * NB);
+        h->launches++;
+        if ((rc = invert_factor(h, L, ZT, Kinv, np))) break;        // Kinv doubles as workspace until the next line
+        // Ky^-1[i][j] = sum_{k >= max(i,j)} ZT[i][k] ZT[j][k]; lower tiles, then mirrored
+        if ((rc = dgemm_nt(h, np, np, np, 1.0, ZT, ld, ZT, ld, 0.0, Kinv, ld, true, 2))) break;
+        dim3 mblk(32, 8), mgrid(np / 32, np / 32);
+        mirror_lower_kernel<<<mgrid, mblk, 0, st>>>(Kinv, np, ld);
+        h->launches++;
+        // beta = Ky^-1 y   (src/tools/uncertainty_prop.py:327)
+        gemv_kernel<<<(np + 7) / 8, 256, 0, st>>>(Kinv, ld, n, h->Y.as<double>() + (size_t)a * ld,
+                                                  h->beta.as<double>() + (size_t)a * ld, np);
+        h->launches++;
+        if ((rc = derive_weights(h, a))) break;
+        if (s > 0) {
+            cudaError_t e = cudaEventRecord(h->aux_events[s - 1], st);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(main_stream, h->aux_events[s - 1], 0);
+            if (e != cudaSuccess) rc = fail(h, GPMPC_ERR_CUDA, cudaGetErrorString(e));
+        }
+    }
+    h->stream = main_stream;
+    if (rc) { cudaDeviceSynchronize(); return rc; }
+    {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(h, GPMPC_ERR_CUDA, std::string("fit kernels: ") + cudaGetErrorString(e));
+    }
+    // one host synchronisation for all leaders: pivots and log-determinants
+    std::vector<int> info(nl ? nl : 1, 0);
+    std::vector<double> ldet(nl ? nl : 1, 0.0);
+    if (nl) GP_CUDA(h, cudaMemcpyAsync(info.data(), h->info.p, nl * sizeof(int), cudaMemcpyDeviceToHost, main_stream));
+    for (size_t s = 0; s < nl; ++s)
+        GP_CUDA(h, cudaMemcpyAsync(&ldet[s], h->linv.as<double>() + s * ((size_t)NB * NB + 8) + (size_t)NB * NB, sizeof(double),
+                                   cudaMemcpyDeviceToHost, main_stream));
+    GP_CUDA(h, cudaStreamSynchronize(main_stream));
+    for (size_t s = 0; s < nl; ++s) {
+        if (info[s] != 0) {
             char msg[160];
-            snprintf(msg, sizeof msg, "gpmpc_fit: Ky of output %d is not positive definite (pivot %d)", a, info - 1);
+            snprintf(msg, sizeof msg, "gpmpc_fit: Ky of output %d is not positive definite (pivot %d)", leaders[s], info[s] - 1);
             return fail(h, GPMPC_ERR_NOT_PD, msg);
         }
-        double *Kinv = h->Kinv.as<double>() + a * mat;
-        rc = invert_factor(h, L, ZT, Kinv, np);          // Kinv doubles as workspace until the next line
-        if (rc) return rc;
-        // Ky^-1[i][j] = sum_{k >= max(i,j)} ZT[i][k] ZT[j][k]; lower tiles, then mirrored
-        rc = dgemm_nt(h, np, np, np, 1.0, ZT, ld, ZT, ld, 0.0, Kinv, ld, true, 2);
-        if (rc) return rc;
-        dim3 mblk(32, 8), mgrid(np / 32, np / 32);
-        mirror_lower_kernel<<<mgrid, mblk, 0, h->stream>>>(Kinv, np, ld);
+        h->logdet[leaders[s]] = ldet[s];
+    }
+    for (int a = 0; a < E; ++a) {
+        if (!which[a] || twin[a] < 0) continue;
+        GP_CUDA(h, cudaMemcpyAsync(h->Kinv.as<double>() + a * mat, h->Kinv.as<double>() + twin[a] * mat, mat * sizeof(double),
+                                   cudaMemcpyDeviceToDevice, main_stream));
+        h->logdet[a] = h->logdet[twin[a]];
+        gemv_kernel<<<(np + 7) / 8, 256, 0, main_stream>>>(h->Kinv.as<double>() + a * mat, ld, n,
+                                                           h->Y.as<double>() + (size_t)a * ld,
+                                                           h->beta.as<double>() + (size_t)a * ld, np);
         GP_LAUNCH_CHECK(h);
-        // beta = Ky^-1 y   (src/tools/uncertainty_prop.py:327)
-        gemv_kernel<<<(np + 7) / 8, 256, 0, h->stream>>>(Kinv, ld, n, h->Y.as<double>() + (size_t)a * ld,
-                                                         h->beta.as<double>() + (size_t)a * ld, np);
-        GP_LAUNCH_CHECK(h);
-        rc = derive_weights(h, a);
-        if (rc) return rc;
+        if ((rc = derive_weights(h, a))) return rc;
     }
     h->fitted = true;
     return GPMPC_OK;

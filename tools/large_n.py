@@ -5,13 +5,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import gpmpc_b200 as gp
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+ard = len(sys.argv) > 2 and sys.argv[2] == "ard"      # distinct hyper-parameters per output: no shared factorisation
 E, m = 4, 1
 rng = np.random.default_rng(0)
 S = rng.uniform(-1, 1, (n, E)); A = rng.uniform(-1, 1, (n, m))
 nxt = 0.9 * S + 0.2 * np.tanh(np.concatenate([S, A], 1) @ rng.normal(0, 0.3, (E + m, E)))
 dyn = gp.Dynamics(E, m)
 for a in range(E):
-    dyn.gpr_err[a].set_lambdas(np.full(E + m, 2.0)); dyn.gpr_err[a].set_sigma_n(np.float64(0.1))
+    dyn.gpr_err[a].set_lambdas(np.full(E + m, 2.0 + (0.1 * a if ard else 0.0))); dyn.gpr_err[a].set_sigma_n(np.float64(0.1))
 t0 = time.perf_counter(); dyn.append_train_data(S, A, nxt); dyn._bundle.synchronize(); t1 = time.perf_counter()
 print(f"n={n}: fit of {E} outputs {t1 - t0:.3f} s; mem {torch.cuda.memory_allocated()/1e9:.1f} GB torch + lib buffers")
 t0 = time.perf_counter(); dyn.append_train_data(S, A, nxt); dyn._bundle.synchronize(); t1 = time.perf_counter()
