@@ -179,16 +179,24 @@ class BatchedSolver:
             slope = np.einsum("bn,bn->b", Dir, Gf)
             bad = ~(slope < 0)
             Dir[bad] = -Gf[bad]
-            step = np.ones(B)
+            # first trial: the unit quasi-Newton step; without curvature history (first iteration, or after a reset)
+            # a steepest-descent step of unit length, like L-BFGS-B's first line search
+            dnorm = np.linalg.norm(Dir, axis=1)
+            step = np.where((count == 0) & (dnorm > 1.0), 1.0 / np.where(dnorm > 0, dnorm, 1.0), 1.0)
             Xn, Fn, Gn = X.copy(), F.copy(), G.copy()
             pending = active.copy()
             retried = np.zeros(B, dtype=bool)
             for _ in range(2 * self.max_backtracks):
-                T = np.clip(X + step[:, None] * Dir, self.lb, self.ub)
-                Ft, Gt = self._eval(x0, np.where(pending[:, None], T, X), gamma, last_u)
-                dec = np.einsum("bn,bn->b", G, T - X)
-                ok = pending & np.isfinite(Ft) & (Ft <= F + 1e-4 * dec) & (dec < 0)
-                Xn[ok], Fn[ok], Gn[ok] = T[ok], Ft[ok], Gt[ok]
+                # only the problems that still need a trial point are evaluated (converged problems and accepted
+                # steps cost nothing): the device batch shrinks as the line searches finish
+                idx = np.where(pending)[0]
+                T = np.clip(X[idx] + step[idx, None] * Dir[idx], self.lb, self.ub)
+                Ft, Gt = self._eval(x0[idx], T, gamma[idx], None if last_u is None else np.asarray(last_u)[idx])
+                dec = np.einsum("bn,bn->b", G[idx], T - X[idx])
+                good = np.isfinite(Ft) & (Ft <= F[idx] + 1e-4 * dec) & (dec < 0)
+                acc = idx[good]
+                Xn[acc], Fn[acc], Gn[acc] = T[good], Ft[good], Gt[good]
+                ok = np.zeros(B, dtype=bool); ok[acc] = True
                 pending &= ~ok
                 if not pending.any():
                     break

@@ -186,14 +186,17 @@ def test_batched_solver_matches_lbfgsb_on_box_constrained_quadratics():
     c = rng.normal(size=(B, n)) * 3
 
     def fake(x0, U, gamma, last_u=None, host_out=True, want_grad=True):
+        # the solver evaluates only the problems that still need a trial point: x0[:, 0] carries the problem id
+        ids = np.asarray(x0)[:, 0].astype(int)
         X = U.reshape(U.shape[0], -1)
-        QX = np.einsum("bij,bj->bi", Q, X)
-        f = 0.5 * np.einsum("bi,bi->b", X, QX) + np.einsum("bi,bi->b", c, X)
-        f[3] = np.where(np.abs(X[3]).max() > 0.9, np.nan, f[3])      # a NaN region must be treated as a rejected step
-        return f, (QX + c).reshape(U.shape)
+        QX = np.einsum("bij,bj->bi", Q[ids], X)
+        f = 0.5 * np.einsum("bi,bi->b", X, QX) + np.einsum("bi,bi->b", c[ids], X)
+        nan_region = (ids == 3) & (np.abs(X).max(axis=1) > 0.9)     # a NaN region must be treated as a rejected step
+        f = np.where(nan_region, np.nan, f)
+        return f, (QX + c[ids]).reshape(U.shape)
 
     sol = BatchedSolver(BatchedRollouts(evaluate_fn=fake), H, m, lb=[-1, -1], ub=[1, 1], max_iter=300, gtol=1e-8)
-    r = sol.solve(np.zeros((B, 3)), np.full(B, -1.0))
+    r = sol.solve(np.repeat(np.arange(B, dtype=np.float64)[:, None], 3, axis=1), np.full(B, -1.0))
     for b in range(B):
         if b == 3:
             assert np.isfinite(r["cost"][b]) and np.abs(r["U"][b]).max() <= 0.9 + 1e-12
