@@ -131,6 +131,17 @@ inline cudaError_t to_device(gpmpc_ctx *h, void *dst, const void *src, size_t by
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// cudaFuncSetAttribute is per device: `done` is a per-call-site table indexed by the current device
+constexpr int kMaxDevices = 64;
+inline bool first_use_on_device(bool (&done)[kMaxDevices]) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= kMaxDevices) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+}
+
 // ---- fit.cu -------------------------------------------------------------------------------
 int fit_all(gpmpc_ctx *h, const bool *which);           // (re)fit the outputs flagged in which[E]
 int derive_weights(gpmpc_ctx *h, int a);                // Wt[a] from Kinv[a], beta[a], lam_prop[a]

@@ -13,12 +13,11 @@ template <int D, int EG, bool GRAD>
 static cudaError_t launch_one(const PairArgs &a, dim3 grid, cudaStream_t st)
 {
     const size_t smem = pair_smem_bytes<D, EG>();
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {};
+    if (first_use_on_device(configured)) {
         cudaError_t e = cudaFuncSetAttribute(mm_pairs_batch<D, EG, GRAD>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     mm_pairs_batch<D, EG, GRAD><<<grid, PAIR_THREADS, smem, st>>>(a);
     return cudaGetLastError();
@@ -44,12 +43,11 @@ template <int D, int EG, bool GRAD>
 static cudaError_t launch_single_one(const SingleStepArgs &a, dim3 grid, cudaStream_t st)
 {
     const size_t smem = single_smem_bytes<D, EG>();
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {};
+    if (first_use_on_device(configured)) {
         cudaError_t e = cudaFuncSetAttribute(mm_step_single<D, EG, GRAD>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     // programmatic dependent launch: consecutive step kernels overlap this grid's prologue (barrier setup, first
     // TMA tile loads) with the previous grid's tail; the kernel orders itself with griddepcontrol.wait

@@ -556,11 +556,9 @@ static void launch_cost_adjoint(gpmpc_ctx *h, const CostArgs &ca, int B, int H)
         const size_t smem = ((size_t)2 * (H + 1) * ca.d.E + (size_t)H * (ca.d.m > 0 ? ca.d.m : 1) + 2 * H + 1 + 2 * ca.d.E +
                              (size_t)H * ca.d.E * 4 * ca.d.D) * sizeof(double);
         if (smem <= 160 * 1024) {
-            static bool configured = false;
-            if (!configured) {
+            static bool configured[kMaxDevices] = {};
+            if (first_use_on_device(configured))
                 cudaFuncSetAttribute(cost_adjoint_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-                configured = true;
-            }
             cost_adjoint_small_kernel<<<B, 128, smem, h->stream>>>(ca);
             return;
         }
@@ -729,12 +727,10 @@ static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int ctas, int P, lon
     if (h->time_pairs) cudaEventRecord(h->ev1, h->stream);
     if (!few) {
         dim3 fgrid((d.B + 31) / 32, d.E);
-        static bool fin_configured = false;
-        if (!fin_configured) {
+        static bool fin_configured[kMaxDevices] = {};
+        if (first_use_on_device(fin_configured))
             GP_CUDA(h, cudaFuncSetAttribute(finalize_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)finalize_smem_bytes(kMaxD)));
-            fin_configured = true;
-        }
         finalize_step_kernel<<<fgrid, 32 * FIN_WARPS, finalize_smem_bytes(d.D), h->stream>>>(d, t, P, h->part.as<double>(), h->mpart.as<double>(),
                                                                       us, h->hyp.as<double>(), mu, var, tape,
                                                                       want_grad ? 1 : 0);

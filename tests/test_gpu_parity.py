@@ -700,3 +700,25 @@ def test_config5_gamma_sweep_batched_solver_vs_scalar_solves(gp):
         assert sol["cost"][b] <= c + 1e-5 * max(1.0, abs(c)), (b, sol["cost"][b], c)
         assert abs(sol["cost"][b] - c) <= 1e-4 * max(1.0, abs(c)), (b, sol["cost"][b], c)
         assert np.max(np.abs(sol["U"][b] - u)) <= 2e-2
+
+
+def test_two_devices_in_one_process_agree(gp):
+    """One handle per device: the same problem on cuda:0 and cuda:1 (if present) gives bit-identical results."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    n, E, m, H = 300, 2, 1, 4
+    rng = np.random.default_rng(3)
+    S = rng.uniform(-1, 1, (n, E)); A = rng.uniform(-1, 1, (n, m))
+    nxt = 0.9 * S + 0.2 * np.tanh(np.concatenate([S, A], 1) @ rng.normal(0, 0.3, (E + m, E)))
+    X = np.concatenate([S, A], 1)
+    x0 = rng.uniform(-0.5, 0.5, (130, E)); U = rng.uniform(-0.3, 0.3, (130, H, m))
+    out = []
+    for dev in (0, 1):
+        from gpmpc_b200.backend import GPBundle
+        b = GPBundle(E + m, E, dev)
+        with torch.cuda.device(dev):
+            b.fit(X, nxt, np.full((E, E + m), 2.0), np.ones(E), np.full(E, float(np.float32(0.01))))
+            res = [b.cost_grad(x0[:k], U[:k], np.full(k, -1.0), 2 * np.eye(E), 0.01 * np.eye(m), host_out=True)[:2] for k in (1, 130)]
+        out.append(res)
+    for (c0, g0), (c1, g1) in zip(out[0], out[1]):
+        assert np.array_equal(c0, c1) and np.array_equal(g0, g1)
