@@ -53,7 +53,7 @@ static pair_launch_fn single_launcher(int D)
 // measured on B200 at n=4096 it costs 1.55 ms per rollout and evaluation, the batched kernel 174 ms per started
 // chunk of 128 rollouts, i.e. the crossover is at 112
 constexpr int kSingleMaxB = 112;
-constexpr int MEAN_JP = 16;          // partitions of the training set in the mean kernel
+constexpr int MEAN_JP = 64;          // partitions of the training set in the mean kernel (64 x rollout chunks CTAs)
 constexpr int MEAN_THREADS = 128;
 
 
@@ -179,7 +179,6 @@ __global__ void __launch_bounds__(MEAN_THREADS) mean_sums_kernel(const MeanArgs 
 //   tape[((t-1)*E + a) * (2+4D) + e][Bpad]:  e = 0 mean, 1 var, 2.. dm/du, dm/ds, dv/du, dv/ds
 // ---------------------------------------------------------------------------------------------
 constexpr int FIN_WARPS = 16;
-static_assert(MEAN_JP <= FIN_WARPS, "one warp per mean partition");
 __host__ __device__ inline size_t finalize_smem_bytes(int D) { return (size_t)FIN_WARPS * 2 * nacc(D) * 32 * sizeof(double); }
 __global__ void __launch_bounds__(32 * FIN_WARPS)
 finalize_step_kernel(StepDims d, int t, int P, const double *__restrict__ part,
@@ -209,7 +208,7 @@ finalize_step_kernel(StepDims d, int t, int P, const double *__restrict__ part,
                 s3 += src[(size_t)(p + 3 * FIN_WARPS) * stride];
             }
             for (; p < P; p += FIN_WARPS) s0 += src[(size_t)p * stride];
-            if (wid < MEAN_JP) sm = mpart[(((size_t)wid * d.E + a) * NA + e) * d.Bpad + b];
+            for (int q = wid; q < MEAN_JP; q += FIN_WARPS) sm += mpart[(((size_t)q * d.E + a) * NA + e) * d.Bpad + b];
         }
         red[((size_t)wid * 2 * NA + e) * 32 + lane] = (s0 + s1) + (s2 + s3);
         red[((size_t)wid * 2 * NA + NA + e) * 32 + lane] = sm;
