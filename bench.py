@@ -236,6 +236,7 @@ def run_ours(args):
     bundle.pair_kernel_timing()              # arms the timers
     step_device(); torch.cuda.synchronize()
     pair_ms, pair_evals = bundle.pair_kernel_timing()     # summed over the H launches of one evaluation
+    bundle.set_pair_timing(False)                          # armed timers synchronise after every horizon step
     fma_tflops, exp_gops = bundle.measure_fp64_peak()
     pairs = pair_evals / E                                 # (rollout, pair) evaluations, 4 outputs each
     achieved_tflops = pairs * OPS_PER_PAIR_GROUP4 * 2.0 / (pair_ms * 1e-3) / 1e12
@@ -302,6 +303,7 @@ def run_ours(args):
         x1 = torch.tensor(x0[None, :], device=dev); U1 = torch.tensor(U_all[:1], device=dev); g1 = torch.tensor([-1.0], device=dev, dtype=torch.float64)
         bundle.cost_grad(x1, U1, g1, Q, R, want_grad=True, host_out=False); torch.cuda.synchronize()
         single_ms, _ = bundle.pair_kernel_timing()
+        bundle.set_pair_timing(False)
         line["roofline_single"] = {
             "bound": "hbm", "kernel": "mm_step_single<5,4,grad> (B=1: one fused launch per horizon step)",
             "achieved": bytes_algo / (single_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",

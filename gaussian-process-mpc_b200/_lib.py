@@ -37,6 +37,7 @@ SIGNATURES = {
     "gpmpc_rollout_cost_grad": (c_int, [_P, c_int, c_int] + [_P] * 13),
     "gpmpc_launch_count": (c_longlong, [_P]),
     "gpmpc_last_pair_kernel_ms": (c_int, [_P, POINTER(c_double), POINTER(c_longlong)]),
+    "gpmpc_set_pair_timing": (c_int, [_P, c_int]),
     "gpmpc_measure_fp64_peak": (c_int, [_P, POINTER(c_double), POINTER(c_double)]),
 }
 

@@ -232,6 +232,10 @@ class GPBundle:
         check(self.h, self.lib.gpmpc_last_pair_kernel_ms(self.h, ctypes.byref(ms), ctypes.byref(ev)), "timing")
         return ms.value, ev.value
 
+    def set_pair_timing(self, on):
+        """Armed timers synchronise the stream after every horizon step: disarm them after a measurement."""
+        check(self.h, self.lib.gpmpc_set_pair_timing(self.h, int(bool(on))), "timing")
+
     def measure_fp64_peak(self):
         a = ctypes.c_double(0.0); b = ctypes.c_double(0.0)
         self._sync_stream()

@@ -96,6 +96,13 @@ extern "C" int gpmpc_last_pair_kernel_ms(gpmpc_handle h, double *ms, long long *
     return GPMPC_OK;
 }
 
+extern "C" int gpmpc_set_pair_timing(gpmpc_handle h, int on)
+{
+    if (!h) return GPMPC_ERR_INVALID;
+    h->time_pairs = on != 0;
+    return GPMPC_OK;
+}
+
 // fetch a small host-or-device array into host memory
 static int fetch_host(gpmpc_ctx *h, const double *src, double *dst, size_t cnt)
 {

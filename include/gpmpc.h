@@ -160,6 +160,9 @@ int gpmpc_rollout_cost_grad(gpmpc_handle h, int B, int H, const double *x0, cons
  * (ms, CUDA events on the handle's stream) of the last pair-sum kernel sequence.                      */
 long long gpmpc_launch_count(gpmpc_handle h);
 int gpmpc_last_pair_kernel_ms(gpmpc_handle h, double *ms, long long *pair_evals);
+/* The timers above synchronise the stream after every horizon step while armed (the first call of
+ * gpmpc_last_pair_kernel_ms arms them); gpmpc_set_pair_timing(h, 0) disarms them again.              */
+int gpmpc_set_pair_timing(gpmpc_handle h, int on);
 
 /* Measured ceilings for the roofline: sustained fp64 FMA rate (TFLOP/s, 2 flop per FMA) and the rate of
  * the library's own exp() (Gexp/s) on this device.                                                    */
