@@ -62,21 +62,34 @@ int gram_into(gpmpc_ctx *h, int a, double *dst, int ldd, bool add_noise)
 // ---------------------------------------------------------------------------------------------
 // Diagonal block: Cholesky of a 64x64 block and the inverse of its factor, one CTA, matrix in REGISTERS.
 // 256 threads form a 16x16 grid; thread (ty, tx) owns the 4x4 sub-block rows 4ty.., columns 4tx.. (threads above the
-// diagonal idle along).  Each of the 64 right-looking steps publishes one column (and, for the inverse, one row)
-// through a double-buffered 64-entry shared array: one barrier, 8 shared loads and 16 FMAs per thread and step.
-// (A shared-memory-resident version was bound by the shared-memory bandwidth of the one SM it runs on: 63 us.)
+// diagonal idle along).  Both sweeps advance FOUR columns / rows per barrier: the 64x4 panel is published through a
+// double-buffered shared array, every thread factorises the 4x4 diagonal tile redundantly (4 dependent rsqrt chains
+// instead of 64 barrier + rsqrt + publish round trips), solves its own rows against it and applies a rank-4 update
+// (64 FMAs) to its tile.  (History: shared-memory resident 63 us, registers with one column per barrier 46 us.)
 // Writes
 //   A    : L_kk in place (upper part of the block zeroed),
 //   Linv : L_kk^-1 dense row-major (the panel solve A[i,k] L_kk^-T is then a tensor-core GEMM),
 //   ZT   : (L_kk^-1)^T into the diagonal block of L^-T (leaf of the recursive triangular inverse).
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load4(const double *p, double (&v)[4])
+{
+    const double2 a = *reinterpret_cast<const double2 *>(p), b = *reinterpret_cast<const double2 *>(p + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void store4(double *p, const double (&v)[4])
+{
+    *reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]);
+    *reinterpret_cast<double2 *>(p + 2) = make_double2(v[2], v[3]);
+}
+
 __global__ void __launch_bounds__(256)
 potrf_diag_kernel(double *__restrict__ A, int ld, int k0, double *__restrict__ Linv, double *__restrict__ ZT,
                   int ldz, int *info)
 {
-    __shared__ __align__(32) double colb[2][NB];   // published column of the current step (double buffered)
-    __shared__ __align__(32) double rowb[2][NB];   // inverse: published row k of X
-    __shared__ double rinv[NB];            // 1 / L_cc
+    __shared__ __align__(32) double pan[2][NB * 4];     // published 64x4 panel (rows x 4 columns), double buffered
+    __shared__ __align__(32) double rowp[2][4 * NB];    // inverse: published 4 rows of X
+    __shared__ __align__(32) double diag[16][16];       // the 16 diagonal 4x4 tiles of L (for the inverse sweep)
+    __shared__ double rinv[NB];                         // 1 / L_cc
     __shared__ int bad;
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
@@ -97,50 +110,78 @@ potrf_diag_kernel(double *__restrict__ A, int ld, int k0, double *__restrict__ L
         }
     __syncthreads();
     POTRF_STAMP(1);
-    // ---- Cholesky, right-looking by columns ----
+    // ---- Cholesky, right-looking, four columns per step ----
 #pragma unroll 1
     for (int tc = 0; tc < 16; ++tc) {
+        double *buf = pan[tc & 1];
+        if (tx == tc) {
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            const int c = 4 * tc + cc;
-            double *col = colb[c & 1];
-            if (tx == tc) {
+            for (int i = 0; i < 4; ++i) store4(&buf[(4 * ty + i) * 4], a[i]);
+        }
+        __syncthreads();
+        // the 4x4 diagonal tile, factorised by every thread
+        double d[4][4], r[4], l[4][4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) col[4 * ty + i] = a[i][cc];
-            }
-            __syncthreads();
-            double d = col[c];
-            const bool ok = d > 0.0;
-            if (!ok) { d = 1.0; if (tid == 0 && !bad) bad = k0 + c + 1; }
-            const double rs = rsqrt(d);        // 1 / L_cc
-            // 4 consecutive doubles per thread as two 16-byte loads (stride-4 scalar loads are 4-way bank conflicts)
-            const double2 r01 = *reinterpret_cast<const double2 *>(&col[4 * ty]), r23 = *reinterpret_cast<const double2 *>(&col[4 * ty + 2]);
-            const double2 c01 = *reinterpret_cast<const double2 *>(&col[4 * tx]), c23 = *reinterpret_cast<const double2 *>(&col[4 * tx + 2]);
-            const double lr[4] = {r01.x * rs, r01.y * rs, r23.x * rs, r23.y * rs};
-            const double lc[4] = {c01.x * rs, c01.y * rs, c23.x * rs, c23.y * rs};
-            if (tx == tc) {                    // the owners keep the scaled column
+        for (int i = 0; i < 4; ++i) load4(&buf[(4 * tc + i) * 4], d[i]);
+        bool okall = true;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int r = 4 * ty + i;
-                    if (r > c) a[i][cc] = lr[i];
-                    else if (r == c) a[i][cc] = ok ? d * rs : 1.0;
-                }
-            }
-            if (tid == 0) rinv[c] = ok ? rs : 1.0;
-            // trailing update: a[r][j] -= L[r][c] L[j][c] for columns j > c (rows above the diagonal hold garbage that
-            // is never read)
-            if (tx >= tc) {
+        for (int p = 0; p < 4; ++p) {
+            double t = d[p][p];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+            for (int q = 0; q < p; ++q) t = fma(-l[p][q], l[p][q], t);
+            const bool ok = t > 0.0;
+            if (!ok) { t = 1.0; if (okall && tid == 0 && !bad) bad = k0 + 4 * tc + p + 1; okall = false; }
+            r[p] = rsqrt(t);
+            l[p][p] = ok ? t * r[p] : 1.0;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (4 * tx + j > c) a[i][j] = fma(-lr[i], lc[j], a[i][j]);
+            for (int i = p + 1; i < 4; ++i) {
+                double v = d[i][p];
+#pragma unroll
+                for (int q = 0; q < p; ++q) v = fma(-l[i][q], l[p][q], v);
+                l[i][p] = v * r[p];
             }
         }
+        if (tid == 0) {                        // (compile-time indices: r[] must stay in registers)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) rinv[4 * tc + p] = r[p];
+        }
+        // rows of the panel this thread needs: its own row block and (as the other factor of the update) its column block
+        double lr[4][4], lc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            double pr[4], pc[4];
+            load4(&buf[(4 * ty + i) * 4], pr);
+            load4(&buf[(4 * tx + i) * 4], pc);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {      // x L_kk^T = row  ->  forward substitution
+                double vr = pr[p], vc = pc[p];
+#pragma unroll
+                for (int q = 0; q < p; ++q) { vr = fma(-lr[i][q], l[p][q], vr); vc = fma(-lc[i][q], l[p][q], vc); }
+                lr[i][p] = vr * r[p];
+                lc[i][p] = vc * r[p];
+            }
+        }
+        if (tx == tc) {                        // the owners keep the finished panel (rows above the diagonal: garbage, never read)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int p = 0; p < 4; ++p) a[i][p] = lr[i][p];
+        } else if (tx > tc && ty >= tx) {      // rank-4 update of the lower tiles to the right of the panel
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) a[i][j] = fma(-lr[i][p], lc[j][p], a[i][j]);
+        }
+    }
+    if (ty == tx) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) store4(&diag[ty][4 * i], a[i]);
     }
     __syncthreads();
     POTRF_STAMP(2);
-    // ---- X = L^-1, right-looking by rows: once row k of X is final it is pushed into the sums of the rows below ----
+    // ---- X = L^-1, right-looking, four rows per step: X[kb] = L_kk^-1 (I - sums), then pushed into the rows below ----
     double x[4][4];                            // running sums, then X
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -148,49 +189,70 @@ potrf_diag_kernel(double *__restrict__ A, int ld, int k0, double *__restrict__ L
         for (int j = 0; j < 4; ++j) x[i][j] = 0.0;
 #pragma unroll 1
     for (int tk = 0; tk < 16; ++tk) {
+        double *rows = rowp[tk & 1], *cols = pan[tk & 1];
+        if (ty == tk) {                        // owners of the row block: finalise and publish it
+            double lk[4][4], rk[4];
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-            const int k = 4 * tk + kk;
-            double *row = rowb[k & 1], *col = colb[k & 1];
-            if (ty == tk) {                    // owners of row k: finalise and publish it
-                const double rk = rinv[k];
+            for (int i = 0; i < 4; ++i) { load4(&diag[tk][4 * i], lk[i]); rk[i] = rinv[4 * tk + i]; }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int c = 4 * tx + j;
-                    const double v = c <= k ? ((c == k ? 1.0 : 0.0) - x[kk][j]) * rk : 0.0;
-                    x[kk][j] = v;
-                    row[c] = v;
+            for (int j = 0; j < 4; ++j) {
+                double v[4];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    double t = ((tx == tk && p == j) ? 1.0 : 0.0) - x[p][j];
+#pragma unroll
+                    for (int q = 0; q < p; ++q) t = fma(-lk[p][q], v[q], t);
+                    v[p] = t * rk[p];
                 }
+#pragma unroll
+                for (int p = 0; p < 4; ++p) x[p][j] = tx <= tk ? v[p] : 0.0;
             }
-            if (tx == tk) {                    // owners of column k of L publish it
 #pragma unroll
-                for (int i = 0; i < 4; ++i) col[4 * ty + i] = a[i][kk];
-            }
-            __syncthreads();
-            if (ty >= tk) {
-                const double2 l01 = *reinterpret_cast<const double2 *>(&col[4 * ty]), l23 = *reinterpret_cast<const double2 *>(&col[4 * ty + 2]);
-                const double2 x01 = *reinterpret_cast<const double2 *>(&row[4 * tx]), x23 = *reinterpret_cast<const double2 *>(&row[4 * tx + 2]);
-                const double li[4] = {l01.x, l01.y, l23.x, l23.y};
-                const double xj[4] = {x01.x, x01.y, x23.x, x23.y};
+            for (int p = 0; p < 4; ++p) store4(&rows[p * NB + 4 * tx], x[p]);
+        }
+        if (tx == tk) {                        // owners of the column block of L publish it
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i) store4(&cols[(4 * ty + i) * 4], a[i]);
+        }
+        __syncthreads();
+        if (ty > tk && tx <= tk) {
+            double xr[4][4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (4 * ty + i > k) x[i][j] = fma(li[i], xj[j], x[i][j]);
+            for (int p = 0; p < 4; ++p) load4(&rows[p * NB + 4 * tx], xr[p]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                double li[4];
+                load4(&cols[(4 * ty + i) * 4], li);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) x[i][j] = fma(li[p], xr[p][j], x[i][j]);
             }
         }
     }
     POTRF_STAMP(3);
+    // write-out through shared memory so that every global store is a coalesced row segment
+    __shared__ double stage[NB][NB + 1];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int pass = 0; pass < 2; ++pass) {
+        __syncthreads();
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int r = 4 * ty + i, c = 4 * tx + j;
-            const bool low = c <= r;
-            A[(size_t)(k0 + r) * ld + k0 + c] = low ? a[i][j] : 0.0;          // upper part of the block is zero
-            Linv[r * NB + c] = low ? x[i][j] : 0.0;
-            ZT[(size_t)(k0 + c) * ldz + k0 + r] = low ? x[i][j] : 0.0;        // transposed
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int r = 4 * ty + i, c = 4 * tx + j;
+                stage[r][c] = (c <= r) ? (pass == 0 ? a[i][j] : x[i][j]) : 0.0;      // upper part of the block is zero
+            }
+        __syncthreads();
+        for (int e = tid; e < NB * NB; e += 256) {
+            const int r = e / NB, c = e % NB;
+            if (pass == 0) A[(size_t)(k0 + r) * ld + k0 + c] = stage[r][c];
+            else {
+                Linv[e] = stage[r][c];
+                ZT[(size_t)(k0 + r) * ldz + k0 + c] = stage[c][r];                   // transposed
+            }
         }
+    }
     if (tid == 0 && bad) atomicCAS(info, 0, bad);
 #ifdef GPMPC_POTRF_TIMING
     POTRF_STAMP(4);
