@@ -65,3 +65,17 @@ if "5" in which:      # gamma sweep x 512 initial states as lock-step MPC solves
     t0 = time.perf_counter(); sol = solver.solve(starts[I.reshape(-1)], G.reshape(-1)); t = time.perf_counter() - t0
     print(f"config 5: {G.size} MPC instances (4 gammas x 128 initial states) solved in lock step: {t:.1f} s, {sol['iters']} iterations, "
           f"{sol['evals']} batched evaluations, {int(sol['converged'].sum())} converged to gtol 1e-4 -> {G.size/t:.1f} solves/s")
+
+if "n" in which:      # the "next" rows: incremental refit (N2) and hyper-parameter training steps (N3), n=4096
+    dyn, rng, tf = dynamics(4096, 4, 1, ard=True)
+    t0 = time.perf_counter(); dyn._fit_all(); dyn._bundle.synchronize(); t_full = time.perf_counter() - t0
+    ts = []
+    for _ in range(5):
+        s = rng.uniform(-1, 1, 4); a = rng.uniform(-1, 1, 1)
+        t0 = time.perf_counter(); dyn.append_train_data(s, a, 0.9 * s); dyn._bundle.synchronize(); ts.append(time.perf_counter() - t0)
+    print(f"N2: full refit of 4 outputs (distinct hyper-parameters) at n=4096: {1e3*t_full:.1f} ms; one appended observation "
+          f"(bordered update of Ky^-1, beta, Wt for 4 outputs): {1e3*np.median(ts):.2f} ms")
+    g = dyn.gpr_err[0]
+    t0 = time.perf_counter(); g.update_hyperparams(num_iters=10, verbose=False); dyn._bundle.synchronize(); t = time.perf_counter() - t0
+    print(f"N3: 10 Adam steps on the log marginal likelihood of one output at n={g.num_train} (likelihood + analytic gradient + "
+          f"refit per step): {1e3*t/10:.1f} ms per step")
