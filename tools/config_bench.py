@@ -79,3 +79,27 @@ if "n" in which:      # the "next" rows: incremental refit (N2) and hyper-parame
     t0 = time.perf_counter(); g.update_hyperparams(num_iters=10, verbose=False); dyn._bundle.synchronize(); t = time.perf_counter() - t0
     print(f"N3: 10 Adam steps on the log marginal likelihood of one output at n={g.num_train} (likelihood + analytic gradient + "
           f"refit per step): {1e3*t/10:.1f} ms per step")
+
+if "1" in which:      # the reference's own experiment (src/experiments/pretrain_uncertainty.py): n=400, E=2, m=2, H=6, gamma=-1
+    g = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "shipped.npz"))
+    mpc = gp.RiskSensitiveMPC(-1, 6, 2, 2, 2 * np.identity(2), np.zeros((2, 2)), None)
+    for i in range(2):
+        mpc.dynamics.gpr_err[i].set_sigma_n(np.float64(g["ship_sn"][i]))
+        mpc.dynamics.gpr_err[i].set_lambdas(np.asarray(g["ship_lam"][i], dtype=np.float64))
+        mpc.dynamics.gpr_err[i].set_sigma_f(np.float64(g["ship_sf"][i]))
+    t0 = time.perf_counter(); mpc.dynamics.append_train_data(g["ship_S"], g["ship_A"], g["ship_next"]); mpc.dynamics._bundle.synchronize()
+    tf = time.perf_counter() - t0
+    mpc.set_xref(np.array([0., 0.])); mpc.set_uref(np.array([0., 0.])); mpc.set_lb([-1.0, -1.0]); mpc.set_ub([1.0, 1.0])
+    mpc.curr_state = torch.tensor(g["ship_x0"], device="cuda")
+    x = g["ship_U0"].reshape(-1).copy()
+    for _ in range(3): mpc.objective(x); mpc.gradient(x)
+    ts = []
+    for i in range(50):
+        xi = x + 1e-4 * i
+        t0 = time.perf_counter(); c = mpc.objective(xi); gr = mpc.gradient(xi); ts.append(time.perf_counter() - t0)
+    st = []
+    for i in range(5):
+        n0 = mpc.n_evals; t0 = time.perf_counter(); mpc.get_optimal_trajectory(g["ship_x0"]); st.append((time.perf_counter() - t0, mpc.n_evals - n0))
+    print(f"config 1 (shipped data, n=400, H=6): fit {1e3*tf:.1f} ms (first call), objective+gradient {1e3*np.median(ts):.3f} ms "
+          f"(reference on CPU: 150 + 30 ms, SURVEY appendix C); one solve p50 {1e3*np.median([t for t, _ in st]):.1f} ms "
+          f"({[k for _, k in st]} evaluations, L-BFGS-B fallback)")
