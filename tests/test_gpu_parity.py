@@ -722,3 +722,52 @@ def test_two_devices_in_one_process_agree(gp):
         out.append(res)
     for (c0, g0), (c1, g1) in zip(out[0], out[1]):
         assert np.array_equal(c0, c1) and np.array_equal(g0, g1)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_randomized_shapes_vs_c_oracle(gp, seed):
+    """Seeded sweep over ragged shapes and hyper-parameter patterns (shared / per-output ARD lambdas, i.e. one or
+    several lambda groups; general Q, R, R_delta; gamma of either sign) through both kernels, against the C oracle."""
+    from oracle import oracle as orc
+    rng = np.random.default_rng(1000 + seed)
+    E = int(rng.integers(1, 6)); m = int(rng.integers(1, 3))
+    D = E + m
+    n = int(rng.integers(5, 400)); H = int(rng.integers(1, 6))
+    S = rng.uniform(-1, 1, (n, E)); A = rng.uniform(-1, 1, (n, m))
+    nxt = 0.9 * S + 0.2 * np.tanh(np.concatenate([S, A], 1) @ rng.normal(0, 0.3, (D, E)))
+    X = np.concatenate([S, A], 1)
+    pattern = seed % 3                      # 0: all outputs share lambda, 1: all distinct, 2: two groups
+    lam = np.empty((E, D)); sf = np.empty(E); sn = np.empty(E)
+    base = [rng.uniform(1.0, 3.0, D), rng.uniform(1.0, 3.0, D)]
+    for a in range(E):
+        lam[a] = base[0] if pattern == 0 else (rng.uniform(1.0, 3.0, D) if pattern == 1 else base[a % 2])
+        sf[a] = 1.0 if pattern == 0 else rng.uniform(0.8, 1.3)
+        sn[a] = rng.uniform(0.08, 0.2)
+    dyn = gp.Dynamics(E, m)
+    for a in range(E):
+        dyn.gpr_err[a].set_lambdas(lam[a].astype(np.float64)); dyn.gpr_err[a].set_sigma_f(np.float64(sf[a]))
+        dyn.gpr_err[a].set_sigma_n(np.float64(sn[a]))
+    dyn.append_train_data(S, A, nxt)
+    lam_e = np.stack([dyn.gpr_err[a].get_lambdas() for a in range(E)]).astype(np.float64)      # effective (rounded) values
+    sf_e = np.array([dyn.gpr_err[a].get_sigma_f() for a in range(E)], dtype=np.float64)
+    sn_e = np.array([dyn.gpr_err[a].get_sigma_n() for a in range(E)], dtype=np.float64)
+    fits = [orc.fit(X, nxt[:, a], lam_e[a], sf_e[a], float(np.float32(sn_e[a] ** 2)) ** 0.5) for a in range(E)]
+    Qm = rng.normal(size=(E, E)) * 0.3; Q = Qm @ Qm.T + 1.5 * np.eye(E)
+    Rm = rng.normal(size=(m, m)) * 0.1; R = Rm @ Rm.T + 0.05 * np.eye(m)
+    Rd = (0.3 * np.eye(m) + 0.05) if seed % 2 else None
+    xref = rng.uniform(-0.2, 0.2, E); uref = rng.uniform(-0.1, 0.1, m)
+    gamma = float(rng.choice([-1.0, -0.5, 0.7]))
+    br = gp.BatchedRollouts(dyn, Q, R, R_delta=Rd, x_ref=xref, u_ref=uref)
+    for B in (int(rng.integers(1, 8)), int(rng.integers(112, 200))):
+        x0 = rng.uniform(-0.5, 0.5, (B, E)); U = rng.uniform(-0.3, 0.3, (B, H, m))
+        lu = rng.uniform(-0.3, 0.3, (B, m)) if Rd is not None else None
+        cost, grad = br.cost_and_grad(x0, U, gamma, last_u=lu, host_out=True)
+        for b in {0, B // 2, B - 1}:
+            c, gr, _, _ = orc.c_rollout_cost_grad(X, [f["Ky_inv"] for f in fits], [f["beta"] for f in fits], lam_e, sf_e,
+                                                  x0[b], U[b], gamma, Q, R, R_delta=Rd,
+                                                  last_u=None if lu is None else lu[b], x_ref=xref, u_ref=uref)
+            if np.isnan(c):
+                assert np.isnan(cost[b])
+                continue
+            close(cost[b], c, RTOL)
+            norm_close(grad[b], gr, RTOL)
