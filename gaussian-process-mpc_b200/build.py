@@ -18,7 +18,7 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libgpmpc.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"] + os.environ.get("GPMPC_EXTRA_NVCC_FLAGS", "").split()
 PAIR_DIMS = range(2, 9)
 
 

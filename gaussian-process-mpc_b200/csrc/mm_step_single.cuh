@@ -22,11 +22,22 @@
 
 namespace gpmpc {
 
-constexpr int SINGLE_THREADS = 128;    // 2 CTAs per SM
+// Build-time geometry (defaults = shipped): threads per CTA, CTAs per SM, ring slots per CTA.
+#ifndef GPMPC_SINGLE_THREADS
+#define GPMPC_SINGLE_THREADS 128
+#endif
+#ifndef GPMPC_SINGLE_CTAS
+#define GPMPC_SINGLE_CTAS 2
+#endif
+#ifndef GPMPC_SINGLE_STAGES
+#define GPMPC_SINGLE_STAGES 3
+#endif
+constexpr int SINGLE_THREADS = GPMPC_SINGLE_THREADS;
+constexpr int SINGLE_CTAS_PER_SM = GPMPC_SINGLE_CTAS;
 constexpr int SINGLE_WARPS = SINGLE_THREADS / 32;
-constexpr int SINGLE_ROWS = PT / SINGLE_WARPS;       // rows of a tile handled by one thread (8)
+constexpr int SINGLE_ROWS = PT / SINGLE_WARPS;       // rows of a tile handled by one thread
 constexpr int SINGLE_GROUP = 16;       // CTAs per first-level reduction group
-constexpr int SINGLE_STAGES = 3;       // ring slots per CTA: 2-3 tiles in flight (x2 CTAs per SM = ~200 KB per SM)
+constexpr int SINGLE_STAGES = GPMPC_SINGLE_STAGES;   // ring slots per CTA: STAGES-1 tiles in flight
 
 static_assert(kGroupMax <= SINGLE_WARPS, "the finalize maps one warp to each output of the group");
 
@@ -74,7 +85,7 @@ __device__ __forceinline__ void mbar_arrive(void *bar)
 }
 
 template <int D, int EG, bool GRAD>
-__global__ void __launch_bounds__(SINGLE_THREADS, 2)
+__global__ void __launch_bounds__(SINGLE_THREADS, SINGLE_CTAS_PER_SM)
 mm_step_single(const SingleStepArgs a)
 {
     constexpr int NA = 1 + 2 * D;
