@@ -152,7 +152,7 @@ def run_ours(args):
     S, A, nxt, rng = synth(n, E, m, 0)
     dyn = gp.Dynamics(E, m)
     for a in range(E):
-        dyn.gpr_err[a].set_lambdas(np.full(D, 2.0)); dyn.gpr_err[a].set_sigma_n(np.float64(0.1))
+        dyn.gpr_err[a].set_lambdas(np.full(D, 2.0 + (0.1 * a if args.ard else 0.0))); dyn.gpr_err[a].set_sigma_n(np.float64(0.1))
     t0 = time.perf_counter()
     dyn.append_train_data(S, A, nxt)
     dyn._bundle.synchronize()
@@ -265,7 +265,8 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"config3: n={n} E=4 m=1 H={H} gamma=-1, B={B} multi-start control sequences",
+        "config": {"workload": f"config3: n={n} E=4 m=1 H={H} gamma=-1, B={B} multi-start control sequences"
+                               + (" (distinct lambdas per output)" if args.ard else ""),
                    "n": n, "H": H, "B": B, "sharding": f"rollouts/{world}", "l2": "per-step Wt working set "
                    f"{E * n * n * 8 / 2 / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2)", "fit_s": t_fit},
         "clocks": clocks,
@@ -363,6 +364,7 @@ def main():
     ap.add_argument("--B", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--ard", action="store_true", help="distinct length-scales per output (not the headline workload)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
