@@ -24,7 +24,7 @@
 namespace gpmpc {
 
 // Build-time tuning knobs (defaults = the shipped configuration; tools/pair_bench.cu overrides them).
-// Chosen from a 40-variant sweep on B200 (profiles/r01_pair_kernel_tuning.md): the kernel is limited by the
+// Chosen from the variant sweeps on B200 (profiles/r01_pair_kernel_tuning.md): the kernel is limited by the
 // register-file bandwidth of three-source DFMAs (2.76 cycles each unless an operand is reused, vs 2.0), so all
 // reasonable schedules land within a few percent; the defaults are the best robust combination.
 #ifndef GPMPC_EXP_VARIANT

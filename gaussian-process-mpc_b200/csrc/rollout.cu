@@ -590,7 +590,7 @@ static void pair_geometry(gpmpc_ctx *h, int B, long long total_tiles, int &ctas_
 {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-    if (B < kSingleMaxB) {                       // mm_pairs_single: two CTAs per SM and rollout, static tile ranges
+    if (B < kSingleMaxB) {                       // mm_step_single: SINGLE_CTAS_PER_SM CTAs per SM and rollout, static tile ranges
         long long c = (long long)SINGLE_CTAS_PER_SM * sms;
         if (c > total_tiles) c = total_tiles;
         ctas_per_chunk = (int)c;
