@@ -771,3 +771,32 @@ def test_randomized_shapes_vs_c_oracle(gp, seed):
                 continue
             close(cost[b], c, RTOL)
             norm_close(grad[b], gr, RTOL)
+
+
+def test_closed_loop_incremental_vs_full_refit(gp):
+    """The Simulator pattern (src/simulator.py:46-56): solve, apply the first action to the plant, append the observed
+    transition, repeat.  With the bordered O(n^2) update (`Dynamics.incremental`) the closed loop must follow the same
+    trajectory as with the reference's full rebuild on every step."""
+    E, m, H, n0, steps = 2, 1, 4, 120, 8
+    rng = np.random.default_rng(21)
+    Wm = rng.normal(0, 0.3, (E + m, E))
+    plant = lambda s, a: 0.9 * s + 0.2 * np.tanh(np.concatenate([s, a]) @ Wm)      # noqa: E731
+    S = rng.uniform(-1, 1, (n0, E)); A = rng.uniform(-1, 1, (n0, m))
+    nxt = np.stack([plant(S[i], A[i]) for i in range(n0)])
+    trajs = []
+    for incremental in (True, False):
+        mpc = gp.RiskSensitiveMPC(-1.0, H, E, m, 2 * np.eye(E), 0.01 * np.eye(m))
+        mpc.dynamics.incremental = incremental
+        for a in range(E):
+            mpc.dynamics.gpr_err[a].set_lambdas(np.full(E + m, 2.0)); mpc.dynamics.gpr_err[a].set_sigma_n(np.float64(0.1))
+        mpc.dynamics.append_train_data(S, A, nxt)
+        mpc.set_lb([-1.0]); mpc.set_ub([1.0])
+        s = np.array([0.5, -0.4]); traj = [s.copy()]
+        for _ in range(steps):
+            u = mpc.get_optimal_trajectory(s)[0]
+            s_next = plant(s, u)
+            mpc.dynamics.append_train_data(s, u, s_next)
+            s = s_next; traj.append(s.copy())
+        assert mpc.dynamics.gpr_err[0].num_train == n0 + steps
+        trajs.append(np.array(traj))
+    assert np.max(np.abs(trajs[0] - trajs[1])) <= 1e-6, np.max(np.abs(trajs[0] - trajs[1]))
