@@ -217,8 +217,8 @@ def test_rollout_cost_gradient_vs_reference(gp, name):
 
 
 def test_shipped_experiment_config1(gp):
-    """BASELINE config 1 inputs (shipped data, n=400, sigma_n=1e-5, cond(Ky) ~ 2.6e6): values, gradient, NaN mask.
-    With this conditioning LU-inverse vs Cholesky-inverse differences are amplified, hence 1e-5."""
+    """BASELINE config 1 inputs (shipped data, n=400, sigma_n=1e-5, cond(Ky) ~ 2.6e6): values, gradient, NaN mask at the
+    stated 1e-6 bar (measured on B200: cost 6e-9, gradient 2e-8 of its max, despite LU-inverse vs Cholesky-inverse)."""
     g = golden("shipped")
     H = 6
     mpc = gp.RiskSensitiveMPC(-1, H, 2, 2, 2 * np.identity(2), np.zeros((2, 2)), None)
@@ -242,8 +242,8 @@ def test_shipped_experiment_config1(gp):
         ref = float(g[f"ship_cost{i}"])
         assert np.isnan(c) == np.isnan(ref)
         if not np.isnan(ref):
-            close(c, ref, 1e-5)
-            norm_close(np.asarray(mpc.gradient(U.reshape(-1).copy())), g[f"ship_grad{i}"], 1e-5)
+            close(c, ref, RTOL)
+            norm_close(np.asarray(mpc.gradient(U.reshape(-1).copy())), g[f"ship_grad{i}"], RTOL)
 
 
 def test_cost_known_answers(gp):
