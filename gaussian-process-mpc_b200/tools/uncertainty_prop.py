@@ -83,3 +83,37 @@ def covariance_prop_torch(lambdas1, lambdas2, u, S, X_train, mean1, mean2, beta1
                                           _scalar(mean2), _ptr(b1), _ptr(b2), _scalar(sigma_f1), _scalar(sigma_f2),
                                           int(bool(bugcompat)), _ptr(cov)), "gpmpc_covariance_raw")
     return cov[0]
+
+
+# ---- NumPy-interface twins (reference `src/tools/uncertainty_prop.py:6-44,91-136,187-236`) -------------------------
+# The reference's versions are O(n^2) Python loops kept as test oracles (sigma_f = 1, they take the evidence matrix
+# K = Ky rather than its inverse).  Same signatures and return types here, evaluated by the same device kernels as
+# the torch functions above.  (The Monte-Carlo checkers `*_mc` are not provided: they are test utilities.)
+def _inv_dev(K, dev):
+    return torch.linalg.inv(torch.as_tensor(np.asarray(K, dtype=np.float64), device=dev))
+
+
+def mean_prop(K, Lambda, u, S, X_train, y_train):
+    """Mean of the GP output for x ~ N(u, S); returns (float, {'beta': ndarray, 'l': ndarray})."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    mean, params = mean_prop_torch(_inv_dev(K, dev), np.diag(np.asarray(Lambda, dtype=np.float64)).copy(), u, S, X_train,
+                                   y_train, 1.0)
+    return float(mean.item()), {'beta': params['beta'].cpu().numpy(), 'l': params['l'].cpu().numpy()}
+
+
+def variance_prop(K, Lambda, u, S, X_train, y_train):
+    """Variance of the GP output (sigma_f = 1): 1 - tr((K^-1 - beta beta^T) L) - mean^2."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    Kinv = _inv_dev(K, dev)
+    lam = np.diag(np.asarray(Lambda, dtype=np.float64)).copy()
+    mean, params = mean_prop_torch(Kinv, lam, u, S, X_train, y_train, 1.0)
+    return float(variance_prop_torch(Kinv, lam, u, S, X_train, mean, params['beta'], 1.0).item())
+
+
+def covariance_prop(K1, K2, Lambda1, Lambda2, u, S, X_train, y_train):
+    """Covariance of two GP outputs that share the targets y_train (as the reference's signature has it)."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    lam1 = np.diag(np.asarray(Lambda1, dtype=np.float64)).copy(); lam2 = np.diag(np.asarray(Lambda2, dtype=np.float64)).copy()
+    m1, p1 = mean_prop_torch(_inv_dev(K1, dev), lam1, u, S, X_train, y_train, 1.0)
+    m2, p2 = mean_prop_torch(_inv_dev(K2, dev), lam2, u, S, X_train, y_train, 1.0)
+    return float(covariance_prop_torch(lam1, lam2, u, S, X_train, m1, m2, p1['beta'], p2['beta'], 1.0, 1.0).item())

@@ -800,3 +800,29 @@ def test_closed_loop_incremental_vs_full_refit(gp):
         assert mpc.dynamics.gpr_err[0].num_train == n0 + steps
         trajs.append(np.array(traj))
     assert np.max(np.abs(trajs[0] - trajs[1])) <= 1e-6, np.max(np.abs(trajs[0] - trajs[1]))
+
+
+def test_numpy_interface_moment_matching_twins(gp):
+    """mean_prop / variance_prop / covariance_prop with the reference's NumPy signatures (they take K, not K^-1, and a
+    diagonal matrix Lambda) against the NumPy oracle, with ARD length-scales and a full input covariance."""
+    from oracle import oracle as orc
+    from gpmpc_b200.tools.uncertainty_prop import mean_prop, variance_prop, covariance_prop
+    rng = np.random.default_rng(8)
+    n, D = 120, 3
+    X = rng.normal(size=(n, D)); y = np.sum(X ** 2, axis=1) + rng.normal(0, 0.5, n)
+    lam1 = np.array([1.0, 2.0, 0.5]); lam2 = np.array([2.0, 0.7, 1.5])
+    u = rng.normal(size=D) * 0.3
+    Am = rng.normal(size=(D, D)) * 0.2; S = Am @ Am.T + 0.02 * np.eye(D)
+    f1 = orc.fit(X, y, lam1, 1.0, 0.3); f2 = orc.fit(X, y, lam2, 1.0, 0.3)
+    K1 = np.linalg.inv(f1["Ky_inv"]); K2 = np.linalg.inv(f2["Ky_inv"])
+    m, params = mean_prop(K1, np.diag(lam1), u, S, X, y)
+    mo, beta, _ = orc.mean_prop(f1["Ky_inv"], lam1, u, S, X, y, 1.0)
+    close(m, mo, 1e-8)
+    norm_close(params["beta"], beta, 1e-8)
+    v = variance_prop(K1, np.diag(lam1), u, S, X, y)
+    vo = orc.variance_prop(f1["Ky_inv"], lam1, u, S, X, mo, beta, 1.0)
+    assert abs(v - vo) <= RTOL * max(abs(vo), 1e-3)
+    c = covariance_prop(K1, K2, np.diag(lam1), np.diag(lam2), u, S, X, y)
+    m2, beta2, _ = orc.mean_prop(f2["Ky_inv"], lam2, u, S, X, y, 1.0)
+    co = orc.covariance_prop(lam1, lam2, u, S, X, mo, m2, beta, beta2)
+    assert abs(c - co) <= RTOL * max(abs(co), 1e-3)
