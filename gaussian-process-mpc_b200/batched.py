@@ -114,12 +114,14 @@ class BatchedSolver:
         self.ub = np.full(n, np.inf) if ub is None else np.tile(np.asarray(ub, dtype=np.float64), self.H)
         self.memory, self.max_iter, self.gtol, self.ftol = memory, max_iter, gtol, ftol
         self.max_backtracks = max_backtracks
-        self.n_evals = 0
+        self.n_evals = 0              # batched device evaluations
+        self.n_rollout_evals = 0      # rollouts evaluated in total (sum of the batch sizes)
 
     def _eval(self, x0, X, gamma, last_u):
         B = X.shape[0]
         cost, grad = self.rollouts.cost_and_grad(x0, X.reshape(B, self.H, self.m), gamma, last_u, host_out=True)
         self.n_evals += 1
+        self.n_rollout_evals += B
         return np.asarray(cost, dtype=np.float64), np.asarray(grad, dtype=np.float64).reshape(B, -1)
 
     def _direction(self, G, S, Y, rho, count):
@@ -225,4 +227,4 @@ class BatchedSolver:
             converged |= active & small & ~stalled
             active &= ~(stalled | small)
         return {"U": X.reshape(B, self.H, self.m), "cost": F, "iters": it, "evals": self.n_evals,
-                "converged": converged}
+                "rollout_evals": self.n_rollout_evals, "converged": converged}

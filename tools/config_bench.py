@@ -64,7 +64,8 @@ if "5" in which:      # gamma sweep x 512 initial states as lock-step MPC solves
     solver = gp.BatchedSolver(br, 30, 1, lb=[-1.0], ub=[1.0], max_iter=40, gtol=1e-4)
     t0 = time.perf_counter(); sol = solver.solve(starts[I.reshape(-1)], G.reshape(-1)); t = time.perf_counter() - t0
     print(f"config 5: {G.size} MPC instances (4 gammas x 128 initial states) solved in lock step: {t:.1f} s, {sol['iters']} iterations, "
-          f"{sol['evals']} batched evaluations, {int(sol['converged'].sum())} converged to gtol 1e-4 -> {G.size/t:.1f} solves/s")
+          f"{sol['evals']} batched evaluations ({sol['rollout_evals'] / G.size:.1f} rollout evaluations per instance), "
+          f"{int(sol['converged'].sum())} converged to gtol 1e-4 -> {G.size/t:.1f} solves/s")
 
 if "n" in which:      # the "next" rows: incremental refit (N2) and hyper-parameter training steps (N3), n=4096
     dyn, rng, tf = dynamics(4096, 4, 1, ard=True)
