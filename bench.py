@@ -82,7 +82,7 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(float(r[2]) for r in self.rows), "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_reference_sample(n, E, m, H_full, H_sample, seed, threads):
+def cpu_reference_sample(n, E, m, H_full, H_sample, seed, threads, device="cpu"):
     """Time the reference algorithm (torch port) on a bounded sample: full n, H_sample horizon steps, one
     control sequence; cost is linear in H, so evals/s = 1 / (t * H_full / H_sample)."""
     import torch
@@ -92,7 +92,7 @@ def cpu_reference_sample(n, E, m, H_full, H_sample, seed, threads):
     X = np.concatenate([S, A], 1)
     t0 = time.perf_counter()
     prob = RefPortProblem(X, nxt, np.full((E, E + m), 2.0), np.ones(E), np.full(E, 0.1), -1.0, 2 * np.eye(E),
-                          0.01 * np.eye(m))
+                          0.01 * np.eye(m), device=device)
     t_fit = time.perf_counter() - t0
     x0 = rng.uniform(-0.5, 0.5, E); U = rng.uniform(-0.3, 0.3, (H_sample, m))
 
@@ -329,6 +329,22 @@ def run_ours(args):
             "value": 1.0 / (t * H), "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"oracle/ref_port.py (reference op sequence, torch CPU fp64): objective+gradient of ONE control "
                       f"sequence at n={n}, H=1 ({t:.2f} s), extrapolated linearly to H={H}"}
+        try:
+            # context only: the same operation sequence in eager torch fp64 on THIS GPU (the reference picks cuda:0 when
+            # it is available, src/gpr.py:22), one control sequence, H=1 at full n, extrapolated like the CPU figure
+            del one
+            torch.cuda.empty_cache()
+            _, one_gpu, _ = cpu_reference_sample(n, E, m, H, 1, 0, threads, device=f"cuda:{local}")
+            one_gpu(); torch.cuda.synchronize()
+            tg = min(one_gpu(), one_gpu())
+            line["reference_ops_on_this_gpu"] = {
+                "value": 1.0 / (tg * H), "unit": UNIT, "kind": "port",
+                "sample": f"oracle/ref_port.py with device=cuda (eager torch fp64, explicit inverse, n^3 mm + trace, autograd): "
+                          f"one control sequence at n={n}, H=1 ({tg:.3f} s), extrapolated linearly to H={H}"}
+            del one_gpu
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            line["reference_ops_on_this_gpu"] = {"error": repr(ex)}
         try:
             from oracle import oracle as orc
             orc.c_set_threads(threads)

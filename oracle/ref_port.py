@@ -100,28 +100,34 @@ class RefPortProblem:
     reference's cyipopt callbacks do (`src/mpc.py:202-255`)."""
 
     def __init__(self, X, Y, lambdas, sigma_fs, sigma_ns, gamma, Q, R, R_delta=None, last_u=None,
-                 x_ref=None, u_ref=None):
-        self.X = torch.as_tensor(np.asarray(X)).type(F64)
-        self.Y = torch.as_tensor(np.asarray(Y)).type(F64)
-        self.E = self.Y.shape[1]
-        self.lambdas = [torch.as_tensor(np.asarray(lambdas[a])).type(F64) for a in range(self.E)]
-        self.sigma_fs = [float(s) for s in sigma_fs]
-        self.Ky_invs = [build_inverse(self.X, self.lambdas[a], float(sigma_fs[a]), float(sigma_ns[a]))[2]
-                        for a in range(self.E)]
-        self.gamma = float(gamma)
-        self.Q = torch.as_tensor(np.asarray(Q)).type(F64)
-        self.R = torch.as_tensor(np.asarray(R)).type(F64)
-        self.Rd = None if R_delta is None else torch.as_tensor(np.asarray(R_delta)).type(F64)
-        m = self.R.shape[0]
-        self.last_u = torch.zeros(m).type(F64) if last_u is None else torch.as_tensor(np.asarray(last_u)).type(F64)
-        self.x_ref = torch.zeros(self.E).type(F64) if x_ref is None else torch.as_tensor(np.asarray(x_ref)).type(F64)
-        self.u_ref = torch.zeros(m).type(F64) if u_ref is None else torch.as_tensor(np.asarray(u_ref)).type(F64)
+                 x_ref=None, u_ref=None, device="cpu"):
+        # device="cuda" runs the same eager torch operation sequence on the GPU: what a user of the reference gets on
+        # a GPU box (the reference picks cuda:0 when available, `src/gpr.py:22`); used for context by bench.py only
+        self.device = torch.device(device)
+        t = lambda a: torch.as_tensor(np.asarray(a)).type(F64).to(self.device)      # noqa: E731
+        with torch.device(self.device):
+            self.X = t(X)
+            self.Y = t(Y)
+            self.E = self.Y.shape[1]
+            self.lambdas = [t(lambdas[a]) for a in range(self.E)]
+            self.sigma_fs = [float(s) for s in sigma_fs]
+            self.Ky_invs = [build_inverse(self.X, self.lambdas[a], float(sigma_fs[a]), float(sigma_ns[a]))[2]
+                            for a in range(self.E)]
+            self.gamma = float(gamma)
+            self.Q = t(Q)
+            self.R = t(R)
+            self.Rd = None if R_delta is None else t(R_delta)
+            m = self.R.shape[0]
+            self.last_u = torch.zeros(m).type(F64) if last_u is None else t(last_u)
+            self.x_ref = torch.zeros(self.E).type(F64) if x_ref is None else t(x_ref)
+            self.u_ref = torch.zeros(m).type(F64) if u_ref is None else t(u_ref)
 
     def cost_and_grad(self, x0, U):
-        x0 = torch.as_tensor(np.asarray(x0)).type(F64)
-        U = torch.as_tensor(np.asarray(U)).type(F64).clone().requires_grad_(True)
-        means, covs = propagate(self.X, self.Ky_invs, self.Y, self.lambdas, self.sigma_fs, x0, U)
-        c = risk_cost(means, U, covs, self.x_ref, self.u_ref, self.gamma, self.Q, self.R, self.Rd, self.last_u)
-        c.backward()
-        return c.item(), U.grad.numpy().copy(), torch.stack(means).detach().numpy(), \
-            torch.stack([torch.diag(s) for s in covs]).detach().numpy()
+        with torch.device(self.device):
+            x0 = torch.as_tensor(np.asarray(x0)).type(F64).to(self.device)
+            U = torch.as_tensor(np.asarray(U)).type(F64).to(self.device).clone().requires_grad_(True)
+            means, covs = propagate(self.X, self.Ky_invs, self.Y, self.lambdas, self.sigma_fs, x0, U)
+            c = risk_cost(means, U, covs, self.x_ref, self.u_ref, self.gamma, self.Q, self.R, self.Rd, self.last_u)
+            c.backward()
+            return c.item(), U.grad.cpu().numpy().copy(), torch.stack(means).detach().cpu().numpy(), \
+                torch.stack([torch.diag(s) for s in covs]).detach().cpu().numpy()
