@@ -250,7 +250,7 @@ def run_ours(args):
     roofline = {
         "bound": "fp64_pipe", "kernel": "mm_pairs_batch<5,4,grad>", "achieved": achieved_tflops, "peak": fma_tflops,
         "unit": "TFLOP/s", "frac": achieved_tflops / fma_tflops if fma_tflops else None,
-        "traffic": 460.4e6,       # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/r01b_*)
+        "traffic": 457.3e6,       # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/r01d_*)
         "note": "FP64-pipe instructions (x2 flop) per launch / CUDA-event duration of the pair kernel; peak = DFMA rate "
                 "measured live by gpmpc_measure_fp64_peak (MEASURED_PEAKS.json has no fp64 figure); this kernel is "
                 "neither HBM- nor tensor-bound (see DESIGN.md)",
@@ -275,8 +275,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "roofline": roofline,
     }
-    if rank == 0 and world == 1 and not args.no_latency:
-      try:
+    def single_solve_section():
         # single-sequence latency (the cyipopt callback pattern, B = 1) and the p50 of one NLP solve on the same GP
         mpc = gp.RiskSensitiveMPC(-1.0, H, E, m, Q, R)
         mpc.dynamics = dyn
@@ -312,15 +311,13 @@ def run_ours(args):
             "ms_per_launch": single_ms / H,
             "note": "algorithmic bytes = H*E*n(n+1)/2*8 (Wt upper triangle once per step) / CUDA-event time of the H "
                     "launches of one B=1 evaluation (events on the library stream, programmatic dependent launch off "
-                    "between timed launches); traffic = dram__bytes_read+write per launch from profiles/r01c_*"}
+                    "between timed launches); traffic = dram__bytes_read+write per launch from profiles/r01d_*"}
         line["single_solve"] = {"objective_plus_gradient_ms": 1e3 * float(np.median(lat)),
                                 "solve_p50_ms": 1e3 * float(np.median([t for t, _ in solves])),
                                 "evals_per_solve": [k for _, k in solves], "solver": solver,
-                                "note": "B=1 path (lanes<->pairs kernels), wall clock incl. host<->device copies"}
-      except Exception as ex:                             # secondary numbers must never cost the headline line
-        line["single_solve"] = {"error": repr(ex)}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-      try:
+                                "note": "B=1 path (one fused launch per horizon step), wall clock incl. host<->device copies"}
+
+    def cpu_baseline_section():
         threads = os.cpu_count() or 1
         _, one, tf = cpu_reference_sample(n, E, m, H, 1, 0, threads)
         one()
@@ -361,8 +358,18 @@ def run_ours(args):
                                                        f"scaled by (n/{sub})^2 * H/2"}
         except Exception as ex:                             # the C oracle is optional here
             line["cpu_baseline_c_oracle"] = {"error": str(ex)}
-      except Exception as ex:
-        line["cpu_baseline"] = {"error": repr(ex)}
+
+    # secondary numbers must never cost the headline line
+    if rank == 0 and world == 1 and not args.no_latency:
+        try:
+            single_solve_section()
+        except Exception as ex:
+            line["single_solve"] = {"error": repr(ex)}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu_baseline_section()
+        except Exception as ex:
+            line["cpu_baseline"] = {"error": repr(ex)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
