@@ -826,3 +826,26 @@ def test_numpy_interface_moment_matching_twins(gp):
     m2, beta2, _ = orc.mean_prop(f2["Ky_inv"], lam2, u, S, X, y, 1.0)
     co = orc.covariance_prop(lam1, lam2, u, S, X, mo, m2, beta, beta2)
     assert abs(c - co) <= RTOL * max(abs(co), 1e-3)
+
+
+def test_kernel_switch_boundary_and_long_horizon(gp):
+    """B = 111 runs the few-rollouts kernel, B = 112 the batched one: the shared rollouts must agree across the switch;
+    a long horizon (H = 64, tape and adjoint buffers beyond the usual sizes) against the C oracle."""
+    from oracle import oracle as orc
+    n, E, m, H = 200, 3, 1, 64
+    dyn, S, A, nxt, rng = _synth_dynamics(gp, n, E, m, seed=77)
+    Q = 2 * np.eye(E); R = 0.01 * np.eye(m)
+    br = gp.BatchedRollouts(dyn, Q, R)
+    x0 = rng.uniform(-0.5, 0.5, (112, E)); U = rng.uniform(-0.3, 0.3, (112, H, m))
+    c111, g111 = br.cost_and_grad(x0[:111], U[:111], -1.0, host_out=True)
+    c112, g112 = br.cost_and_grad(x0, U, -1.0, host_out=True)
+    close(c111, c112[:111], 1e-9)
+    norm_close(g111, g112[:111], 1e-8)
+    X = np.concatenate([S, A], 1)
+    lam = np.full((E, E + m), 2.0)
+    fits = [orc.fit(X, nxt[:, a], lam[a], 1.0, float(np.float32(0.1 ** 2)) ** 0.5) for a in range(E)]
+    for b in (0, 111):
+        c, gr, _, _ = orc.c_rollout_cost_grad(X, [f["Ky_inv"] for f in fits], [f["beta"] for f in fits], lam, np.ones(E),
+                                              x0[b], U[b], -1.0, Q, R)
+        close(c112[b], c, RTOL)
+        norm_close(g112[b], gr, RTOL)
