@@ -14,10 +14,25 @@ static cudaError_t launch_one(const PairArgs &a, dim3 grid, cudaStream_t st)
 {
     const size_t smem = pair_smem_bytes<D, EG>();
     static bool configured[kMaxDevices] = {};
+    static int resident[kMaxDevices] = {};       // CTAs of this variant that fit on the whole device (one wave)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= kMaxDevices) dev = 0;
     if (first_use_on_device(configured)) {
         cudaError_t e = cudaFuncSetAttribute(mm_pairs_batch<D, EG, GRAD>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        int occ = 0, sms = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mm_pairs_batch<D, EG, GRAD>, PAIR_THREADS, smem);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        resident[dev] = occ * sms;
+    }
+    // Work items are drawn from ticket counters, so any number of CTAs produces the same (bit-identical) result: the
+    // variants with few outputs or without the gradient moments need fewer registers and run more CTAs per SM than
+    // the 2 the caller assumed.
+    if (resident[dev] > 0) {
+        const int per_chunk = resident[dev] / a.chunks;
+        if (per_chunk * a.chunks > (int)grid.x) grid.x = per_chunk * a.chunks;
     }
     mm_pairs_batch<D, EG, GRAD><<<grid, PAIR_THREADS, smem, st>>>(a);
     return cudaGetLastError();
