@@ -334,7 +334,12 @@ mm_pairs_batch(const PairArgs a)
             const double *xj = xi + PT * D;
 
             if (warp_active) {
-#if GPMPC_PIPELINE
+            // Variants with 3-4 outputs per launch are limited by the FP64 issue rate and use the hand-rotated loop with a
+            // 2-row micro-tile; with 1-2 outputs the exp chain is most of the work and there are registers to spare, so a
+            // 4-row micro-tile with four independent chains per column (compiler scheduled) is 14 % faster.
+            constexpr bool USE_PIPE = GPMPC_PIPELINE && EG >= 3;
+            constexpr int RIX = USE_PIPE ? RI : (EG >= 3 ? RI : 4);
+            if constexpr (USE_PIPE) {
             // One pair = chain (q, q^2, S, exp: a ~15-deep dependency chain) + sums (4 + 44 independent FMAs).
             // ptxas does not software-pipeline loops, so the loop is rotated by hand: the chain of pair p+1 and the
             // sums of pair p sit in the same basic block and overlap.  Pairs are visited (j, r)-major; the chain
@@ -356,10 +361,10 @@ mm_pairs_batch(const PairArgs a)
                 return exp_neg(S, tab);
             };
 #pragma unroll 1
-            for (int r0 = 0; r0 < PT; r0 += RI) {
-                double zi[RI][D], zj[D];
+            for (int r0 = 0; r0 < PT; r0 += RIX) {
+                double zi[RIX][D], zj[D];
 #pragma unroll
-                for (int r = 0; r < RI; ++r)
+                for (int r = 0; r < RIX; ++r)
 #pragma unroll
                     for (int k = 0; k < D; ++k) zi[r][k] = fma(-GP_C(k), xi[(r0 + r) * D + k], GP_CU(k));
 #pragma unroll
@@ -369,9 +374,9 @@ mm_pairs_batch(const PairArgs a)
 #pragma unroll 1
                 for (int j = 0; j < PTJ; ++j) {
 #pragma unroll
-                    for (int r = 0; r < RI; ++r) {
+                    for (int r = 0; r < RIX; ++r) {
                         double qn[D], qqn[D], en;
-                        if (r + 1 < RI) {
+                        if (r + 1 < RIX) {
                             en = chain(zi[r + 1], zj, qn, qqn);
                         } else {
                             const int jn = min(j + 1, PTJ - 1);
@@ -397,12 +402,12 @@ mm_pairs_batch(const PairArgs a)
                     }
                 }
             }
-#else
+            } else {
 #pragma unroll 1
-            for (int r0 = 0; r0 < PT; r0 += RI) {
-                double zi[RI][D];
+            for (int r0 = 0; r0 < PT; r0 += RIX) {
+                double zi[RIX][D];
 #pragma unroll
-                for (int r = 0; r < RI; ++r)
+                for (int r = 0; r < RIX; ++r)
 #pragma unroll
                     for (int k = 0; k < D; ++k) zi[r][k] = fma(-GP_C(k), xi[(r0 + r) * D + k], GP_CU(k));
 #pragma unroll 1
@@ -411,7 +416,7 @@ mm_pairs_batch(const PairArgs a)
 #pragma unroll
                     for (int k = 0; k < D; ++k) zj[k] = fma(-GP_C(k), xj[j * D + k], GP_CU(k));
 #pragma unroll
-                    for (int r = 0; r < RI; ++r) {
+                    for (int r = 0; r < RIX; ++r) {
                         double q[D], qq[D];
 #pragma unroll
                         for (int k = 0; k < D; ++k) { q[k] = zi[r][k] + zj[k]; qq[k] = q[k] * q[k]; }
@@ -479,7 +484,7 @@ mm_pairs_batch(const PairArgs a)
                     }
                 }
             }
-#endif
+            }
             }
             __syncthreads();
             stage ^= 1; I = In; J = Jn;
