@@ -334,11 +334,12 @@ mm_pairs_batch(const PairArgs a)
             const double *xj = xi + PT * D;
 
             if (warp_active) {
-            // Variants with 3-4 outputs per launch are limited by the FP64 issue rate and use the hand-rotated loop with a
-            // 2-row micro-tile; with 1-2 outputs the exp chain is most of the work and there are registers to spare, so a
-            // 4-row micro-tile with four independent chains per column (compiler scheduled) is 14 % faster.
-            constexpr bool USE_PIPE = GPMPC_PIPELINE && EG >= 3;
-            constexpr int RIX = USE_PIPE ? RI : (EG >= 3 ? RI : 4);
+            // The gradient variants with 3-4 outputs per launch are limited by the FP64 issue rate and use the hand-rotated
+            // loop with a 2-row micro-tile; with 1-2 outputs, or without the gradient moments, the exp chain is most of
+            // the work and there are registers to spare, so a 4-row micro-tile with four independent chains per column
+            // (compiler scheduled) is 14-23 % faster.
+            constexpr bool USE_PIPE = GPMPC_PIPELINE && EG >= 3 && GRAD;
+            constexpr int RIX = USE_PIPE ? RI : 4;
             if constexpr (USE_PIPE) {
             // One pair = chain (q, q^2, S, exp: a ~15-deep dependency chain) + sums (4 + 44 independent FMAs).
             // ptxas does not software-pipeline loops, so the loop is rotated by hand: the chain of pair p+1 and the
