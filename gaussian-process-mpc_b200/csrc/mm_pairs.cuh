@@ -43,8 +43,8 @@ namespace gpmpc {
 #define GPMPC_ACC_ORDER 0        // accumulation loop nest: 0 output-major, 1 dimension-major, 2 e-scaled features
 #endif
 #ifndef GPMPC_PIPELINE
-#define GPMPC_PIPELINE 1         // 1: software-pipelined pair loop (exp chain of pair p+1 overlaps the sums of pair p)
-#endif
+#define GPMPC_PIPELINE 0         // 1: hand-rotated pair loop with a 2-row micro-tile for the 3-4-output gradient variants
+#endif                           //    (46.4 ms, run-to-run 45.9-47.5); 0: 4-row micro-tile everywhere (45.15 ms, stable)
 #ifndef GPMPC_MINBLOCKS
 #define GPMPC_MINBLOCKS 2        // CTAs per SM promised to ptxas
 #endif
