@@ -250,7 +250,7 @@ def run_ours(args):
     roofline = {
         "bound": "fp64_pipe", "kernel": "mm_pairs_batch<5,4,grad>", "achieved": achieved_tflops, "peak": fma_tflops,
         "unit": "TFLOP/s", "frac": achieved_tflops / fma_tflops if fma_tflops else None,
-        "traffic": 457.3e6,       # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/r01d_*)
+        "traffic": 460.8e6,       # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/r01e_*)
         "note": "FP64-pipe instructions (x2 flop) per launch / CUDA-event duration of the pair kernel; peak = DFMA rate "
                 "measured live by gpmpc_measure_fp64_peak (MEASURED_PEAKS.json has no fp64 figure); this kernel is "
                 "neither HBM- nor tensor-bound (see DESIGN.md)",
