@@ -25,13 +25,13 @@ namespace gpmpc {
 
 // Build-time tuning knobs (defaults = the shipped configuration; tools/pair_bench.cu overrides them).
 // Chosen from the variant sweeps on B200 (profiles/r01_pair_kernel_tuning.md): the kernel is limited by the
-// register-file bandwidth of three-source DFMAs (2.76 cycles each unless an operand is reused, vs 2.0), so all
-// reasonable schedules land within a few percent; the defaults are the best robust combination.
+// register-file bandwidth of three-source DFMAs (2.76 cycles each unless an operand is reused, vs 2.0), so most
+// schedules land within a few percent; the defaults are the best robust combination.
 #ifndef GPMPC_EXP_VARIANT
 #define GPMPC_EXP_VARIANT 3      // 0: Horner deg 11, 1: Estrin deg 11, 2: 16-entry table + deg 6, 3: 2 + integer clamp
 #endif
 #ifndef GPMPC_RI
-#define GPMPC_RI 2               // rows of the register micro-tile
+#define GPMPC_RI 2               // rows of the register micro-tile of the hand-rotated loop (GPMPC_PIPELINE=1); else 4
 #endif
 #ifndef GPMPC_CST_SMEM
 #define GPMPC_CST_SMEM 1         // 1: keep the per-rollout constants c, c*u in shared memory instead of registers
