@@ -204,3 +204,24 @@ def test_batched_solver_matches_lbfgsb_on_box_constrained_quadratics():
         ref = minimize(lambda x: (0.5 * x @ Q[b] @ x + c[b] @ x, Q[b] @ x + c[b]), np.zeros(n), jac=True, method="L-BFGS-B",
                        bounds=[(-1, 1)] * n, options={"gtol": 1e-10, "ftol": 1e-15})
         assert r["converged"][b] and abs(r["cost"][b] - ref.fun) < 1e-8 and np.max(np.abs(r["U"][b].ravel() - ref.x)) < 1e-4
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours) must print ONE JSON line with the
+    contract's keys; run here on a tiny instance."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--n", "96", "--H", "2"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["metric"] == "gp_mpc_rollout_cost_grad_evals_per_sec" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
