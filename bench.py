@@ -82,9 +82,53 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(float(r[2]) for r in self.rows), "reasons": reasons, "samples": len(self.rows)}
 
 
+def workload_config(n, H, B, world, E=4, ard=False):
+    """`config` of the JSON line -- identical for the `ours` and the `reference` arm."""
+    return {"workload": f"config3: n={n} E=4 m=1 H={H} gamma=-1, B={B} multi-start control sequences"
+                        + (" (distinct lambdas per output)" if ard else ""),
+            "n": n, "H": H, "B": B, "sharding": f"rollouts/{world}",
+            "l2": f"per-step Wt working set {E * n * n * 8 / 2 / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2)"}
+
+
+def reference_available():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import make_ref
+        return make_ref.available()
+    finally:
+        sys.path.pop(0)
+
+
+def run_ref_runner(device, n, Hs, steps, warmup, timeout=1500):
+    """The unmodified reference (oracle/_ref) in a subprocess: objective+gradient of one control sequence at the
+    full n for each horizon in Hs.  Returns the runner's dict."""
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_runner.py"), "--device", device, "--n", str(n),
+           "--H", ",".join(str(h) for h in Hs), "--steps", str(steps), "--warmup", str(warmup)]
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    if r.returncode != 0:
+        raise RuntimeError("ref_runner failed: " + r.stderr[-2000:])
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def extrapolate_reference(res, H_full):
+    """t(H) measured at H=1 and H=2 -> t(H_full) by the measured per-step increment (the cost is linear in H:
+    every horizon step runs the same E x (mean_prop + variance_prop) and keeps its own autograd state)."""
+    t1 = float(np.mean(res["runs"]["1"]["times_s"]))
+    out = {"t_H1_s": t1}
+    if "2" in res["runs"]:
+        t2 = float(np.mean(res["runs"]["2"]["times_s"]))
+        out.update({"t_H2_s": t2, "t_H2_over_t_H1": t2 / t1, "t_full_s": t1 + (H_full - 1) * (t2 - t1)})
+    else:
+        out["t_full_s"] = t1 * H_full
+    return out
+
+
 def cpu_reference_sample(n, E, m, H_full, H_sample, seed, threads, device="cpu"):
-    """Time the reference algorithm (torch port) on a bounded sample: full n, H_sample horizon steps, one
-    control sequence; cost is linear in H, so evals/s = 1 / (t * H_full / H_sample)."""
+    """Fallback when oracle/_ref is absent: the torch port of the reference's op sequence (oracle/ref_port.py) on a
+    bounded sample: full n, H_sample horizon steps, one control sequence."""
     import torch
     from oracle.ref_port import RefPortProblem
     torch.set_num_threads(threads)
@@ -104,28 +148,43 @@ def cpu_reference_sample(n, E, m, H_full, H_sample, seed, threads, device="cpu")
 
 
 def run_reference(args):
+    """The reference arm: the reference's OWN modules (oracle/_ref, staged from /root/reference by
+    oracle/make_ref.py) on the box's host cores.  One step = objective + gradient of one control sequence at the
+    full n for H=1; the same is timed for H=2 and the H=30 evaluation is extrapolated with the measured per-step
+    increment.  Falls back to the torch port (kind "port") only if oracle/_ref was not staged."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n, E, m, H = args.n, 4, 1, args.H
     threads = os.cpu_count() or 1
-    Hs = 1
-    _, one, t_fit = cpu_reference_sample(n, E, m, H, Hs, 0, threads)
-    for _ in range(args.warmup):
-        one()
-    ts = [one() for _ in range(args.steps)]
-    t = float(np.mean(ts))
-    value = 1.0 / (t * H / Hs)
+    if reference_available():
+        res = run_ref_runner("cpu", n, [1, 2], args.steps, args.warmup)
+        # the H=2 leg repeats the step count of the H=1 leg: both are bounded samples of the same workload
+        ex = extrapolate_reference(res, H)
+        kind, t, t_full = "reference", ex["t_H1_s"], ex["t_full_s"]
+        sample = (f"unmodified reference (oracle/_ref: src/mpc.py objective+gradient, torch CPU fp64, {res['cores']} threads): "
+                  f"ONE control sequence at full n={n}; measured H=1 {ex['t_H1_s']:.2f} s and H=2 {ex.get('t_H2_s', float('nan')):.2f} s "
+                  f"(ratio {ex.get('t_H2_over_t_H1', float('nan')):.2f}), H={H} extrapolated with the measured per-step increment "
+                  f"to {t_full:.1f} s; fit ({res['fit_s']:.1f} s) excluded")
+        extra = {"linearity": ex, "cores": res["cores"]}
+        threads = res["cores"]
+    else:
+        _, one, t_fit = cpu_reference_sample(n, E, m, H, 1, 0, threads)
+        for _ in range(args.warmup):
+            one()
+        t = float(np.mean([one() for _ in range(args.steps)]))
+        t_full = t * H
+        kind = "port"
+        sample = (f"oracle/_ref not staged: torch-CPU port of the reference op sequence (oracle/ref_port.py), ONE control "
+                  f"sequence at full n={n}, H=1, extrapolated linearly to H={H}; fit ({t_fit:.1f} s) excluded")
+        extra = {}
+    value = 1.0 / t_full
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"config3: n={n} E=4 m=1 H={H} gamma=-1 multi-start rollouts", "n": n, "H": H,
-                   "B": args.B},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"torch-CPU port of the reference op sequence (oracle/ref_port.py): objective+autograd "
-                                   f"gradient of ONE control sequence at full n={n} for H={Hs} horizon step(s), "
-                                   f"extrapolated linearly to H={H}; fit ({t_fit:.1f} s) excluded"},
+        "config": workload_config(n, H, args.B, args.gpus),
+        "cpu_baseline": dict({"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample}, **extra),
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -265,10 +324,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"config3: n={n} E=4 m=1 H={H} gamma=-1, B={B} multi-start control sequences"
-                               + (" (distinct lambdas per output)" if args.ard else ""),
-                   "n": n, "H": H, "B": B, "sharding": f"rollouts/{world}", "l2": "per-step Wt working set "
-                   f"{E * n * n * 8 / 2 / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2)", "fit_s": t_fit},
+        "config": workload_config(n, H, B, world, E, args.ard), "fit_s_cold": t_fit,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(B * (E + H * m + 1) * 8), "d2h_bytes_per_step": int(B * (1 + H * m) * 8)},
@@ -319,29 +375,34 @@ def run_ours(args):
 
     def cpu_baseline_section():
         threads = os.cpu_count() or 1
-        _, one, tf = cpu_reference_sample(n, E, m, H, 1, 0, threads)
-        one()
-        t = min(one(), one())
-        line["cpu_baseline"] = {
-            "value": 1.0 / (t * H), "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"oracle/ref_port.py (reference op sequence, torch CPU fp64): objective+gradient of ONE control "
-                      f"sequence at n={n}, H=1 ({t:.2f} s), extrapolated linearly to H={H}"}
-        try:
-            # context only: the same operation sequence in eager torch fp64 on THIS GPU (the reference picks cuda:0 when
-            # it is available, src/gpr.py:22), one control sequence, H=1 at full n, extrapolated like the CPU figure
-            del one
-            torch.cuda.empty_cache()
-            _, one_gpu, _ = cpu_reference_sample(n, E, m, H, 1, 0, threads, device=f"cuda:{local}")
-            one_gpu(); torch.cuda.synchronize()
-            tg = min(one_gpu(), one_gpu())
-            line["reference_ops_on_this_gpu"] = {
-                "value": 1.0 / (tg * H), "unit": UNIT, "kind": "port",
-                "sample": f"oracle/ref_port.py with device=cuda (eager torch fp64, explicit inverse, n^3 mm + trace, autograd): "
-                          f"one control sequence at n={n}, H=1 ({tg:.3f} s), extrapolated linearly to H={H}"}
-            del one_gpu
-            torch.cuda.empty_cache()
-        except Exception as ex:
-            line["reference_ops_on_this_gpu"] = {"error": repr(ex)}
+        if reference_available():
+            # the unmodified reference (oracle/_ref) on the host cores, bounded sample: H=1 and H=2 at the full n
+            res = run_ref_runner("cpu", n, [1, 2], 2, 1)
+            ex = extrapolate_reference(res, H)
+            line["cpu_baseline"] = {
+                "value": 1.0 / ex["t_full_s"], "unit": UNIT, "cores": res["cores"], "kind": "reference", "linearity": ex,
+                "sample": f"unmodified reference (oracle/_ref, src/mpc.py objective+gradient, torch CPU fp64): ONE control "
+                          f"sequence at n={n}; H=1 {ex['t_H1_s']:.2f} s, H=2 {ex['t_H2_s']:.2f} s, H={H} extrapolated with the "
+                          f"measured per-step increment to {ex['t_full_s']:.1f} s"}
+            try:
+                # context only: the same unmodified reference on THIS GPU (it picks cuda:0 when it sees one, src/gpr.py:22)
+                resg = run_ref_runner("cuda", n, [1, 2], 2, 1)
+                exg = extrapolate_reference(resg, H)
+                line["reference_on_this_gpu"] = {
+                    "value": 1.0 / exg["t_full_s"], "unit": UNIT, "kind": "reference", "linearity": exg,
+                    "sample": f"unmodified reference (oracle/_ref) with its own device choice cuda:0 (eager torch fp64, explicit "
+                              f"inverse, n^3 mm + trace, autograd): one control sequence at n={n}; H=1 {exg['t_H1_s']:.3f} s, "
+                              f"H=2 {exg['t_H2_s']:.3f} s, extrapolated to H={H}"}
+            except Exception as ex2:
+                line["reference_on_this_gpu"] = {"error": repr(ex2)[-500:]}
+        else:
+            _, one, tf = cpu_reference_sample(n, E, m, H, 1, 0, threads)
+            one()
+            t = min(one(), one())
+            line["cpu_baseline"] = {
+                "value": 1.0 / (t * H), "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": f"oracle/_ref not staged; oracle/ref_port.py (reference op sequence, torch CPU fp64): objective+gradient "
+                          f"of ONE control sequence at n={n}, H=1 ({t:.2f} s), extrapolated linearly to H={H}"}
         try:
             from oracle import oracle as orc
             orc.c_set_threads(threads)

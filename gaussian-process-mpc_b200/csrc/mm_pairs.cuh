@@ -31,7 +31,7 @@ namespace gpmpc {
 #define GPMPC_EXP_VARIANT 3      // 0: Horner deg 11, 1: Estrin deg 11, 2: 16-entry table + deg 6, 3: 2 + integer clamp
 #endif
 #ifndef GPMPC_RI
-#define GPMPC_RI 2               // rows of the register micro-tile of the hand-rotated loop (GPMPC_PIPELINE=1); else 4
+#define GPMPC_RI 4               // rows of the register micro-tile: four independent q -> exp chains per column
 #endif
 #ifndef GPMPC_CST_SMEM
 #define GPMPC_CST_SMEM 1         // 1: keep the per-rollout constants c, c*u in shared memory instead of registers
@@ -39,12 +39,6 @@ namespace gpmpc {
 #ifndef GPMPC_DYNAMIC
 #define GPMPC_DYNAMIC 1          // 1: CTAs draw work items from a ticket counter; 0: item = CTA index
 #endif
-#ifndef GPMPC_ACC_ORDER
-#define GPMPC_ACC_ORDER 0        // accumulation loop nest: 0 output-major, 1 dimension-major, 2 e-scaled features
-#endif
-#ifndef GPMPC_PIPELINE
-#define GPMPC_PIPELINE 0         // 1: hand-rotated pair loop with a 2-row micro-tile for the 3-4-output gradient variants
-#endif                           //    (46.4 ms, run-to-run 45.9-47.5); 0: 4-row micro-tile everywhere (45.15 ms, stable)
 #ifndef GPMPC_MINBLOCKS
 #define GPMPC_MINBLOCKS 2        // CTAs per SM promised to ptxas
 #endif
@@ -221,10 +215,19 @@ __host__ __device__ constexpr size_t pair_smem_bytes()
     return (2 * pair_stage_doubles<D, EG>() + 16 + (GPMPC_CST_SMEM ? 2 * D * 128 : 0)) * sizeof(double);
 }
 
-template <int D, int EG, bool GRAD>
+// Which moments a launch accumulates (the adjoint never reads the others, so they are not computed):
+//   GRAD = 0  T only (forward values);
+//   GRAD = 1  T, N1_k for every input dimension, N2_k for the NS state dimensions k < NS only: d/ds of an ACTION
+//             dimension is never used, the action variance is the constant fp32(1e-3) (src/dynamics.py:162);
+//   GRAD = 2  first horizon step when d/dx0 is not requested: the state part of the input (x0, 1e-3 I) is a
+//             constant, so only N1_k of the action dimensions k >= NS is needed.
+// NS = D accumulates everything (the general moment-matching entry points).
+template <int D, int EG, int GRAD, int NS>
 __global__ void __launch_bounds__(PAIR_THREADS, GPMPC_MINBLOCKS)
 mm_pairs_batch(const PairArgs a)
 {
+    constexpr int K1 = GRAD == 2 ? NS : 0;       // N1_k for k in [K1, D)
+    constexpr int K2 = GRAD == 1 ? NS : 0;       // N2_k for k in [0, K2)
     extern __shared__ __align__(128) double smem[];
     constexpr size_t STAGE = pair_stage_doubles<D, EG>();
     const int tid = threadIdx.x;
@@ -334,81 +337,13 @@ mm_pairs_batch(const PairArgs a)
             const double *xj = xi + PT * D;
 
             if (warp_active) {
-            // The gradient variants with 3-4 outputs per launch are limited by the FP64 issue rate and use the hand-rotated
-            // loop with a 2-row micro-tile; with 1-2 outputs, or without the gradient moments, the exp chain is most of
-            // the work and there are registers to spare, so a 4-row micro-tile with four independent chains per column
-            // (compiler scheduled) is 14-23 % faster.
-            constexpr bool USE_PIPE = GPMPC_PIPELINE && EG >= 3 && GRAD;
-            constexpr int RIX = USE_PIPE ? RI : 4;
-            if constexpr (USE_PIPE) {
-            // One pair = chain (q, q^2, S, exp: a ~15-deep dependency chain) + sums (4 + 44 independent FMAs).
-            // ptxas does not software-pipeline loops, so the loop is rotated by hand: the chain of pair p+1 and the
-            // sums of pair p sit in the same basic block and overlap.  Pairs are visited (j, r)-major; the chain
-            // issued after the last pair of a strip is a dummy (clamped column) whose result is dropped.
-            auto chain = [&](const double (&za)[D], const double (&zb)[D], double (&q)[D], double (&qq)[D]) {
-#pragma unroll
-                for (int k = 0; k < D; ++k) { q[k] = za[k] + zb[k]; qq[k] = q[k] * q[k]; }
-                double S = qq[0];
-                if (D >= 4) {
-                    double S2 = qq[2] + qq[3];
-                    S += qq[1];
-#pragma unroll
-                    for (int k = 4; k < D; k += 2) { S += qq[k]; if (k + 1 < D) S2 += qq[k + 1]; }
-                    S += S2;
-                } else {
-#pragma unroll
-                    for (int k = 1; k < D; ++k) S += qq[k];
-                }
-                return exp_neg(S, tab);
-            };
+            // RI-row register micro-tile per column: RI independent q -> q^2 -> sum -> exp chains (15 deep each) and
+            // RI x EG x (1 + moments) independent accumulation FMAs per basic block, interleaved by the compiler.
 #pragma unroll 1
-            for (int r0 = 0; r0 < PT; r0 += RIX) {
-                double zi[RIX][D], zj[D];
+            for (int r0 = 0; r0 < PT; r0 += RI) {
+                double zi[RI][D];
 #pragma unroll
-                for (int r = 0; r < RIX; ++r)
-#pragma unroll
-                    for (int k = 0; k < D; ++k) zi[r][k] = fma(-GP_C(k), xi[(r0 + r) * D + k], GP_CU(k));
-#pragma unroll
-                for (int k = 0; k < D; ++k) zj[k] = fma(-GP_C(k), xj[k], GP_CU(k));
-                double qc[D], qqc[D];
-                double ec = chain(zi[0], zj, qc, qqc);
-#pragma unroll 1
-                for (int j = 0; j < PTJ; ++j) {
-#pragma unroll
-                    for (int r = 0; r < RIX; ++r) {
-                        double qn[D], qqn[D], en;
-                        if (r + 1 < RIX) {
-                            en = chain(zi[r + 1], zj, qn, qqn);
-                        } else {
-                            const int jn = min(j + 1, PTJ - 1);
-#pragma unroll
-                            for (int k = 0; k < D; ++k) zj[k] = fma(-GP_C(k), xj[jn * D + k], GP_CU(k));
-                            en = chain(zi[0], zj, qn, qqn);
-                        }
-#pragma unroll
-                        for (int g = 0; g < EG; ++g) {
-                            const double w = Ws[(size_t)g * PT * PTJ + (r0 + r) * PTJ + j] * ec;
-                            accT[g] += w;
-                            if (GRAD) {
-#pragma unroll
-                                for (int k = 0; k < D; ++k) {
-                                    acc1[g][k] = fma(w, qc[k], acc1[g][k]);
-                                    acc2[g][k] = fma(w, qqc[k], acc2[g][k]);
-                                }
-                            }
-                        }
-                        ec = en;
-#pragma unroll
-                        for (int k = 0; k < D; ++k) { qc[k] = qn[k]; qqc[k] = qqn[k]; }
-                    }
-                }
-            }
-            } else {
-#pragma unroll 1
-            for (int r0 = 0; r0 < PT; r0 += RIX) {
-                double zi[RIX][D];
-#pragma unroll
-                for (int r = 0; r < RIX; ++r)
+                for (int r = 0; r < RI; ++r)
 #pragma unroll
                     for (int k = 0; k < D; ++k) zi[r][k] = fma(-GP_C(k), xi[(r0 + r) * D + k], GP_CU(k));
 #pragma unroll 1
@@ -417,7 +352,7 @@ mm_pairs_batch(const PairArgs a)
 #pragma unroll
                     for (int k = 0; k < D; ++k) zj[k] = fma(-GP_C(k), xj[j * D + k], GP_CU(k));
 #pragma unroll
-                    for (int r = 0; r < RIX; ++r) {
+                    for (int r = 0; r < RI; ++r) {
                         double q[D], qq[D];
 #pragma unroll
                         for (int k = 0; k < D; ++k) { q[k] = zi[r][k] + zj[k]; qq[k] = q[k] * q[k]; }
@@ -433,58 +368,19 @@ mm_pairs_batch(const PairArgs a)
                             for (int k = 1; k < D; ++k) S += qq[k];
                         }
                         const double e = exp_neg(S, tab);
-#if GPMPC_ACC_ORDER == 0
 #pragma unroll
                         for (int g = 0; g < EG; ++g) {
                             const double w = Ws[(size_t)g * PT * PTJ + (r0 + r) * PTJ + j] * e;
                             accT[g] += w;
                             if (GRAD) {
 #pragma unroll
-                                for (int k = 0; k < D; ++k) {
-                                    acc1[g][k] = fma(w, q[k], acc1[g][k]);
-                                    acc2[g][k] = fma(w, qq[k], acc2[g][k]);
-                                }
+                                for (int k = K1; k < D; ++k) acc1[g][k] = fma(w, q[k], acc1[g][k]);
+#pragma unroll
+                                for (int k = 0; k < K2; ++k) acc2[g][k] = fma(w, qq[k], acc2[g][k]);
                             }
                         }
-#elif GPMPC_ACC_ORDER == 1
-                        double w[EG];
-#pragma unroll
-                        for (int g = 0; g < EG; ++g) {
-                            w[g] = Ws[(size_t)g * PT * PTJ + (r0 + r) * PTJ + j] * e;
-                            accT[g] += w[g];
-                        }
-                        if (GRAD) {
-#pragma unroll
-                            for (int k = 0; k < D; ++k) {
-#pragma unroll
-                                for (int g = 0; g < EG; ++g) acc1[g][k] = fma(q[k], w[g], acc1[g][k]);
-#pragma unroll
-                                for (int g = 0; g < EG; ++g) acc2[g][k] = fma(qq[k], w[g], acc2[g][k]);
-                            }
-                        }
-#else
-                        // e-scaled features: F = e*(1, q, q^2) once per pair, then acc += Wt_g * F (Wt_g reused)
-                        double eq[D], eqq[D];
-                        if (GRAD) {
-#pragma unroll
-                            for (int k = 0; k < D; ++k) { eq[k] = e * q[k]; eqq[k] = eq[k] * q[k]; }
-                        }
-#pragma unroll
-                        for (int g = 0; g < EG; ++g) {
-                            const double wt = Ws[(size_t)g * PT * PTJ + (r0 + r) * PTJ + j];
-                            accT[g] = fma(wt, e, accT[g]);
-                            if (GRAD) {
-#pragma unroll
-                                for (int k = 0; k < D; ++k) {
-                                    acc1[g][k] = fma(wt, eq[k], acc1[g][k]);
-                                    acc2[g][k] = fma(wt, eqq[k], acc2[g][k]);
-                                }
-                            }
-                        }
-#endif
                     }
                 }
-            }
             }
             }
             __syncthreads();
@@ -499,8 +395,8 @@ mm_pairs_batch(const PairArgs a)
                 dst[0] = accT[g];
 #pragma unroll
                 for (int k = 0; k < D; ++k) {
-                    dst[(size_t)(1 + k) * a.Bpad] = GRAD ? acc1[g][k] : 0.0;
-                    dst[(size_t)(1 + D + k) * a.Bpad] = GRAD ? acc2[g][k] : 0.0;
+                    dst[(size_t)(1 + k) * a.Bpad] = (GRAD && k >= K1) ? acc1[g][k] : 0.0;
+                    dst[(size_t)(1 + D + k) * a.Bpad] = (GRAD && k < K2) ? acc2[g][k] : 0.0;
                 }
             }
         }

@@ -2,6 +2,7 @@
 // D = 2..8 with -DGPMPC_INST_D=<D> so that the seven translation units build in parallel).
 #include "mm_pairs.cuh"
 #include "mm_step_single.cuh"
+#include <type_traits>
 
 #ifndef GPMPC_INST_D
 #error "compile with -DGPMPC_INST_D=<2..8>"
@@ -9,7 +10,7 @@
 
 namespace gpmpc {
 
-template <int D, int EG, bool GRAD>
+template <int D, int EG, int GRAD, int NS>
 static cudaError_t launch_one(const PairArgs &a, dim3 grid, cudaStream_t st)
 {
     const size_t smem = pair_smem_bytes<D, EG>();
@@ -19,11 +20,11 @@ static cudaError_t launch_one(const PairArgs &a, dim3 grid, cudaStream_t st)
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= kMaxDevices) dev = 0;
     if (first_use_on_device(configured)) {
-        cudaError_t e = cudaFuncSetAttribute(mm_pairs_batch<D, EG, GRAD>,
+        cudaError_t e = cudaFuncSetAttribute(mm_pairs_batch<D, EG, GRAD, NS>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int occ = 0, sms = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mm_pairs_batch<D, EG, GRAD>, PAIR_THREADS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mm_pairs_batch<D, EG, GRAD, NS>, PAIR_THREADS, smem);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         resident[dev] = occ * sms;
     }
@@ -34,33 +35,17 @@ static cudaError_t launch_one(const PairArgs &a, dim3 grid, cudaStream_t st)
         const int per_chunk = resident[dev] / a.chunks;
         if (per_chunk * a.chunks > (int)grid.x) grid.x = per_chunk * a.chunks;
     }
-    mm_pairs_batch<D, EG, GRAD><<<grid, PAIR_THREADS, smem, st>>>(a);
+    mm_pairs_batch<D, EG, GRAD, NS><<<grid, PAIR_THREADS, smem, st>>>(a);
     return cudaGetLastError();
 }
 
-template <int D>
-static cudaError_t launch_d(int EG, bool grad, const PairArgs &a, dim3 grid, cudaStream_t st)
-{
-    switch (EG * 2 + (grad ? 1 : 0)) {
-        case 2: return launch_one<D, 1, false>(a, grid, st);
-        case 3: return launch_one<D, 1, true>(a, grid, st);
-        case 4: return launch_one<D, 2, false>(a, grid, st);
-        case 5: return launch_one<D, 2, true>(a, grid, st);
-        case 6: return launch_one<D, 3, false>(a, grid, st);
-        case 7: return launch_one<D, 3, true>(a, grid, st);
-        case 8: return launch_one<D, 4, false>(a, grid, st);
-        case 9: return launch_one<D, 4, true>(a, grid, st);
-    }
-    return cudaErrorInvalidValue;
-}
-
-template <int D, int EG, bool GRAD>
+template <int D, int EG, int GRAD, int NS>
 static cudaError_t launch_single_one(const SingleStepArgs &a, dim3 grid, cudaStream_t st)
 {
     const size_t smem = single_smem_bytes<D, EG>();
     static bool configured[kMaxDevices] = {};
     if (first_use_on_device(configured)) {
-        cudaError_t e = cudaFuncSetAttribute(mm_step_single<D, EG, GRAD>,
+        cudaError_t e = cudaFuncSetAttribute(mm_step_single<D, EG, GRAD, NS>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
@@ -72,36 +57,58 @@ static cudaError_t launch_single_one(const SingleStepArgs &a, dim3 grid, cudaStr
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, mm_step_single<D, EG, GRAD>, a);
+    return cudaLaunchKernelEx(&cfg, mm_step_single<D, EG, GRAD, NS>, a);
 }
 
-template <int D>
-static cudaError_t launch_single_d(int EG, bool grad, const SingleStepArgs &a, dim3 grid, cudaStream_t st)
+// Moment selection (mm_pairs.cuh): grad_mode 0 forward only, 1 all steps, 2 first step without d/dx0; ns = number of
+// state dimensions.  The reduced variants are compiled for one or two action dimensions (ns = D-1, D-2), every
+// other layout runs the variant that accumulates all moments (NS = D).
+template <int D, int EG, bool SINGLE, class Args>
+static cudaError_t launch_eg(int grad_mode, int ns, const Args &a, dim3 grid, cudaStream_t st)
 {
-    switch (EG * 2 + (grad ? 1 : 0)) {
-        case 2: return launch_single_one<D, 1, false>(a, grid, st);
-        case 3: return launch_single_one<D, 1, true>(a, grid, st);
-        case 4: return launch_single_one<D, 2, false>(a, grid, st);
-        case 5: return launch_single_one<D, 2, true>(a, grid, st);
-        case 6: return launch_single_one<D, 3, false>(a, grid, st);
-        case 7: return launch_single_one<D, 3, true>(a, grid, st);
-        case 8: return launch_single_one<D, 4, false>(a, grid, st);
-        case 9: return launch_single_one<D, 4, true>(a, grid, st);
+    auto go = [&](auto grad_c, auto ns_c) -> cudaError_t {
+        constexpr int G = decltype(grad_c)::value, N = decltype(ns_c)::value;
+        if constexpr (SINGLE) return launch_single_one<D, EG, G, N>(a, grid, st);
+        else return launch_one<D, EG, G, N>(a, grid, st);
+    };
+    using std::integral_constant;
+    if (grad_mode == 0) return go(integral_constant<int, 0>{}, integral_constant<int, D>{});
+    if constexpr (D >= 2) {
+        if (ns == D - 1)
+            return grad_mode == 2 ? go(integral_constant<int, 2>{}, integral_constant<int, D - 1>{})
+                                  : go(integral_constant<int, 1>{}, integral_constant<int, D - 1>{});
+    }
+    if constexpr (D >= 3) {
+        if (ns == D - 2)
+            return grad_mode == 2 ? go(integral_constant<int, 2>{}, integral_constant<int, D - 2>{})
+                                  : go(integral_constant<int, 1>{}, integral_constant<int, D - 2>{});
+    }
+    return go(integral_constant<int, 1>{}, integral_constant<int, D>{});
+}
+
+template <int D, bool SINGLE, class Args>
+static cudaError_t launch_any(int EG, int grad_mode, int ns, const Args &a, dim3 grid, cudaStream_t st)
+{
+    switch (EG) {
+        case 1: return launch_eg<D, 1, SINGLE>(grad_mode, ns, a, grid, st);
+        case 2: return launch_eg<D, 2, SINGLE>(grad_mode, ns, a, grid, st);
+        case 3: return launch_eg<D, 3, SINGLE>(grad_mode, ns, a, grid, st);
+        case 4: return launch_eg<D, 4, SINGLE>(grad_mode, ns, a, grid, st);
     }
     return cudaErrorInvalidValue;
 }
 
 #define GPMPC_CAT2(a, b) a##b
 #define GPMPC_CAT(a, b) GPMPC_CAT2(a, b)
-cudaError_t GPMPC_CAT(launch_pairs_batch_D, GPMPC_INST_D)(int EG, bool grad, const PairArgs &a,
+cudaError_t GPMPC_CAT(launch_pairs_batch_D, GPMPC_INST_D)(int EG, int grad_mode, int ns, const PairArgs &a,
                                                           dim3 grid, cudaStream_t st)
 {
-    return launch_d<GPMPC_INST_D>(EG, grad, a, grid, st);
+    return launch_any<GPMPC_INST_D, false>(EG, grad_mode, ns, a, grid, st);
 }
-cudaError_t GPMPC_CAT(launch_step_single_D, GPMPC_INST_D)(int EG, bool grad, const SingleStepArgs &a,
+cudaError_t GPMPC_CAT(launch_step_single_D, GPMPC_INST_D)(int EG, int grad_mode, int ns, const SingleStepArgs &a,
                                                           dim3 grid, cudaStream_t st)
 {
-    return launch_single_d<GPMPC_INST_D>(EG, grad, a, grid, st);
+    return launch_any<GPMPC_INST_D, true>(EG, grad_mode, ns, a, grid, st);
 }
 
 }  // namespace gpmpc

@@ -84,10 +84,13 @@ __device__ __forceinline__ void mbar_arrive(void *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int D, int EG, bool GRAD>
+// GRAD / NS select the accumulated moments exactly as in mm_pairs_batch (mm_pairs.cuh).
+template <int D, int EG, int GRAD, int NS>
 __global__ void __launch_bounds__(SINGLE_THREADS, SINGLE_CTAS_PER_SM)
 mm_step_single(const SingleStepArgs a)
 {
+    constexpr int K1 = GRAD == 2 ? NS : 0;       // N1_k for k in [K1, D)
+    constexpr int K2 = GRAD == 1 ? NS : 0;       // N2_k for k in [0, K2)
     constexpr int NA = 1 + 2 * D;
     constexpr int NV = 2 * EG * NA;
     constexpr size_t STAGE = single_stage_doubles<D, EG>();
@@ -284,10 +287,9 @@ mm_step_single(const SingleStepArgs a)
                 accT[g] += w;
                 if (GRAD) {
 #pragma unroll
-                    for (int k = 0; k < D; ++k) {
-                        acc1[g][k] = fma(w, q[k], acc1[g][k]);
-                        acc2[g][k] = fma(w, qq[k], acc2[g][k]);
-                    }
+                    for (int k = K1; k < D; ++k) acc1[g][k] = fma(w, q[k], acc1[g][k]);
+#pragma unroll
+                    for (int k = 0; k < K2; ++k) acc2[g][k] = fma(w, qq[k], acc2[g][k]);
                 }
             }
         }
@@ -310,8 +312,8 @@ mm_step_single(const SingleStepArgs a)
         if (lane == 0) red[wid][g * NA] = v;
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            const double v1 = warp_sum(GRAD ? acc1[g][k] : 0.0);
-            const double v2 = warp_sum(GRAD ? acc2[g][k] : 0.0);
+            const double v1 = (GRAD && k >= K1) ? warp_sum(acc1[g][k]) : 0.0;
+            const double v2 = (GRAD && k < K2) ? warp_sum(acc2[g][k]) : 0.0;
             if (lane == 0) { red[wid][g * NA + 1 + k] = v1; red[wid][g * NA + 1 + D + k] = v2; }
         }
     }

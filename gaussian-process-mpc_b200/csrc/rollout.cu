@@ -20,13 +20,14 @@
 
 namespace gpmpc {
 
-#define DECL_LAUNCH(D) cudaError_t launch_pairs_batch_D##D(int, bool, const PairArgs &, dim3, cudaStream_t); \
-                       cudaError_t launch_step_single_D##D(int, bool, const SingleStepArgs &, dim3, cudaStream_t);
+#define DECL_LAUNCH(D) cudaError_t launch_pairs_batch_D##D(int, int, int, const PairArgs &, dim3, cudaStream_t); \
+                       cudaError_t launch_step_single_D##D(int, int, int, const SingleStepArgs &, dim3, cudaStream_t);
 DECL_LAUNCH(2) DECL_LAUNCH(3) DECL_LAUNCH(4) DECL_LAUNCH(5) DECL_LAUNCH(6) DECL_LAUNCH(7) DECL_LAUNCH(8)
 #undef DECL_LAUNCH
 
-typedef cudaError_t (*pair_launch_fn)(int, bool, const SingleStepArgs &, dim3, cudaStream_t);
-typedef cudaError_t (*pair_tma_launch_fn)(int, bool, const PairArgs &, dim3, cudaStream_t);
+// (outputs in the group, grad_mode 0/1/2, state dimensions, ...): see the moment selection in mm_pairs.cuh
+typedef cudaError_t (*pair_launch_fn)(int, int, int, const SingleStepArgs &, dim3, cudaStream_t);
+typedef cudaError_t (*pair_tma_launch_fn)(int, int, int, const PairArgs &, dim3, cudaStream_t);
 static pair_tma_launch_fn pair_launcher(int D)
 {
     switch (D) {
@@ -105,6 +106,7 @@ __global__ void prep_step_kernel(StepDims d, int t, const double *__restrict__ m
 struct MeanArgs {
     const double *X; const double *beta[kGroupMax]; int out_idx[kGroupMax]; int EG;
     const double *cst; double *mpart; StepDims d;
+    int k1, k2;                   // moments kept: M1_k for k >= k1, M2_k for k < k2 (same selection as the pair kernel)
 };
 
 template <int D>
@@ -151,7 +153,10 @@ __global__ void __launch_bounds__(MEAN_THREADS) mean_sums_kernel(const MeanArgs 
                     const double w = bs[g][j] * l;
                     m0[g] += w;
 #pragma unroll
-                    for (int k = 0; k < D; ++k) { m1[g][k] = fma(w, p[k], m1[g][k]); m2[g][k] = fma(w, pp[k], m2[g][k]); }
+                    for (int k = 0; k < D; ++k) {
+                        if (k >= a.k1) m1[g][k] = fma(w, p[k], m1[g][k]);
+                        if (k < a.k2) m2[g][k] = fma(w, pp[k], m2[g][k]);
+                    }
                 }
             }
         }
@@ -630,9 +635,12 @@ struct NextPrep { bool on = false; const double *Uint = nullptr; const double *l
 // (slot t of mu/var) and, if want_grad, the tape entry t-1.
 //   B <  kSingleMaxB: one launch of mm_step_single per lambda group does everything (pairs, mean, finalize)
 //   B >= kSingleMaxB: mm_pairs_batch + mean_sums per group, then finalize_step
-static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int ctas, int P, long long total_tiles, bool want_grad,
+// grad_mode: 0 forward values only, 1 all moments the adjoint reads, 2 first step of a rollout whose d/dx0 is not
+// requested (mm_pairs.cuh).
+static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int ctas, int P, long long total_tiles, int grad_mode,
                     double *us, double *cst, double *mu, double *var, double *tape, const NextPrep &next = NextPrep())
 {
+    const bool want_grad = grad_mode != 0;
     const size_t mat = (size_t)h->ld * h->ld;
     const bool few = d.B < kSingleMaxB;
     if (h->time_pairs) cudaEventRecord(h->ev0, h->stream);
@@ -663,7 +671,7 @@ static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int ctas, int P, lon
                 GP_CUDA(h, cudaMemsetAsync(h->dbg.p, 0, (size_t)d.B * ctas * 6 * sizeof(unsigned long long), h->stream));
                 sa.dbg = h->dbg.as<unsigned long long>();
             }
-            e = single_launcher(d.D)(grp.count, want_grad, sa, dim3(d.B, ctas), h->stream);
+            e = single_launcher(d.D)(grp.count, grad_mode, d.E, sa, dim3(d.B, ctas), h->stream);
             h->launches++;
             if (e != cudaSuccess) return fail(h, GPMPC_ERR_CUDA, std::string("mm_step_single: ") + cudaGetErrorString(e));
             if (step_debug) {
@@ -715,11 +723,13 @@ static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int ctas, int P, lon
         const int chunks = (d.B + PAIR_THREADS - 1) / PAIR_THREADS;
         pa.counters = h->tickets.as<int>();
         GP_CUDA(h, cudaMemsetAsync(pa.counters, 0, chunks * sizeof(int), h->stream));
-        e = pair_launcher(d.D)(grp.count, want_grad, pa, dim3(ctas * chunks), h->stream);
+        e = pair_launcher(d.D)(grp.count, grad_mode, d.E, pa, dim3(ctas * chunks), h->stream);
         h->launches++;
         if (e != cudaSuccess) return fail(h, GPMPC_ERR_CUDA, std::string("mm_pairs_batch: ") + cudaGetErrorString(e));
 
         ma.X = pa.X; ma.EG = grp.count; ma.cst = pa.cst; ma.mpart = h->mpart.as<double>(); ma.d = d;
+        ma.k1 = grad_mode == 2 ? d.E : (grad_mode ? 0 : d.D);
+        ma.k2 = grad_mode == 1 ? d.E : 0;
         dim3 mgrid((d.B + MEAN_THREADS - 1) / MEAN_THREADS, MEAN_JP);
         launch_mean_d(d.D, ma, mgrid, h->stream);
         GP_LAUNCH_CHECK(h);
@@ -790,7 +800,9 @@ static int stage_in(gpmpc_ctx *h, DevBuf &buf, size_t &off, const double *src, s
 }
 
 // forward rollout into h->mu / h->var (+ tape).  x0_dev [B,E], U_dev [B,H,m] are device pointers.
-static int forward(gpmpc_ctx *h, int B, int H, const double *x0_dev, const double *U_dev, bool want_grad, RolloutWork &w)
+// need_gx0: the caller may ask for d/dx0 later (gpmpc_rollout_vjp), so step 1 keeps the state-dimension moments too.
+static int forward(gpmpc_ctx *h, int B, int H, const double *x0_dev, const double *U_dev, bool want_grad, bool need_gx0,
+                   RolloutWork &w)
 {
     int rc = reserve_rollout(h, B, H, w);
     if (rc) return rc;
@@ -817,7 +829,8 @@ static int forward(gpmpc_ctx *h, int B, int H, const double *x0_dev, const doubl
         }
         NextPrep next;
         next.on = fused_prep && t < H; next.Uint = w.Uint; next.lam_group = w.lamg; next.act_var = act_var;
-        rc = run_step(h, d, t, w.ctas, w.P, w.total_tiles, want_grad, w.us, w.cst, h->mu.as<double>(),
+        const int grad_mode = !want_grad ? 0 : ((t == 1 && !need_gx0) ? 2 : 1);
+        rc = run_step(h, d, t, w.ctas, w.P, w.total_tiles, grad_mode, w.us, w.cst, h->mu.as<double>(),
                       h->var.as<double>(), h->tape.as<double>(), next);
         if (rc) return rc;
         if (h->time_pairs) {
@@ -828,8 +841,9 @@ static int forward(gpmpc_ctx *h, int B, int H, const double *x0_dev, const doubl
             h->last_pair_evals += (long long)B * d.E * ((long long)h->n * (h->n + 1) / 2);
         }
     }
-    h->tape_B = want_grad ? B : 0;
-    h->tape_H = want_grad ? H : 0;
+    // only a tape with the step-1 state derivatives can serve gpmpc_rollout_vjp (which may be asked for d/dx0)
+    h->tape_B = (want_grad && need_gx0) ? B : 0;
+    h->tape_H = (want_grad && need_gx0) ? H : 0;
     return GPMPC_OK;
 }
 
@@ -871,7 +885,7 @@ extern "C" int gpmpc_rollout(gpmpc_handle h, int B, int H, const double *x0, con
     if ((rc = stage_in(h, h->stage_in, off, x0, (size_t)B * h->E, &x0d))) return rc;
     if (H > 0 && h->m > 0 && (rc = stage_in(h, h->stage_in, off, U, (size_t)B * H * h->m, &Ud))) return rc;
     RolloutWork w;
-    if ((rc = forward(h, B, H, x0d, Ud, true, w))) return rc;
+    if ((rc = forward(h, B, H, x0d, Ud, true, true, w))) return rc;
     return export_traj(h, w.d, H, means, vars);
 }
 
@@ -949,7 +963,7 @@ extern "C" int gpmpc_rollout_cost_grad(gpmpc_handle h, int B, int H, const doubl
 
     const bool want_grad = grad != nullptr;
     RolloutWork w;
-    if ((rc = forward(h, B, H, x0d, Ud, want_grad, w))) return rc;
+    if ((rc = forward(h, B, H, x0d, Ud, want_grad, false, w))) return rc;
     const StepDims &d = w.d;
 
     CostArgs ca;
@@ -1085,7 +1099,7 @@ extern "C" int gpmpc_moment_match_diag_internal(gpmpc_handle h, int B, const dou
     GP_LAUNCH_CHECK(h);
     h->last_pair_ms = 0.0; h->last_pair_evals = 0;
     // results land in slot t = 1 of mu / var
-    if ((rc = run_step(h, d, 1, w.ctas, w.P, w.total_tiles, false, w.us, w.cst, h->mu.as<double>(),
+    if ((rc = run_step(h, d, 1, w.ctas, w.P, w.total_tiles, 0, w.us, w.cst, h->mu.as<double>(),
                        h->var.as<double>(), h->tape.as<double>()))) return rc;
     if (h->time_pairs) {
         GP_CUDA(h, cudaEventSynchronize(h->ev1));

@@ -5,7 +5,10 @@
 #include <random>
 using namespace gpmpc;
 #ifndef GPMPC_BENCH_GRAD
-#define GPMPC_BENCH_GRAD true
+#define GPMPC_BENCH_GRAD 1       // moment selection of mm_pairs.cuh: 0 forward, 1 all steps, 2 first step
+#endif
+#ifndef GPMPC_BENCH_NS
+#define GPMPC_BENCH_NS 4         // state dimensions (N2 only for k < NS); 5 = all moments (the round-1 kernel)
 #endif
 
 __global__ void dfma_latency_kernel(double *out, int iters, double m, double c)
@@ -81,14 +84,14 @@ int main(int argc, char **argv)
     unsigned long long *dtimes; cudaMalloc(&dtimes, (size_t)ctas * chunks * 3 * 8); a.cta_times = dtimes;
 #endif
     const size_t smem = pair_smem_bytes<D, EG>();
-    cudaFuncSetAttribute(mm_pairs_batch<D, EG, GPMPC_BENCH_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(mm_pairs_batch<D, EG, GPMPC_BENCH_GRAD, GPMPC_BENCH_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(ctas * chunks);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {
         cudaMemset(dcnt, 0, chunks * sizeof(int));
         cudaEventRecord(e0);
-        mm_pairs_batch<D, EG, GPMPC_BENCH_GRAD><<<grid, PAIR_THREADS, smem>>>(a);
+        mm_pairs_batch<D, EG, GPMPC_BENCH_GRAD, GPMPC_BENCH_NS><<<grid, PAIR_THREADS, smem>>>(a);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
     }
