@@ -26,6 +26,8 @@ SIGNATURES = {
     "gpmpc_get_matrix": (c_int, [_P, c_int, c_int, _P]),
     "gpmpc_kernel_matrix": (c_int, [_P, c_int, c_int, _P, _P]),
     "gpmpc_predict": (c_int, [_P, c_int, c_int, _P, _P, _P, c_int]),
+    "gpmpc_kernel_matrix_ex": (c_int, [_P, c_int, c_int, _P, _P, _P]),
+    "gpmpc_predict_ex": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, c_int]),
     "gpmpc_marginal_likelihood": (c_int, [_P, c_int, _P, _P, _P]),
     "gpmpc_moment_match": (c_int, [_P, c_int, _P, _P, c_int, _P, _P]),
     "gpmpc_moment_match_cov": (c_int, [_P, c_int, _P, _P, _P, _P]),

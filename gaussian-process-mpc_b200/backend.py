@@ -117,22 +117,30 @@ class GPBundle:
         check(self.h, self.lib.gpmpc_get_matrix(self.h, int(which), int(a), _ptr(out)), "gpmpc_get_matrix")
         return out
 
-    def kernel_matrix(self, a, Xs):
+    def kernel_matrix(self, a, Xs, hyp=None):
+        """K(X*, X) [p,n]; hyp = [lambdas (D), sigma_f, noise_var] overrides the fit-time kernel hyper-parameters."""
         self._sync_stream()
         Xs = as_f64(Xs)
         p = Xs.shape[0]
         out = torch.empty((p, self.n), dtype=F64, device=self.device)
-        check(self.h, self.lib.gpmpc_kernel_matrix(self.h, int(a), p, _ptr(Xs), _ptr(out)), "gpmpc_kernel_matrix")
+        hp = None if hyp is None else as_f64(hyp).reshape(self.D + 2)
+        check(self.h, self.lib.gpmpc_kernel_matrix_ex(self.h, int(a), p, _ptr(Xs), _ptr(hp), _ptr(out)),
+              "gpmpc_kernel_matrix_ex")
         return out
 
-    def predict(self, a, Xs, want_cov, add_noise):
+    def predict(self, a, Xs, want_cov, add_noise, resid=None, hyp=None):
+        """Posterior mean [p] (K* Ky^-1 resid if a residual vector y - f_nom(X) is given, else K* Ky^-1 y) and cov [p,p];
+        hyp = [lambdas (D), sigma_f, noise_var] overrides the fit-time kernel hyper-parameters of K* and K**."""
         self._sync_stream()
         Xs = as_f64(Xs)
         p = Xs.shape[0]
         mean = np.empty(p)
         cov = np.empty((p, p)) if want_cov else None
-        check(self.h, self.lib.gpmpc_predict(self.h, int(a), p, _ptr(Xs), _ptr(mean), _ptr(cov), int(bool(add_noise))),
-              "gpmpc_predict")
+        r = None if resid is None else as_f64(resid).reshape(-1)
+        assert r is None or r.shape[0] == self.n
+        hp = None if hyp is None else as_f64(hyp).reshape(self.D + 2)
+        check(self.h, self.lib.gpmpc_predict_ex(self.h, int(a), p, _ptr(Xs), _ptr(r), _ptr(hp), _ptr(mean), _ptr(cov),
+                                                int(bool(add_noise))), "gpmpc_predict_ex")
         return mean, cov
 
     def marginal_likelihood(self, a, resid=None, want_grad=True):

@@ -124,6 +124,14 @@ static KsArg ks_arg(const gpmpc_ctx *h, int a)
     k.sf2 = h->sf_fit[a] * h->sf_fit[a];
     return k;
 }
+// kernel hyper-parameters supplied by the caller: hyp = [lambda_1..D, sigma_f, noise_var]
+static KsArg ks_arg_from(int D, const double *hyp)
+{
+    KsArg k;
+    for (int i = 0; i < kMaxD; ++i) k.inv_lam[i] = i < D ? 1.0 / hyp[i] : 0.0;
+    k.sf2 = hyp[D] * hyp[D];
+    return k;
+}
 __global__ void transpose_y_kernel(const double *__restrict__ Y, int n, int E, int ld, double *__restrict__ Yt)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -202,6 +210,9 @@ extern "C" int gpmpc_refit_output(gpmpc_handle h, int a, const double *y, const 
     bool which[kMaxE];
     for (int i = 0; i < kMaxE; ++i) which[i] = i == a;
     h->tape_B = h->tape_H = 0;
+    // a failed factorisation leaves Kinv / beta / Wt of this output half-written: the handle must not keep
+    // reporting "fitted" (fit_all sets the flag again on success)
+    h->fitted = false;
     return fit_all(h, which);
 }
 
@@ -279,8 +290,15 @@ extern "C" int gpmpc_append_point(gpmpc_handle h, const double *x, const double 
     }
     GP_CUDA(h, cudaMemcpyAsync(hs.data(), scal, 2 * E * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     GP_CUDA(h, cudaStreamSynchronize(h->stream));
-    for (int a = 0; a < E; ++a)
-        if (!(hs[2 * a] > 0.0) || !std::isfinite(hs[2 * a])) return GPMPC_REFIT_NEEDED;
+    // The Schur complement s = kappa - k^T Ky^-1 k is a difference computed from an EXPLICIT inverse, so it carries an
+    // absolute error of about cond(Ky) eps kappa with cond(Ky) <= n sf^2 / noise + 1.  The true value is >= noise; when
+    // the error bound is not far below it (the reference's experiments use sigma_n = 1e-5, i.e. noise 1e-10) 1/s and
+    // the whole rank-1 update would be garbage without any visible sign, so the caller is told to refit instead.
+    for (int a = 0; a < E; ++a) {
+        const double kappa = h->sf_fit[a] * h->sf_fit[a] + h->noise[a];
+        const double tol = 1e3 * 2.220446049250313e-16 * (double)n * kappa / h->noise[a];
+        if (!(hs[2 * a] > tol * kappa) || !std::isfinite(hs[2 * a])) return GPMPC_REFIT_NEEDED;
+    }
     // second pass: apply
     GP_CUDA(h, cudaMemcpyAsync(h->X.as<double>() + (size_t)n * D, xh, D * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     for (int a = 0; a < E; ++a) {
@@ -422,6 +440,11 @@ __global__ void post_cov_kernel(const double *__restrict__ Xs, int p, int D, KsA
 
 extern "C" int gpmpc_kernel_matrix(gpmpc_handle h, int a, int p, const double *Xs, double *out)
 {
+    return gpmpc_kernel_matrix_ex(h, a, p, Xs, nullptr, out);
+}
+
+extern "C" int gpmpc_kernel_matrix_ex(gpmpc_handle h, int a, int p, const double *Xs, const double *hyp, double *out)
+{
     if (!h) return GPMPC_ERR_INVALID;
     if (!h->fitted) return fail(h, GPMPC_ERR_NOT_FIT, "gpmpc_kernel_matrix: not fitted");
     if (a < 0 || a >= h->E || p <= 0 || !Xs || !out) return fail(h, GPMPC_ERR_INVALID, "gpmpc_kernel_matrix: bad argument");
@@ -439,7 +462,14 @@ extern "C" int gpmpc_kernel_matrix(gpmpc_handle h, int a, int p, const double *X
     double *dev = out;
     if (host) { GP_CUDA(h, h->stage_out.reserve((size_t)p * n * sizeof(double))); dev = h->stage_out.as<double>(); }
     dim3 blk(32, 8), grid((n + 31) / 32, (p + 7) / 8);
-    kstar_kernel<<<grid, blk, 0, h->stream>>>(Xd, p, h->X.as<double>(), n, D, ks_arg(h, a), dev, n, p, n);
+    KsArg ka = ks_arg(h, a);
+    if (hyp) {
+        double hh[kMaxD + 2];
+        int rc = fetch_host(h, hyp, hh, (size_t)D + 2);
+        if (rc) return rc;
+        ka = ks_arg_from(D, hh);
+    }
+    kstar_kernel<<<grid, blk, 0, h->stream>>>(Xd, p, h->X.as<double>(), n, D, ka, dev, n, p, n);
     GP_LAUNCH_CHECK(h);
     if (host) {
         GP_CUDA(h, cudaMemcpyAsync(out, dev, (size_t)p * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -450,6 +480,12 @@ extern "C" int gpmpc_kernel_matrix(gpmpc_handle h, int a, int p, const double *X
 
 extern "C" int gpmpc_predict(gpmpc_handle h, int a, int p, const double *Xs, double *mean, double *cov, int add_noise)
 {
+    return gpmpc_predict_ex(h, a, p, Xs, nullptr, nullptr, mean, cov, add_noise);
+}
+
+extern "C" int gpmpc_predict_ex(gpmpc_handle h, int a, int p, const double *Xs, const double *resid, const double *hyp,
+                                double *mean, double *cov, int add_noise)
+{
     if (!h) return GPMPC_ERR_INVALID;
     if (!h->fitted) return fail(h, GPMPC_ERR_NOT_FIT, "gpmpc_predict: not fitted");
     if (a < 0 || a >= h->E || p <= 0 || !Xs || !mean) return fail(h, GPMPC_ERR_INVALID, "gpmpc_predict: bad argument");
@@ -457,8 +493,8 @@ extern "C" int gpmpc_predict(gpmpc_handle h, int a, int p, const double *Xs, dou
     const int n = h->n, D = h->D, ld = h->ld;
     const int pp = round_up(p, kTile);
     const size_t mat = (size_t)ld * ld;
-    // workspace (gbuf): Xs [pp*D] | Ks [pp, ld] | T [pp, ld] | TK [pp, pp] | mean [pp] | cov [p*p]
-    const size_t cnt = (size_t)pp * D + 2 * (size_t)pp * ld + (size_t)pp * pp + pp + (size_t)p * p + 64;
+    // workspace (gbuf): Xs [pp*D] | Ks [pp, ld] | T [pp, ld] | TK [pp, pp] | mean [pp] | cov [p*p] | resid [ld]
+    const size_t cnt = (size_t)pp * D + 2 * (size_t)pp * ld + (size_t)pp * pp + pp + (size_t)p * p + ld + 64;
     GP_CUDA(h, h->gbuf.reserve(cnt * sizeof(double)));
     double *w = h->gbuf.as<double>();
     double *Xd = w; w += (size_t)pp * D;
@@ -466,17 +502,29 @@ extern "C" int gpmpc_predict(gpmpc_handle h, int a, int p, const double *Xs, dou
     double *T = w; w += (size_t)pp * ld;
     double *TK = w; w += (size_t)pp * pp;
     double *md = w; w += pp;
-    double *cd = w;
+    double *cd = w; w += (size_t)p * p;
+    double *rd = w;
+    const double *yv = h->Y.as<double>() + (size_t)a * ld;      // targets, or the caller's residual y - f_nom(X)
+    if (resid) { GP_CUDA(h, to_device(h, rd, resid, (size_t)n * sizeof(double))); yv = rd; }
+    KsArg ka = ks_arg(h, a);
+    double noise = h->noise[a];
+    if (hyp) {
+        double hh[kMaxD + 2];
+        int rch = fetch_host(h, hyp, hh, (size_t)D + 2);
+        if (rch) return rch;
+        ka = ks_arg_from(D, hh);
+        noise = hh[D + 1];
+    }
     GP_CUDA(h, cudaMemsetAsync(Xd, 0, (size_t)pp * D * sizeof(double), h->stream));
     GP_CUDA(h, to_device(h, Xd, Xs, (size_t)p * D * sizeof(double)));
     dim3 blk(32, 8), grid((ld + 31) / 32, (pp + 7) / 8);
-    kstar_kernel<<<grid, blk, 0, h->stream>>>(Xd, p, h->X.as<double>(), n, D, ks_arg(h, a), Ks, ld, pp, ld);
+    kstar_kernel<<<grid, blk, 0, h->stream>>>(Xd, p, h->X.as<double>(), n, D, ka, Ks, ld, pp, ld);
     GP_LAUNCH_CHECK(h);
     // T = Ks Ky^-1 (Ky^-1 symmetric -> NT form), the order the reference multiplies in (src/gpr.py:306)
     int rc = dgemm_nt(h, pp, ld, ld, 1.0, Ks, ld, h->Kinv.as<double>() + a * mat, ld, 0.0, T, ld, false, 0);
     if (rc) return rc;
     // mean = T y   (rows of the padded region of Ky^-1 are identity, but Ks is zero there)
-    gpmpc_rowdot_kernel<<<(pp + 7) / 8, 256, 0, h->stream>>>(T, ld, n, h->Y.as<double>() + (size_t)a * ld, md, pp);
+    gpmpc_rowdot_kernel<<<(pp + 7) / 8, 256, 0, h->stream>>>(T, ld, n, yv, md, pp);
     GP_LAUNCH_CHECK(h);
     GP_CUDA(h, cudaMemcpyAsync(mean, md, (size_t)p * sizeof(double), cudaMemcpyDefault, h->stream));
     if (cov) {
@@ -485,7 +533,7 @@ extern "C" int gpmpc_predict(gpmpc_handle h, int a, int p, const double *Xs, dou
         dim3 cgrid((p + 31) / 32, (p + 7) / 8);
         const bool host = !is_device_ptr(cov);
         double *dev = host ? cd : cov;
-        post_cov_kernel<<<cgrid, blk, 0, h->stream>>>(Xd, p, D, ks_arg(h, a), TK, pp, add_noise ? h->noise[a] : 0.0, dev);
+        post_cov_kernel<<<cgrid, blk, 0, h->stream>>>(Xd, p, D, ka, TK, pp, add_noise ? noise : 0.0, dev);
         GP_LAUNCH_CHECK(h);
         if (host) GP_CUDA(h, cudaMemcpyAsync(cov, dev, (size_t)p * p * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     }

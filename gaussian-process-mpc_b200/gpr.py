@@ -101,9 +101,25 @@ class GaussianProcessRegression(object):
     def get_sigma_n(self):
         return torch.exp(self.log_sigma_n).item()
 
+    _HYPER_ATTRS = ("log_lambdas", "log_sigma_f", "log_sigma_n")
+
+    def __setattr__(self, name, value):
+        # every (re)assignment of a hyper-parameter tensor -- by a set_* method or directly -- bumps a generation
+        # counter; id() alone cannot tell two tensors apart once the first has been freed and its id recycled
+        if name in GaussianProcessRegression._HYPER_ATTRS:
+            object.__setattr__(self, "_hyper_gen", getattr(self, "_hyper_gen", 0) + 1)
+        object.__setattr__(self, name, value)
+
     def _hyper_key(self):
-        """Cheap change detector (no device sync): identity + in-place version of the three tensors."""
-        return tuple((id(t), t._version) for t in (self.log_lambdas, self.log_sigma_f, self.log_sigma_n))
+        """Cheap change detector (no device sync): assignment generation + in-place version of the three tensors."""
+        return (self._hyper_gen,) + tuple(t._version for t in (self.log_lambdas, self.log_sigma_f, self.log_sigma_n))
+
+    def _call_time_hypers(self):
+        """[lambdas, sigma_f, sigma_n^2] as the object holds them NOW: the reference evaluates K(X*,X) and K(X*,X*) with
+        the current hyper-parameters and adds the fp64 sigma_n^2 to target covariances (`src/gpr.py:268-276,317-329`),
+        while Ky^-1 stays from the last build."""
+        return np.concatenate([self.get_lambdas().astype(np.float64), [float(self.get_sigma_f())],
+                               [float(self.get_sigma_n()) ** 2]])
 
     def _hyper_values(self):
         return self.get_lambdas().astype(np.float64), float(self.get_sigma_f()), noise_variance(self.get_sigma_n())
@@ -185,7 +201,7 @@ class GaussianProcessRegression(object):
         bundle, a = self._bundle_and_index()
         Xp = np.asarray(X_pred, dtype=np.float64)
         single = Xp.ndim == 1
-        K = bundle.kernel_matrix(a, Xp.reshape(-1, self.x_dim))
+        K = bundle.kernel_matrix(a, Xp.reshape(-1, self.x_dim), hyp=self._call_time_hypers())
         return K[0] if single else K
 
     def predict_latent_vars(self, X_pred, covar=False, targets=False):
@@ -193,17 +209,14 @@ class GaussianProcessRegression(object):
         bundle, a = self._bundle_and_index()
         Xp = np.asarray(X_pred, dtype=np.float64).reshape(-1, self.x_dim)
         if self.f_nom is not None:
-            # residual form K* Ky^-1 (y - f_nom(X)) + f_nom(X*)  (`src/gpr.py:309`): off the hot path,
-            # evaluated with the materialised inverse
-            Ks = bundle.kernel_matrix(a, Xp)
+            # residual form K* Ky^-1 (y - f_nom(X)) + f_nom(X*)  (`src/gpr.py:309`): the nominal model is a Python
+            # callable, so it is evaluated here; the products with K* and Ky^-1 run in the library
             Xt = torch.tensor(Xp, device=self.device).type(F64)
-            f_pred = Ks @ self.Ky_inv @ (self.y_train - self.f_nom(self.X_train)) + self.f_nom(Xt)
-            mean = f_pred.cpu().detach().numpy()
-            if not covar:
-                return mean, None
-            _, cov = bundle.predict(a, Xp, True, targets)
-            return mean, cov
-        mean, cov = bundle.predict(a, Xp, covar, targets)
+            resid = (self.y_train - self.f_nom(self.X_train)).detach().reshape(-1)
+            mean, cov = bundle.predict(a, Xp, covar, targets, resid=resid, hyp=self._call_time_hypers())
+            f_pred = torch.tensor(mean, device=self.device).type(F64)[:, None] + self.f_nom(Xt)
+            return f_pred.cpu().detach().numpy(), (cov if covar else None)
+        mean, cov = bundle.predict(a, Xp, covar, targets, hyp=self._call_time_hypers())
         return mean[:, None], (cov if covar else None)
 
     # ---- hyper-parameter training (src/gpr.py:240-251,334-370) ---------------------------------------

@@ -193,12 +193,20 @@ class RiskSensitiveMPC:
         else:
             from scipy.optimize import minimize
 
+            last = {"z": x0.copy(), "f": None}
+
             def fun(z):
                 c = self.objective(z)
                 g = np.asarray(self.gradient(z), dtype=np.float64).reshape(-1)
-                if not np.isfinite(c):
-                    return 1e300, np.zeros_like(g)
-                return c, g
+                if np.isfinite(c) and np.all(np.isfinite(g)):
+                    last["z"], last["f"] = np.array(z, dtype=np.float64), c
+                    return c, g
+                # A non-finite cost (the NaN of log(det) < 0, `src/mpc.py:183`) is an evaluation error: IPOPT shortens
+                # the step.  L-BFGS-B's line search cannot take NaN, so it is shown a steep bowl centred on the last
+                # finite iterate instead, which makes it back off towards that iterate in the same way.
+                d = np.asarray(z, dtype=np.float64) - last["z"]
+                scale = 1e3 * max(1.0, abs(last["f"] or 0.0))
+                return (last["f"] or 0.0) + scale * (1.0 + d @ d), 2.0 * scale * d
             bounds = [(None if l <= -1e15 else l, None if u >= 1e15 else u) for l, u in zip(lb, ub)]
             res = minimize(fun, x0, jac=True, method="L-BFGS-B", bounds=bounds,
                            options={"maxiter": 300, "ftol": 1e-10, "gtol": 1e-4})

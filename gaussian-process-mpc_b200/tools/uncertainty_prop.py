@@ -6,7 +6,9 @@ for a Gaussian input N(u, S) with a FULL covariance S, evaluated by libgpmpc's g
 These are the stateless forms: every call ships the caller's tensors to the library.  The rollout does not
 go through them -- it uses the fitted bundle and the batched kernels (`Dynamics.forward_propagate_torch`).
 Outputs are detached device tensors (the reference's tests use values only; gradients w.r.t. the control
-sequence are provided by the rollout adjoint instead).
+sequence are provided by the rollout adjoint instead).  The reference's functions are differentiable torch code;
+to keep a caller that composes them the reference way from silently training on missing gradients, they raise
+when u or S asks for a gradient.
 """
 from __future__ import annotations
 
@@ -25,12 +27,20 @@ def _dev(t):
     return torch.device("cuda", torch.cuda.current_device())
 
 
+def _no_autograd(*tensors):
+    for t in tensors:
+        if isinstance(t, torch.Tensor) and t.requires_grad and torch.is_grad_enabled():
+            raise RuntimeError("the moment-matching free functions return values only; differentiate through "
+                               "Dynamics.forward_propagate_torch (device adjoint) or detach the inputs")
+
+
 def _scalar(x):
     return float(x.item()) if isinstance(x, torch.Tensor) else float(x)
 
 
 def mean_prop_torch(Ky_inv, lambdas, u, S, X_train, y_train, sigma_f=1):
     """Mean of the GP output; returns (0-D tensor, {'beta': [n], 'l': [n]})."""
+    _no_autograd(u, S)
     dev = _dev(Ky_inv)
     b = default_bundle(dev.index or 0)
     b._sync_stream()
@@ -49,6 +59,7 @@ def mean_prop_torch(Ky_inv, lambdas, u, S, X_train, y_train, sigma_f=1):
 
 def variance_prop_torch(Ky_inv, lambdas, u, S, X_train, mean, beta, sigma_f=1):
     """Variance of the GP output (latent; no noise term) given the mean and beta of mean_prop_torch."""
+    _no_autograd(u, S)
     dev = _dev(Ky_inv)
     b = default_bundle(dev.index or 0)
     b._sync_stream()
@@ -71,6 +82,7 @@ def covariance_prop_torch(lambdas1, lambdas2, u, S, X_train, mean1, mean2, beta1
     Evaluates the published formula (and the reference's NumPy twin, `uncertainty_prop.py:187-236`).  The
     reference's torch function transposes the cross term (`:446`), which only matters when lambdas1 is not
     proportional to lambdas2; pass bugcompat=True to reproduce that function bit-for-formula."""
+    _no_autograd(u, S)
     dev = _dev(X_train)
     b = default_bundle(dev.index or 0)
     b._sync_stream()

@@ -73,8 +73,9 @@ int gpmpc_refit_output(gpmpc_handle h, int a, const double *y, const double *lam
  * log det Ky and weight matrix: O(E n^2) instead of the O(E n^3) rebuild the reference performs on every
  * closed-loop step (src/simulator.py:55 -> src/gpr.py:122,171; its own attempt at this, src/gpr.py:137-157, is
  * marked "don't use").  Returns GPMPC_OK, or GPMPC_REFIT_NEEDED (> 0, not an error) when the padded layout
- * is full or a Schur complement is not positive: the caller then calls gpmpc_fit with all the data, which also
- * bounds the drift of repeated updates to at most 63 of them.                                        */
+ * is full or a Schur complement s = kappa - k^T Ky^-1 k is not safely positive (s <= 1e3 eps n kappa^2 / noise, the
+ * rounding error an explicit inverse of condition n sf^2 / noise leaves in it): the caller then calls gpmpc_fit
+ * with all the data, which also bounds the drift of repeated updates to at most 63 of them.              */
 #define GPMPC_REFIT_NEEDED 1
 int gpmpc_append_point(gpmpc_handle h, const double *x, const double *y);
 
@@ -92,6 +93,14 @@ int gpmpc_kernel_matrix(gpmpc_handle h, int a, int p, const double *Xs, double *
 /* Posterior at p test inputs for output a: mean[p]; cov[p,p] if cov != NULL (+ noise_var I if
  * add_noise).  Replaces predict_latent_vars with f_nom = None (src/gpr.py:285-332).                  */
 int gpmpc_predict(gpmpc_handle h, int a, int p, const double *Xs, double *mean, double *cov, int add_noise);
+/* Extended forms.  The reference evaluates K(X*, X) and K(X*, X*) with the hyper-parameters held by the object at
+ * CALL time (src/gpr.py:268-276,317-324) while Ky^-1 stays from the last build, and adds the fp64 sigma_n^2 to the
+ * target covariance (src/gpr.py:329): hyp = [lambda_1..D, sigma_f, noise_var] overrides the fit-time values for these
+ * kernel evaluations (NULL = fit-time values).  resid[n] = y - f_nom(X) replaces the targets in the mean,
+ * mean[p] = K(X*,X) Ky^-1 resid; the caller adds f_nom(X*) (src/gpr.py:309).  resid == NULL: the targets.        */
+int gpmpc_kernel_matrix_ex(gpmpc_handle h, int a, int p, const double *Xs, const double *hyp, double *out);
+int gpmpc_predict_ex(gpmpc_handle h, int a, int p, const double *Xs, const double *resid, const double *hyp,
+                     double *mean, double *cov, int add_noise);
 
 /* Log marginal likelihood of output a for the hyper-parameters of the last fit,
  *   ml = -1/2 r^T Ky^-1 r - 1/2 log det Ky - n/2 log 2 pi,   r = resid (or the training targets if resid == NULL),

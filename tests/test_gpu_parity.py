@@ -849,3 +849,185 @@ def test_kernel_switch_boundary_and_long_horizon(gp):
                                               x0[b], U[b], -1.0, Q, R)
         close(c112[b], c, RTOL)
         norm_close(g112[b], gr, RTOL)
+
+
+# ------------------------------------------------------------------------------------------------
+# Round 2: the sizes BASELINE.json names that round 1 left untested
+# ------------------------------------------------------------------------------------------------
+def _host_gram(X, lam, sf, noise_var):
+    Xs = X / np.sqrt(lam)
+    sq = np.sum(Xs * Xs, axis=1)
+    d2 = np.maximum(sq[:, None] + sq[None, :] - 2.0 * (Xs @ Xs.T), 0.0)
+    K = sf ** 2 * np.exp(-0.5 * d2)
+    K[np.diag_indices_from(K)] = sf ** 2 + noise_var        # exact diagonal (the reference's cdist gives sqrt(eps), B.7)
+    return K
+
+
+def test_config4_size_fit_n16384(gp):
+    """configs[3] size: the blocked Cholesky / recursive triangular inverse at n = 16384 (256 diagonal blocks deep).
+    (a) residual max|Ky^-1 Ky - I| on 64 random probe columns of Ky built on the host; (b) beta of every output against a
+    host fp64 Cholesky solve (LAPACK potrf/potrs, independent of the device factorisation)."""
+    import scipy.linalg as sla
+    n, E, m = 16384, 4, 1
+    dyn, S, A, nxt, rng = _synth_dynamics(gp, n, E, m, seed=0)
+    X = np.concatenate([S, A], 1)
+    noise = float(np.float32(0.1 ** 2))
+    Ky = _host_gram(X, np.full(E + m, 2.0), 1.0, noise)
+    cols = np.sort(rng.choice(n, 64, replace=False))
+    Kinv = dyn.gpr_err[0].Ky_inv                       # [n, n] device tensor
+    assert float(torch.max(torch.abs(Kinv - Kinv.T))) == 0.0
+    R = (Kinv @ torch.tensor(Ky[:, cols], device=Kinv.device)).cpu().numpy()
+    R[cols, np.arange(64)] -= 1.0
+    assert np.max(np.abs(R)) < 1e-8, np.max(np.abs(R))
+    c = sla.cho_factor(Ky, lower=True, overwrite_a=True, check_finite=False)
+    beta_host = sla.cho_solve(c, nxt, check_finite=False)
+    for a in range(E):
+        beta = dyn._bundle.matrix(3, a).cpu().numpy()
+        norm_close(beta, beta_host[:, a], 1e-7)
+    # the explicit inverse applied to y agrees with the solve as well (what the reference computes, uncertainty_prop.py:327)
+    norm_close((Kinv @ torch.tensor(nxt[:, 0], device=Kinv.device)).cpu().numpy(), beta_host[:, 0], 1e-7)
+
+
+def test_config4_size_variance_only_rollout_n16384(gp):
+    """configs[3] size, variance-only rollout: H = 2, both kernels (B = 2 lanes<->pairs, B = 128 lanes<->rollouts)
+    against the C oracle driven by a HOST LU inverse (np.linalg.inv, the reference's factorisation)."""
+    from oracle import oracle as orc
+    n, E, m, H = 16384, 4, 1, 2
+    dyn, S, A, nxt, rng = _synth_dynamics(gp, n, E, m, seed=0)
+    X = np.concatenate([S, A], 1)
+    lam = np.full((E, E + m), 2.0)
+    # one LU inverse: the outputs share Ky (orc.fit's [n,n,D] temporaries would need 20 GB of host memory at this n)
+    Kinv = np.linalg.inv(_host_gram(X, lam[0], 1.0, float(np.float32(0.1 ** 2))))
+    betas = [Kinv @ nxt[:, a] for a in range(E)]
+    Q = 2 * np.eye(E); R = 0.01 * np.eye(m)
+    br = gp.BatchedRollouts(dyn, Q, R)
+    x0 = rng.uniform(-0.5, 0.5, E); U = rng.uniform(-0.3, 0.3, (128, H, m))
+    cost, grad = br.cost_and_grad(x0, U, -1.0, host_out=True)
+    cs, gs = br.cost_and_grad(x0, U[:2], -1.0, host_out=True)
+    for b in (0, 1):
+        c, gr, _, _ = orc.c_rollout_cost_grad(X, [Kinv] * E, betas, lam, np.ones(E), x0, U[b], -1.0, Q, R)
+        close(cost[b], c, RTOL); norm_close(grad[b], gr, RTOL)
+        close(cs[b], c, RTOL); norm_close(gs[b], gr, RTOL)
+
+
+def test_config3_full_size_eight_rollouts_across_chunks_both_kernels(gp):
+    """configs[2] at size (n=4096, H=30): 8 rollouts spread over different 128-lane chunks of a 1024 batch against the C
+    oracle, through the batched kernel AND through the few-rollouts kernel."""
+    from oracle import oracle as orc
+    n, E, m, H, B = 4096, 4, 1, 30, 1024
+    dyn, S, A, nxt, rng = _synth_dynamics(gp, n, E, m, seed=0)
+    Q = 2 * np.eye(E); R = 0.01 * np.eye(m)
+    br = gp.BatchedRollouts(dyn, Q, R)
+    x0 = rng.uniform(-0.5, 0.5, E); U = rng.uniform(-0.3, 0.3, (B, H, m))
+    cost, grad = br.cost_and_grad(x0, U, -1.0, host_out=True)
+    X = np.concatenate([S, A], 1)
+    lam = np.full((E, E + m), 2.0)
+    f0 = orc.fit(X, nxt[:, 0], lam[0], 1.0, float(np.float32(0.1 ** 2)) ** 0.5)
+    betas = [f0["Ky_inv"] @ nxt[:, a] for a in range(E)]
+    picks = [0, 131, 258, 389, 516, 647, 900, 1023]            # one per 128-lane chunk
+    cs, gs = br.cost_and_grad(x0, U[picks], -1.0, host_out=True)    # 8 rollouts: the lanes<->pairs kernel
+    for i, b in enumerate(picks):
+        c, gr, _, _ = orc.c_rollout_cost_grad(X, [f0["Ky_inv"]] * E, betas, lam, np.ones(E), x0, U[b], -1.0, Q, R)
+        close(cost[b], c, RTOL); norm_close(grad[b], gr, RTOL)
+        close(cs[i], c, RTOL); norm_close(gs[i], gr, RTOL)
+
+
+def test_config2_full_size_eight_inputs_across_chunks(gp):
+    """configs[1] at size (n=2048, 8192 inputs): 8 inputs from different 128-lane chunks against the C oracle."""
+    from oracle import oracle as orc
+    n, E, m, B = 2048, 4, 1, 8192
+    D = E + m
+    dyn, S, A, nxt, rng = _synth_dynamics(gp, n, E, m, seed=0)
+    X = np.concatenate([S, A], 1)
+    lam = np.full((E, D), 2.0)
+    f0 = orc.fit(X, nxt[:, 0], lam[0], 1.0, float(np.float32(0.1 ** 2)) ** 0.5)
+    betas = [f0["Ky_inv"] @ nxt[:, a] for a in range(E)]
+    U = rng.uniform(-0.5, 0.5, (B, D)); Sd = rng.uniform(1e-3, 5e-2, (B, D))
+    mean, var = dyn._bundle.moment_match(U, Sd, out_device=False)
+    for b in (3, 1000, 2049, 3100, 4500, 5800, 7000, 8190):
+        for a in range(E):
+            mo, vo, _ = orc.c_moment_match_diag(X, f0["Ky_inv"], betas[a], lam[a], 1.0, U[b], Sd[b])
+            close(mean[b, a], mo, 1e-8)
+            assert abs(var[b, a] - vo) <= RTOL * max(abs(vo), 1e-3)
+
+
+def test_config5_full_size_gamma_sweep_batched_solver(gp):
+    """configs[4] at size: n=4096, H=30, a gamma sweep x initial states (64 MPC instances) solved in lock step by
+    BatchedSolver.  Every final cost is re-evaluated through the scalar cyipopt-protocol callback path
+    (RiskSensitiveMPC.objective, B=1 kernel) at 1e-6; the solver must have decreased every cost from U=0 and reached
+    its projected-gradient tolerance."""
+    n, E, m, H = 4096, 4, 1, 30
+    S, A, nxt, rng = _synth(n, E, m, seed=0)
+    Q = 2 * np.eye(E); R = 0.01 * np.eye(m)
+    mpc = gp.RiskSensitiveMPC(-1.0, H, E, m, Q, R)
+    for a in range(E):
+        mpc.dynamics.gpr_err[a].set_lambdas(np.full(E + m, 2.0)); mpc.dynamics.gpr_err[a].set_sigma_n(np.float64(0.1))
+    mpc.dynamics.append_train_data(S, A, nxt)
+    gammas = np.array([-2.0, -1.0, 0.5, 1.0])
+    starts = rng.uniform(-0.5, 0.5, (16, E))
+    G, X0 = np.meshgrid(gammas, np.arange(len(starts)), indexing="ij")
+    gam = G.reshape(-1); x0 = starts[X0.reshape(-1)]
+    B = gam.size
+    assert B == 64
+    br = gp.BatchedRollouts(mpc.dynamics, Q, R)
+    c0, _ = br.cost_and_grad(x0, np.zeros((B, H, m)), gam, host_out=True)
+    sol = gp.BatchedSolver(br, H, m, lb=[-1.0], ub=[1.0], max_iter=60, gtol=1e-4).solve(x0, gam)
+    assert np.all(np.isfinite(sol["cost"])) and np.all(sol["cost"] <= c0 + 1e-12)
+    assert sol["converged"].mean() >= 0.9, sol["converged"].mean()
+    for b in range(B):
+        mpc.gamma = float(gam[b])
+        mpc.curr_state = torch.tensor(x0[b], device="cuda:0")
+        c = mpc.objective(sol["U"][b].reshape(-1))
+        close(sol["cost"][b], c, RTOL)
+
+
+def test_incremental_append_refuses_ill_conditioned_updates(gp):
+    """with the reference's experiment hyper-parameters (sigma_n = 1e-5, sigma_f = 5) the Schur complement of a
+    bordered update is below the rounding error of the explicit inverse; the library must ask for a full refit instead
+    of applying a garbage rank-1 update, so appending one point gives the same state as fitting everything at once."""
+    n0, E, m = 200, 2, 1
+    S, A, nxt, rng = _synth(n0 + 3, E, m, seed=21)
+    def make():
+        d = gp.Dynamics(E, m)
+        for a in range(E):
+            d.gpr_err[a].set_lambdas(np.full(E + m, 1.0)); d.gpr_err[a].set_sigma_f(np.float64(5.0))
+            d.gpr_err[a].set_sigma_n(np.float64(1e-5))
+        return d
+    inc = make(); inc.append_train_data(S[:n0], A[:n0], nxt[:n0])
+    for i in range(n0, n0 + 3):
+        inc.append_train_data(S[i], A[i], nxt[i])
+    full = make(); full.append_train_data(S, A, nxt)
+    for a in range(E):
+        assert torch.equal(inc.gpr_err[a].Ky_inv, full.gpr_err[a].Ky_inv)      # same code path => bit-identical
+    x0 = np.array([0.2, -0.1]); U = rng.uniform(-0.3, 0.3, (3, m))
+    mi, ci = inc.forward_propagate(3, x0, U); mf, cf = full.forward_propagate(3, x0, U)
+    assert np.array_equal(mi, mf) and np.array_equal(ci, cf)
+
+
+def test_hyper_key_detects_reassignment_and_call_time_hypers(gp):
+    """(1) two consecutive set_* calls must always be seen (generation counter, not id()); (2) K(X*,X) and
+    K(X*,X*) use the hyper-parameters held at CALL time while Ky^-1 stays from the last build (src/gpr.py:268-276,317-329)."""
+    from oracle import oracle as orc
+    rng = np.random.default_rng(31)
+    n, D = 40, 3
+    X = rng.normal(size=(n, D)); y = np.sin(X.sum(1))
+    g = gp.GaussianProcessRegression(D)
+    g.set_lambdas(np.full(D, 1.5)); g.set_sigma_n(np.float64(0.2))
+    g.append_train_data(X, y)
+    k0 = g._hyper_key()
+    g.set_sigma_f(np.float64(1.0)); k1 = g._hyper_key()
+    g.set_sigma_f(np.float64(1.0)); k2 = g._hyper_key()
+    assert k0 != k1 and k1 != k2
+    Kinv = g.Ky_inv.cpu().numpy()
+    lam2 = np.array([0.7, 2.0, 1.1])
+    g.set_lambdas(lam2); g.set_sigma_f(np.float64(1.3)); g.set_sigma_n(np.float64(0.4))     # no rebuild
+    Xp = rng.normal(size=(5, D))
+    Ks = orc.se_gram(Xp, X, lam2, 1.3)
+    norm_close(g.compute_pred_train_covariance(Xp).cpu().numpy(), Ks, 1e-12)
+    mean, cov = g.predict_latent_vars(Xp, covar=True, targets=True)
+    norm_close(mean[:, 0], Ks @ Kinv @ y, 1e-9)
+    norm_close(cov, orc.se_gram(Xp, Xp, lam2, 1.3) - Ks @ Kinv @ Ks.T + 0.4 ** 2 * np.eye(5), 1e-9)
+    from gpmpc_b200.tools.uncertainty_prop import mean_prop_torch
+    u = torch.zeros(D, dtype=torch.float64, device="cuda:0", requires_grad=True)
+    with pytest.raises(RuntimeError):
+        mean_prop_torch(T(Kinv), T(lam2), u, T(0.1 * np.eye(D)), T(X), T(y), 1.0)
