@@ -182,6 +182,63 @@ def rollout(X, Ky_invs, Ys, lambdas, sigma_fs, x0, U):
     return means, vars_
 
 
+def moment_match_full(X, Ky_invs, betas, lambdas, sigma_fs, u, S, use_c=False):
+    """mean [E] and the full E x E covariance of the E GP outputs for x* ~ N(u, S), S full:
+    variances from `variance_prop` (`uncertainty_prop.py:341-399`), cross-covariances from the formula-correct
+    NumPy form (`uncertainty_prop.py:187-236`).  `use_c` evaluates the same sums with the C restatement."""
+    E = len(Ky_invs)
+    if use_c:
+        X = _c(X); n, D = X.shape
+        Kinv = _c(np.stack(Ky_invs)); bt = _c(np.stack(betas)); lam = _c(lambdas); sf = _c(sigma_fs)
+        uu = _c(u); SS = _c(S)
+        mean = np.zeros(E); cov = np.zeros((E, E))
+        _lib().oracle_moment_match_full(n, D, E, _p(X), _p(Kinv), _p(bt), _p(lam), _p(sf), _p(uu), _p(SS), _p(mean), _p(cov))
+        return mean, cov
+    mean = np.zeros(E); cov = np.zeros((E, E))
+    for a in range(E):
+        V = np.asarray(u)[None, :] - X
+        Bm = np.linalg.inv(np.asarray(S) + np.diag(lambdas[a]))
+        det = np.linalg.det(np.diag(1.0 / np.asarray(lambdas[a])) @ S + np.eye(len(u)))
+        l = det ** (-0.5) * np.exp(-0.5 * np.sum((V @ Bm) * V, axis=1)) * sigma_fs[a] ** 2
+        mean[a] = betas[a] @ l
+    for a in range(E):
+        cov[a, a] = variance_prop(Ky_invs[a], lambdas[a], u, S, X, mean[a], betas[a], sigma_fs[a])
+        for b in range(a + 1, E):
+            cov[a, b] = cov[b, a] = covariance_prop(lambdas[a], lambdas[b], u, S, X, mean[a], mean[b], betas[a],
+                                                    betas[b], sigma_fs[a], sigma_fs[b])
+    return mean, cov
+
+
+def rollout_full(X, Ky_invs, betas, lambdas, sigma_fs, x0, U, use_c=False):
+    """Full-covariance moment-matched rollout: like `rollout` (`src/dynamics.py:126-191`) but Sigma_t keeps the
+    cross-covariances between the outputs -- the wiring the reference leaves as a TODO (`src/dynamics.py:104-121,184`).
+    Input covariance of step t: blockdiag(Sigma_{t-1}, fp32(1e-3) I).  Returns means [H+1,E], covs [H+1,E,E]."""
+    X = np.asarray(X, dtype=np.float64)
+    E = len(Ky_invs)
+    U = np.asarray(U, dtype=np.float64)
+    H, m = U.shape
+    means = np.zeros((H + 1, E)); covs = np.zeros((H + 1, E, E))
+    means[0] = x0
+    covs[0] = STATE0_VAR * np.eye(E)
+    for t in range(1, H + 1):
+        u = np.concatenate([means[t - 1], U[t - 1]])
+        S = np.zeros((E + m, E + m))
+        S[:E, :E] = covs[t - 1]
+        S[E:, E:] = ACTION_VAR * np.eye(m)
+        means[t], covs[t] = moment_match_full(X, Ky_invs, betas, lambdas, sigma_fs, u, S, use_c=use_c)
+    return means, covs
+
+
+def rollout_full_cost(X, Ky_invs, betas, lambdas, sigma_fs, x0, U, gamma, Q, R, R_delta=None, last_u=None,
+                      x_ref=None, u_ref=None, use_c=False):
+    """Cost of a control sequence under the full-covariance rollout (`src/mpc.py:156-200` accepts a full Sigma)."""
+    means, covs = rollout_full(X, Ky_invs, betas, lambdas, sigma_fs, x0, U, use_c=use_c)
+    E = means.shape[1]; m = np.asarray(U).shape[1]
+    xr = np.zeros(E) if x_ref is None else np.asarray(x_ref, dtype=np.float64)
+    ur = np.zeros(m) if u_ref is None else np.asarray(u_ref, dtype=np.float64)
+    return cost(means, U, covs, xr, ur, gamma, Q, R, R_delta, last_u), means, covs
+
+
 def cost(means, U, covs, x_ref, u_ref, gamma, Q, R, R_delta=None, last_u=None):
     """Risk-sensitive cost, `src/mpc.py:156-200`.  covs: [H+1,E,E] (full) or [H+1,E] (diagonal)."""
     means = np.asarray(means, dtype=np.float64)
@@ -243,6 +300,8 @@ def _lib():
         _LIB.oracle_rollout_cost_grad.argtypes = [ctypes.c_int] * 5 + [dp] * 7 + [ctypes.c_double] + \
                                                  [dp] * 10
         _LIB.oracle_rollout_cost_grad.restype = None
+        _LIB.oracle_moment_match_full.argtypes = [ctypes.c_int] * 3 + [dp] * 9
+        _LIB.oracle_moment_match_full.restype = None
         _LIB.oracle_set_threads.argtypes = [ctypes.c_int]
         _LIB.oracle_set_threads.restype = ctypes.c_int
     return _LIB

@@ -239,8 +239,76 @@ def cost_kats():
     return out
 
 
+def fullcov_cases():
+    """Full-covariance rollouts assembled from the reference's NumPy moment-matching functions
+    (`src/tools/uncertainty_prop.py:6-44,91-136,187-236`) exactly as the block the reference left commented out would
+    (`src/dynamics.py:104-121`), and the reference's NumPy cost on the resulting full Sigma (`src/mpc.py:118-154`).
+    `covariance_prop` takes ONE target vector for both GPs, so both outputs are trained on the same targets and differ
+    in their hyper-parameters: fc1 shares the length-scales (different noise), fc2 has distinct ARD length-scales."""
+    out = {}
+    for name, n, lam, sn, seed in [("fc1", 60, [[1.5, 1.5, 1.5]] * 2, [0.1, 0.3], 41),
+                                   ("fc2", 50, [[1.2, 2.2, 0.8], [2.0, 0.9, 1.6]], [0.2, 0.2], 42)]:
+        E, m, H = 2, 1, 3
+        rng = np.random.default_rng(seed)
+        X = rng.uniform(-1, 1, (n, E + m))
+        y = 0.8 * X[:, 0] - 0.3 * X[:, 1] + 0.2 * np.tanh(X @ rng.normal(0, 0.5, E + m)) + 0.05 * rng.normal(size=n)
+        lam = np.array(lam, dtype=np.float64)
+        gps = []
+        for a in range(E):
+            g = GaussianProcessRegression(E + m)
+            g.set_lambdas(np.asarray(lam[a], dtype=np.float64)); g.set_sigma_f(np.float64(1.0)); g.set_sigma_n(np.float64(sn[a]))
+            g.append_train_data(X, y)
+            gps.append(g)
+        Ks = [g.Ky.detach().numpy() for g in gps]
+        Lams = [np.diag(lam[a]) for a in range(E)]
+        x0 = rng.uniform(-0.4, 0.4, E); U = rng.uniform(-0.3, 0.3, (H, m))
+        means = np.zeros((H + 1, E)); covs = np.zeros((H + 1, E, E))
+        means[0] = x0; covs[0] = 1e-3 * np.identity(E)
+        act = (1e-3 * torch.eye(m)).type(torch.float64).numpy()      # fp32 eye promoted, src/dynamics.py:162
+        for t in range(1, H + 1):
+            mean_in = np.concatenate((means[t - 1], U[t - 1]))
+            covar = np.zeros((E + m, E + m)); covar[:E, :E] = covs[t - 1]; covar[E:, E:] = act
+            for a in range(E):
+                means[t, a] = mean_prop(Ks[a], Lams[a], mean_in, covar, X, y)[0]
+                covs[t, a, a] = variance_prop(Ks[a], Lams[a], mean_in, covar, X, y)
+            for i in range(1, E):
+                for j in range(i):
+                    covs[t, i, j] = covs[t, j, i] = covariance_prop(Ks[i], Ks[j], Lams[i], Lams[j], mean_in, covar, X, y)
+        Q = np.array([[2.0, 0.3], [0.3, 1.5]]); R = 0.05 * np.eye(m)
+        xref = np.array([0.1, -0.05]); uref = np.array([0.02])
+        costs = {}
+        for gamma in (-1.0, 0.7):
+            mpc = RiskSensitiveMPC(gamma, H, E, m, Q, R)
+            costs[gamma] = mpc.cost(means, U, covs, xref, uref)
+        out.update({f"{name}_X": X, f"{name}_y": y, f"{name}_lam": lam, f"{name}_sn": np.array([g.get_sigma_n() for g in gps]),
+                    f"{name}_x0": x0, f"{name}_U": U, f"{name}_means": means, f"{name}_covs": covs, f"{name}_Q": Q,
+                    f"{name}_R": R, f"{name}_xref": xref, f"{name}_uref": uref,
+                    f"{name}_cost_gm1": costs[-1.0], f"{name}_cost_gp07": costs[0.7]})
+        print(name, "cov[H]", covs[H].tolist(), "cost", costs)
+    return out
+
+
+def fnom_case():
+    """predict_latent_vars with a nominal model, `src/gpr.py:305-309` (residual form)."""
+    rng = np.random.default_rng(13)
+    n, D = 45, 3
+    X = rng.normal(size=(n, D)); y = X[:, 0] * 0.6 + np.sin(X.sum(1)) * 0.3 + 0.05 * rng.normal(size=n)
+    f_nom = lambda Z: 0.5 * Z[:, :1] + 0.1          # noqa: E731  (n, 1), like y_train
+    g = GaussianProcessRegression(D, nominal_model=f_nom)
+    g.set_lambdas(np.array([0.9, 1.4, 2.0])); g.set_sigma_f(np.float64(1.1)); g.set_sigma_n(np.float64(0.15))
+    g.append_train_data(X, y)
+    Xp = rng.normal(size=(6, D))
+    mean, cov = g.predict_latent_vars(Xp, covar=True, targets=True)
+    return {"fn_X": X, "fn_y": y, "fn_lam": g.get_lambdas(), "fn_sf": g.get_sigma_f(), "fn_sn": g.get_sigma_n(),
+            "fn_Xp": Xp, "fn_mean": mean, "fn_cov_targets": cov}
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
+    np.savez_compressed(os.path.join(OUT, "fullcov.npz"), **fullcov_cases())
+    np.savez_compressed(os.path.join(OUT, "gpr_fnom.npz"), **fnom_case())
+    if "--new-only" in sys.argv:
+        sys.exit(0)
     np.savez_compressed(os.path.join(OUT, "gpr.npz"), **gpr_cases())
     np.savez_compressed(os.path.join(OUT, "moment_matching.npz"), **mm_cases())
     np.savez_compressed(os.path.join(OUT, "rollout.npz"), **rollout_cases())

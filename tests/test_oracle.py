@@ -183,3 +183,69 @@ def test_marginal_likelihood_and_reference_gradient():
         assert abs(fd - g["hy_dlam"][k]) < 1e-5 * max(1, abs(fd))
     fd = (orc.marginal_likelihood(X, y, lam, sf * np.exp(h), sn_eff) - orc.marginal_likelihood(X, y, lam, sf * np.exp(-h), sn_eff)) / (2 * h)
     assert abs(fd - float(g["hy_dsf"])) < 1e-5 * abs(fd)
+
+
+# ---- round 2: full-covariance rollout and the staged reference ------------------------------------
+def _fullcov_setup(g, name):
+    X, y, lam = g[f"{name}_X"], g[f"{name}_y"], g[f"{name}_lam"]
+    sn = g[f"{name}_sn"]
+    fits = [orc.fit(X, y, lam[a], 1.0, float(np.float32(float(sn[a]) ** 2)) ** 0.5) for a in range(2)]
+    return X, lam, [f["Ky_inv"] for f in fits], [f["beta"] for f in fits]
+
+
+@pytest.mark.parametrize("name", ["fc1", "fc2"])
+@pytest.mark.parametrize("use_c", [False, True])
+def test_full_covariance_rollout_vs_reference_numpy_functions(name, use_c):
+    """oracle.rollout_full / the C restatement against rollouts assembled from the reference's NumPy mean_prop /
+    variance_prop / covariance_prop (shared and distinct length-scales), and the reference's NumPy cost on the full Sigma."""
+    g = golden("fullcov")
+    X, lam, Kis, betas = _fullcov_setup(g, name)
+    means, covs = orc.rollout_full(X, Kis, betas, lam, np.ones(2), g[f"{name}_x0"], g[f"{name}_U"], use_c=use_c)
+    np.testing.assert_allclose(means, g[f"{name}_means"], rtol=1e-8, atol=1e-11)
+    np.testing.assert_allclose(covs, g[f"{name}_covs"], rtol=1e-6, atol=1e-10)
+    for key, gamma in (("cost_gm1", -1.0), ("cost_gp07", 0.7)):
+        c = orc.cost(means, g[f"{name}_U"], covs, g[f"{name}_xref"], g[f"{name}_uref"], gamma, g[f"{name}_Q"], g[f"{name}_R"])
+        assert abs(c - float(g[f"{name}_{key}"])) <= 1e-8 * abs(float(g[f"{name}_{key}"]))
+
+
+def test_full_covariance_step_equals_variance_only_step_on_the_diagonal():
+    """With a diagonal input covariance the diagonal of the full-covariance step is the variance-only step."""
+    rng = np.random.default_rng(3)
+    n, E, m = 80, 3, 1
+    D = E + m
+    X = rng.uniform(-1, 1, (n, D)); Y = rng.normal(size=(n, E)) * 0.3
+    lam = rng.uniform(0.8, 2.0, (E, D)); sf = np.array([1.0, 1.2, 0.9])
+    fits = [orc.fit(X, Y[:, a], lam[a], sf[a], 0.2) for a in range(E)]
+    u = rng.normal(size=D) * 0.3; s = rng.uniform(1e-3, 0.05, D)
+    mean, cov = orc.moment_match_full(X, [f["Ky_inv"] for f in fits], [f["beta"] for f in fits], lam, sf, u, np.diag(s), use_c=True)
+    for a in range(E):
+        mo, vo, _ = orc.c_moment_match_diag(X, fits[a]["Ky_inv"], fits[a]["beta"], lam[a], sf[a], u, s)
+        assert abs(mean[a] - mo) < 1e-12 and abs(cov[a, a] - vo) < 1e-11
+
+
+def test_staged_reference_matches_the_oracle():
+    """oracle/_ref (what `bench.py --impl reference` times) is the reference: its objective / gradient agree with the
+    C oracle on a seeded problem.  Skipped where the reference checkout was never staged."""
+    import os
+    import subprocess
+    import sys
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(os.path.join(root, "oracle", "_ref", "src", "mpc.py")):
+        pytest.skip("oracle/_ref not staged")
+    r = subprocess.run([sys.executable, os.path.join(root, "oracle", "ref_runner.py"), "--n", "96", "--H", "2", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-800:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    sys.path.insert(0, root)
+    from bench import synth
+    n, E, m, H = 96, 4, 1, 2
+    S, A, nxt, rng = synth(n, E, m, 0)
+    x0 = rng.uniform(-0.5, 0.5, E)
+    U = np.random.default_rng(1).uniform(-0.3, 0.3, (1, H * m))[0].reshape(H, m)
+    X = np.concatenate([S, A], 1)
+    lam = np.full((E, E + m), 2.0)
+    fits = [orc.fit(X, nxt[:, a], lam[a], 1.0, float(np.float32(0.1 ** 2)) ** 0.5) for a in range(E)]
+    c, _, _, _ = orc.c_rollout_cost_grad(X, [f["Ky_inv"] for f in fits], [f["beta"] for f in fits], lam, np.ones(E),
+                                         x0, U, -1.0, 2 * np.eye(E), 0.01 * np.eye(m))
+    assert abs(out["runs"]["2"]["cost"] - c) <= 1e-8 * max(1.0, abs(c)), (out["runs"]["2"]["cost"], c)
