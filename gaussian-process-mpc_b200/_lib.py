@@ -34,6 +34,9 @@ SIGNATURES = {
     "gpmpc_moment_match_raw": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P, c_double, _P, _P, _P, _P]),
     "gpmpc_covariance_raw": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, c_double, c_double, _P, _P,
                                      c_double, c_double, c_int, _P]),
+    "gpmpc_rollout_full": (c_int, [_P, c_int, c_int, _P, _P, _P, _P]),
+    "gpmpc_rollout_full_vjp": (c_int, [_P, c_int, c_int, _P, _P, _P, _P]),
+    "gpmpc_rollout_cost_grad_full": (c_int, [_P, c_int, c_int] + [_P] * 13),
     "gpmpc_rollout": (c_int, [_P, c_int, c_int, _P, _P, _P, _P]),
     "gpmpc_rollout_vjp": (c_int, [_P, c_int, c_int, _P, _P, _P, _P]),
     "gpmpc_rollout_cost_grad": (c_int, [_P, c_int, c_int] + [_P] * 13),

@@ -31,10 +31,12 @@ def _nvcc():
 
 def _jobs():
     jobs = []
-    for name in ("api", "fit", "gemm", "rollout"):
+    for name in ("api", "fit", "gemm", "rollout", "fullcov"):
         jobs.append((os.path.join(CSRC, name + ".cu"), os.path.join(OBJ, name + ".o"), []))
     for d in PAIR_DIMS:
         jobs.append((os.path.join(CSRC, "mm_pairs_inst.cu"), os.path.join(OBJ, f"mm_pairs_D{d}.o"),
+                     [f"-DGPMPC_INST_D={d}"]))
+        jobs.append((os.path.join(CSRC, "mm_full_inst.cu"), os.path.join(OBJ, f"mm_full_D{d}.o"),
                      [f"-DGPMPC_INST_D={d}"]))
     return jobs
 

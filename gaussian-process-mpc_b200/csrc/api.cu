@@ -57,7 +57,8 @@ extern "C" int gpmpc_destroy(gpmpc_handle h)
     cudaStreamSynchronize(h->stream);
     for (DevBuf *b : {&h->X, &h->Y, &h->Kinv, &h->Wt, &h->beta, &h->chol, &h->zt, &h->tt, &h->linv, &h->info, &h->hyp,
                       &h->mu, &h->var, &h->tape, &h->cst, &h->part, &h->mpart, &h->stage_in, &h->stage_out, &h->gbuf,
-                      &h->tickets, &h->dbg})
+                      &h->tickets, &h->dbg, &h->Wx, &h->fc_plan, &h->fc_mu, &h->fc_cov, &h->fc_cst, &h->fc_raw, &h->fc_part,
+                      &h->fc_red, &h->fc_gbar, &h->fc_seed, &h->fc_carry, &h->fc_io})
         b->release();
     for (cudaStream_t st : h->aux_streams) cudaStreamDestroy(st);
     for (cudaEvent_t ev : h->aux_events) cudaEventDestroy(ev);
@@ -766,7 +767,7 @@ static void full_setup(int D, const double *lam, const double *u, const double *
 }  // namespace gpmpc
 
 static int moment_match_impl(gpmpc_handle h, int B, const double *U, const double *S, int s_is_full,
-                             double *mean, double *var, double *cov);
+                             double *mean, double *var);
 static int cov_core(gpmpc_ctx *h, int n, int D, const double *l1, const double *l2, const double *uh, const double *Sh,
                     const double *Xd, const double *b1, const double *b2, double mean1, double mean2, double sf1,
                     double sf2, int bugcompat, double *rows, double *scal, double *out_host);
@@ -774,22 +775,15 @@ static int cov_core(gpmpc_ctx *h, int n, int D, const double *l1, const double *
 extern "C" int gpmpc_moment_match(gpmpc_handle h, int B, const double *U, const double *S, int s_is_full,
                                   double *mean, double *var)
 {
-    return moment_match_impl(h, B, U, S, s_is_full, mean, var, nullptr);
-}
-
-extern "C" int gpmpc_moment_match_cov(gpmpc_handle h, int B, const double *U, const double *S, double *mean,
-                                      double *cov)
-{
-    if (!cov) return fail(h, GPMPC_ERR_INVALID, "gpmpc_moment_match_cov: cov is null");
-    return moment_match_impl(h, B, U, S, 1, mean, nullptr, cov);
+    return moment_match_impl(h, B, U, S, s_is_full, mean, var);
 }
 
 static int moment_match_impl(gpmpc_handle h, int B, const double *U, const double *S, int s_is_full,
-                             double *mean, double *var, double *cov)
+                             double *mean, double *var)
 {
     if (!h) return GPMPC_ERR_INVALID;
     if (!h->fitted) return fail(h, GPMPC_ERR_NOT_FIT, "gpmpc_moment_match: not fitted");
-    if (B <= 0 || !U || !S || !mean || (!var && !cov)) return fail(h, GPMPC_ERR_INVALID, "gpmpc_moment_match: bad argument");
+    if (B <= 0 || !U || !S || !mean || !var) return fail(h, GPMPC_ERR_INVALID, "gpmpc_moment_match: bad argument");
     GP_CUDA(h, cudaSetDevice(h->device));
     const int D = h->D, E = h->E, n = h->n, ld = h->ld;
     if (!s_is_full) {
@@ -801,56 +795,13 @@ static int moment_match_impl(gpmpc_handle h, int B, const double *U, const doubl
         if (!is_device_ptr(S)) { GP_CUDA(h, cudaMemcpyAsync(st + (size_t)B * D, S, (size_t)B * D * sizeof(double), cudaMemcpyHostToDevice, h->stream)); Sd = st + (size_t)B * D; }
         return gpmpc_moment_match_diag_internal(h, B, Ud, Sd, mean, var);
     }
-    // full covariance: generic kernels, one (input, output) at a time
-    std::vector<double> Uh((size_t)B * D), Sh((size_t)B * D * D), mh((size_t)B * E), vh((size_t)B * E);
-    int rc;
-    if ((rc = fetch_host(h, U, Uh.data(), Uh.size()))) return rc;
-    if ((rc = fetch_host(h, S, Sh.data(), Sh.size()))) return rc;
-    GP_CUDA(h, h->gbuf.reserve(((size_t)2 * ld + 8) * sizeof(double)));
-    double *rows = h->gbuf.as<double>(), *bl = rows + ld, *scal = bl + ld;
-    const size_t mat = (size_t)ld * ld;
+    // full input covariance: the batched full-covariance step (fullcov.cu); the variances are the diagonal of its result
+    std::vector<double> ch((size_t)B * E * E), vh((size_t)B * E);
+    int rc = gpmpc_moment_match_cov(h, B, U, S, mean, ch.data());
+    if (rc) return rc;
     for (int b = 0; b < B; ++b)
-        for (int a = 0; a < E; ++a) {
-            FullSetup fs;
-            full_setup(D, h->lam_prop[a], &Uh[(size_t)b * D], &Sh[(size_t)b * D * D], h->sf_prop[a], fs);
-            mean_full_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->X.as<double>(), n, fs.mean_arg, fs.mean_pref,
-                                                                    h->beta.as<double>() + (size_t)a * ld, nullptr, bl);
-            GP_LAUNCH_CHECK(h);
-            sum_kernel<<<1, 1024, 0, h->stream>>>(bl, n, scal);
-            GP_LAUNCH_CHECK(h);
-            pairs_full_kernel<false><<<(n + 7) / 8, 256, 0, h->stream>>>(h->X.as<double>(), n, fs.var_arg,
-                                                                         h->Wt.as<double>() + a * wt_doubles(ld), ld, nullptr, rows);
-            GP_LAUNCH_CHECK(h);
-            sum_kernel<<<1, 1024, 0, h->stream>>>(rows, n, scal + 1);
-            GP_LAUNCH_CHECK(h);
-            double r2[2];
-            GP_CUDA(h, cudaMemcpyAsync(r2, scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-            GP_CUDA(h, cudaStreamSynchronize(h->stream));
-            const double m = r2[0];
-            mh[(size_t)b * E + a] = m;
-            vh[(size_t)b * E + a] = h->sf_prop[a] * h->sf_prop[a] - fs.var_pref * r2[1] - m * m;
-        }
-    std::vector<double> ch;
-    if (cov) {
-        // full E x E output covariance: variances on the diagonal, cross-covariances from the published formula
-        ch.assign((size_t)B * E * E, 0.0);
-        for (int b = 0; b < B; ++b)
-            for (int a = 0; a < E; ++a) {
-                ch[((size_t)b * E + a) * E + a] = vh[(size_t)b * E + a];
-                for (int c2 = a + 1; c2 < E; ++c2) {
-                    double c = 0.0;
-                    if ((rc = cov_core(h, n, D, h->lam_prop[a], h->lam_prop[c2], &Uh[(size_t)b * D], &Sh[(size_t)b * D * D],
-                                       h->X.as<double>(), h->beta.as<double>() + (size_t)a * ld,
-                                       h->beta.as<double>() + (size_t)c2 * ld, mh[(size_t)b * E + a], mh[(size_t)b * E + c2],
-                                       h->sf_prop[a], h->sf_prop[c2], 0, rows, scal, &c))) return rc;
-                    ch[((size_t)b * E + a) * E + c2] = c;
-                    ch[((size_t)b * E + c2) * E + a] = c;
-                }
-            }
-        GP_CUDA(h, cudaMemcpyAsync(cov, ch.data(), ch.size() * sizeof(double), cudaMemcpyDefault, h->stream));
-    }
-    GP_CUDA(h, cudaMemcpyAsync(mean, mh.data(), mh.size() * sizeof(double), cudaMemcpyDefault, h->stream));
-    if (var) GP_CUDA(h, cudaMemcpyAsync(var, vh.data(), vh.size() * sizeof(double), cudaMemcpyDefault, h->stream));
+        for (int a = 0; a < E; ++a) vh[(size_t)b * E + a] = ch[((size_t)b * E + a) * E + a];
+    GP_CUDA(h, cudaMemcpyAsync(var, vh.data(), vh.size() * sizeof(double), cudaMemcpyDefault, h->stream));
     GP_CUDA(h, cudaStreamSynchronize(h->stream));
     return GPMPC_OK;
 }

@@ -80,6 +80,13 @@ struct gpmpc_ctx {
     gpmpc::DevBuf mu, var, tape, cst, part, mpart, stage_in, stage_out, gbuf, tickets, dbg;
     int tape_B = 0, tape_H = 0;    // shape of the tape held from the last rollout
 
+    // full-covariance rollout (fullcov.cu): cross-output weights (built lazily, rebuilt when Wt changes), the plan
+    // descriptors on the device and the workspaces of the forward / backward sweeps
+    long long weights_epoch = 0;   // bumped by derive_weights (any change of Wt / beta / propagation lambdas)
+    long long cross_epoch = -1;    // weights_epoch the cross weights were built for
+    gpmpc::DevBuf Wx, fc_plan, fc_mu, fc_cov, fc_cst, fc_raw, fc_part, fc_red, fc_gbar, fc_seed, fc_carry, fc_io;
+    int fc_B = 0, fc_H = 0;        // shape of the full-covariance tape held from the last gpmpc_rollout_full
+
     // auxiliary streams / events: independent outputs are fitted concurrently (fit.cu)
     std::vector<cudaStream_t> aux_streams;
     std::vector<cudaEvent_t> aux_events;

@@ -335,6 +335,7 @@ int derive_weights(gpmpc_ctx *h, int a)
                                                        h->beta.as<double>() + (size_t)a * h->ld,
                                                        h->Wt.as<double>() + a * wt_doubles(h->ld), h->ld);
     GP_LAUNCH_CHECK(h);
+    h->weights_epoch++;             // cross-output weights derived from beta / lambda are stale now (fullcov.cu)
     return GPMPC_OK;
 }
 

@@ -120,8 +120,26 @@ int gpmpc_moment_match(gpmpc_handle h, int B, const double *U, const double *S, 
 /* Same for a FULL input covariance S[B,D,D], returning the full E x E output covariance cov[B,E,E]: variances on
  * the diagonal and cross-covariances beta_a^T Qt beta_b - m_a m_b off it (src/tools/uncertainty_prop.py:187-236,
  * the formula-correct NumPy form).  This is the moment-matching step of a full-covariance rollout, which the
- * reference leaves as a TODO (src/dynamics.py:184); generic kernels, not the batched hot path.               */
+ * reference leaves as a TODO (src/dynamics.py:184); all B inputs are evaluated by one batched launch sequence.  */
 int gpmpc_moment_match_cov(gpmpc_handle h, int B, const double *U, const double *S, double *mean, double *cov);
+
+/* FULL-covariance moment-matched rollout of B control sequences: Sigma_t keeps the cross-covariances between the
+ * outputs; the input covariance of step t is blockdiag(Sigma_{t-1}, fp32(1e-3) I) (the wiring the reference left
+ * commented out, src/dynamics.py:104-121,184, with the cross term of src/tools/uncertainty_prop.py:187-236).
+ *   x0[B,E], U[B,H,m]  ->  means[B,H+1,E], covs[B,H+1,E,E]
+ * gpmpc_rollout_full_vjp: vector-Jacobian product of the last gpmpc_rollout_full (reverse mode with recomputation):
+ *   gmeans[B,H+1,E], gcovs[B,H+1,E,E] (either may be NULL)  ->  gU[B,H,m], gx0[B,E] (may be NULL).               */
+int gpmpc_rollout_full(gpmpc_handle h, int B, int H, const double *x0, const double *U, double *means, double *covs);
+int gpmpc_rollout_full_vjp(gpmpc_handle h, int B, int H, const double *gmeans, const double *gcovs, double *gU,
+                           double *gx0);
+
+/* Fused objective + gradient under the full-covariance rollout: same arguments as gpmpc_rollout_cost_grad, the cost
+ * is src/mpc.py:156-200 evaluated on the full Sigma_t (which that function already accepts, :182-185);
+ * covs[B,H+1,E,E] (may be NULL).                                                                               */
+int gpmpc_rollout_cost_grad_full(gpmpc_handle h, int B, int H, const double *x0, const double *U,
+                                 const double *gamma, const double *Q, const double *R, const double *Rdelta,
+                                 const double *last_u, const double *xref, const double *uref, double *cost,
+                                 double *grad, double *means, double *covs);
 
 /* Stateless form of the same two functions for caller-supplied matrices (no handle state is used except
  * the device/stream): Kinv[n,n], lambdas[D], u[D], S[D,D] full, X[n,D], y[n].
