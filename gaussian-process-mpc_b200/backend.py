@@ -201,10 +201,35 @@ class GPBundle:
               "gpmpc_rollout_vjp")
         return gU, gx0
 
+    def rollout_full(self, x0, U, out_device=True):
+        """Full-covariance rollout: x0 [B,E], U [B,H,m] -> means [B,H+1,E], covs [B,H+1,E,E]; keeps the tape for
+        rollout_full_vjp."""
+        self._sync_stream()
+        x0 = as_f64(x0); U = as_f64(U)
+        B, H = U.shape[0], U.shape[1]
+        if out_device:
+            means = torch.empty((B, H + 1, self.E), dtype=F64, device=self.device)
+            covs = torch.empty((B, H + 1, self.E, self.E), dtype=F64, device=self.device)
+        else:
+            means = np.empty((B, H + 1, self.E)); covs = np.empty((B, H + 1, self.E, self.E))
+        check(self.h, self.lib.gpmpc_rollout_full(self.h, B, H, _ptr(x0), _ptr(U), _ptr(means), _ptr(covs)), "gpmpc_rollout_full")
+        return means, covs
+
+    def rollout_full_vjp(self, B, H, gmeans, gcovs, want_gx0=False):
+        self._sync_stream()
+        gm = None if gmeans is None else as_f64(gmeans)
+        gc = None if gcovs is None else as_f64(gcovs)
+        gU = torch.empty((B, H, self.m), dtype=F64, device=self.device)
+        gx0 = torch.empty((B, self.E), dtype=F64, device=self.device) if want_gx0 else None
+        check(self.h, self.lib.gpmpc_rollout_full_vjp(self.h, B, H, _ptr(gm), _ptr(gc), _ptr(gU), _ptr(gx0)),
+              "gpmpc_rollout_full_vjp")
+        return gU, gx0
+
     def cost_grad(self, x0, U, gamma, Q, R, R_delta=None, last_u=None, x_ref=None, u_ref=None, want_grad=True,
-                  want_traj=False, host_out=True):
+                  want_traj=False, host_out=True, full=False):
         """Fused objective + gradient.  x0 [B,E], U [B,H,m], gamma [B].  Host (numpy) inputs are staged by
-        the library; outputs are numpy when host_out else device tensors."""
+        the library; outputs are numpy when host_out else device tensors.  full=True propagates the full E x E state
+        covariance (the 4th return value is then covs [B,H+1,E,E] instead of variances [B,H+1,E])."""
         self._sync_stream()
         x0 = as_f64(x0); U = as_f64(U); gamma = as_f64(gamma)
         B, H = U.shape[0], U.shape[1]
@@ -216,19 +241,21 @@ class GPBundle:
             lu = as_f64(last_u).reshape(B, self.m)
         xr = np.zeros(self.E) if x_ref is None else as_f64(x_ref).reshape(self.E)
         ur = np.zeros(self.m) if u_ref is None else as_f64(u_ref).reshape(self.m)
+        vshape = (B, H + 1, self.E, self.E) if full else (B, H + 1, self.E)
         if host_out:
             cost = np.empty(B)
             grad = np.empty((B, H, self.m)) if want_grad else None
             means = np.empty((B, H + 1, self.E)) if want_traj else None
-            vars_ = np.empty((B, H + 1, self.E)) if want_traj else None
+            vars_ = np.empty(vshape) if want_traj else None
         else:
             cost = torch.empty(B, dtype=F64, device=self.device)
             grad = torch.empty((B, H, self.m), dtype=F64, device=self.device) if want_grad else None
             means = torch.empty((B, H + 1, self.E), dtype=F64, device=self.device) if want_traj else None
-            vars_ = torch.empty((B, H + 1, self.E), dtype=F64, device=self.device) if want_traj else None
-        check(self.h, self.lib.gpmpc_rollout_cost_grad(self.h, B, H, _ptr(x0), _ptr(U), _ptr(gamma), _ptr(Q), _ptr(R),
-                                                       _ptr(Rd), _ptr(lu), _ptr(xr), _ptr(ur), _ptr(cost), _ptr(grad),
-                                                       _ptr(means), _ptr(vars_)), "gpmpc_rollout_cost_grad")
+            vars_ = torch.empty(vshape, dtype=F64, device=self.device) if want_traj else None
+        fn = self.lib.gpmpc_rollout_cost_grad_full if full else self.lib.gpmpc_rollout_cost_grad
+        check(self.h, fn(self.h, B, H, _ptr(x0), _ptr(U), _ptr(gamma), _ptr(Q), _ptr(R), _ptr(Rd), _ptr(lu), _ptr(xr),
+                         _ptr(ur), _ptr(cost), _ptr(grad), _ptr(means), _ptr(vars_)),
+              "gpmpc_rollout_cost_grad_full" if full else "gpmpc_rollout_cost_grad")
         return cost, grad, means, vars_
 
     # ------------------------------------------------------------------------------------

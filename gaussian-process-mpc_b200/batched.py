@@ -31,8 +31,9 @@ class BatchedRollouts:
     `Dynamics`."""
 
     def __init__(self, dynamics=None, Q=None, R=None, R_delta=None, x_ref=None, u_ref=None, evaluate_fn=None,
-                 group=None):
+                 group=None, full=False):
         self.dynamics = dynamics
+        self.full = bool(full)          # propagate the full E x E state covariance (BASELINE config 4)
         self.Q, self.R, self.R_delta = Q, R, R_delta
         self.x_ref, self.u_ref = x_ref, u_ref
         self.group = group
@@ -44,7 +45,7 @@ class BatchedRollouts:
         dyn._require_data()
         dyn._sync_propagation_hypers()
         cost, grad, _, _ = dyn._bundle.cost_grad(x0, U, gamma, self.Q, self.R, self.R_delta, last_u, self.x_ref,
-                                                 self.u_ref, want_grad=want_grad, host_out=host_out)
+                                                 self.u_ref, want_grad=want_grad, host_out=host_out, full=self.full)
         dyn._tape_serial += 1
         return cost, grad
 

@@ -38,6 +38,31 @@ class _Rollout(torch.autograd.Function):
         return None, gx0[0], gU[0]
 
 
+class _RolloutFull(torch.autograd.Function):
+    """means, covs = full-covariance rollout(x0, actions) with d/d actions and d/d x0 from gpmpc_rollout_full_vjp."""
+
+    @staticmethod
+    def forward(ctx, dyn, x0, actions):
+        means, covs = dyn._bundle.rollout_full(x0[None, :], actions[None, :, :])
+        dyn._tape_serial += 1
+        ctx.dyn = dyn
+        ctx.serial = dyn._tape_serial
+        ctx.save_for_backward(x0, actions)
+        return means[0], covs[0]
+
+    @staticmethod
+    def backward(ctx, gmeans, gcovs):
+        dyn = ctx.dyn
+        x0, actions = ctx.saved_tensors
+        H = actions.shape[0]
+        if ctx.serial != dyn._tape_serial:           # another rollout overwrote the tape: replay forward
+            dyn._bundle.rollout_full(x0[None, :], actions[None, :, :])
+            dyn._tape_serial += 1
+            ctx.serial = dyn._tape_serial
+        gU, gx0 = dyn._bundle.rollout_full_vjp(1, H, gmeans.contiguous()[None], gcovs.contiguous()[None], want_gx0=True)
+        return None, gx0[0], gU[0]
+
+
 class Dynamics(object):
 
     def __init__(self, state_dim, action_dim, nominal_models=None):
@@ -130,15 +155,20 @@ class Dynamics(object):
             raise RuntimeError("no training data: call append_train_data first")
 
     # ---- rollouts -------------------------------------------------------------------------------
-    def forward_propagate_torch(self, horizon, curr_state, actions):
+    def forward_propagate_torch(self, horizon, curr_state, actions, full=False):
         """Variance-only moment-matched rollout (`src/dynamics.py:126-191`).
 
         Returns (list of H+1 mean tensors [E], list of H+1 covariance tensors [E,E]); autograd flows from
-        `actions` (and `curr_state`) through the device adjoint."""
+        `actions` (and `curr_state`) through the device adjoint.  full=True keeps the cross-covariances between the
+        outputs (the reference's TODO at `src/dynamics.py:184`): Sigma_t is then a full matrix."""
         self._require_data()
         self._sync_propagation_hypers()
         x0 = curr_state.to(self.device).type(F64)
         U = actions.to(self.device).type(F64)[:horizon]
+        if full:
+            means, covs = _RolloutFull.apply(self, x0, U)
+            return ([curr_state] + [means[t] for t in range(1, horizon + 1)],
+                    [covs[t] for t in range(horizon + 1)])
         means, vars_ = _Rollout.apply(self, x0, U)
         state_means = [curr_state] + [means[t] for t in range(1, horizon + 1)]
         state_covars = [1e-3 * torch.eye(self.state_dim, device=self.device).type(F64)]
@@ -164,22 +194,12 @@ class Dynamics(object):
     def forward_propagate_full(self, horizon, curr_state, actions):
         """Full-covariance moment-matched rollout (the reference's TODO at `src/dynamics.py:184`):
         Sigma_t keeps the cross-covariances between the outputs, computed with the published formula
-        (`src/tools/uncertainty_prop.py:187-236`).  Forward values only (NumPy arrays (H+1, E), (H+1, E, E));
-        the input covariance is blockdiag(Sigma_{t-1}, fp32(1e-3) I) as in the variance-only rollout."""
+        (`src/tools/uncertainty_prop.py:187-236`); the input covariance is blockdiag(Sigma_{t-1}, fp32(1e-3) I) as in
+        the variance-only rollout.  NumPy arrays (H+1, E), (H+1, E, E); one batched device rollout."""
         self._require_data()
         self._sync_propagation_hypers()
-        E, m = self.state_dim, self.action_dim
-        means = np.zeros((horizon + 1, E)); covs = np.zeros((horizon + 1, E, E))
-        means[0] = np.asarray(curr_state, dtype=np.float64).reshape(E)
-        covs[0] = 1e-3 * np.eye(E)
-        U = np.asarray(actions, dtype=np.float64).reshape(-1, m)
-        act_var = float(np.float32(1e-3))
-        for t in range(1, horizon + 1):
-            u = np.concatenate([means[t - 1], U[t - 1]])[None, :]
-            S = np.zeros((1, E + m, E + m))
-            S[0, :E, :E] = covs[t - 1]
-            S[0, E:, E:] = act_var * np.eye(m)
-            mu, cov = self._bundle.moment_match_cov(u, S)
-            means[t], covs[t] = mu[0], cov[0]
+        x0 = np.asarray(curr_state, dtype=np.float64).reshape(1, self.state_dim)
+        U = np.asarray(actions, dtype=np.float64).reshape(1, -1, self.action_dim)[:, :horizon]
+        means, covs = self._bundle.rollout_full(x0, U, out_device=False)
         self._tape_serial += 1
-        return means, covs
+        return means[0], covs[0]

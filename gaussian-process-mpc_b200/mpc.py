@@ -54,6 +54,8 @@ class RiskSensitiveMPC:
         self.ub = [1e16 for _ in range(self.input_dim)]
         self.lb = [-1e16 for _ in range(self.input_dim)]
         self.train_empty = True
+        # extension (off by default = the reference's variance-only rollout): propagate the full state covariance
+        self.full_covariance = False
         self.n_evals = 0
         self._host_cache = {}
 
@@ -135,7 +137,8 @@ class RiskSensitiveMPC:
         cost, grad, _, _ = dyn._bundle.cost_grad(x0, U, np.array([float(self.gamma)]), self._host("Q", self.Q),
                                                  self._host("R", self.R),
                                                  None if self.R_delta is None else self._host("R_delta", self.R_delta),
-                                                 last_u, self._host("x_ref", self.x_ref), self._host("u_ref", self.u_ref))
+                                                 last_u, self._host("x_ref", self.x_ref), self._host("u_ref", self.u_ref),
+                                                 full=self.full_covariance)
         dyn._tape_serial += 1
         self.n_evals += 1
         self.curr_cost = float(cost[0])

@@ -1031,3 +1031,186 @@ def test_hyper_key_detects_reassignment_and_call_time_hypers(gp):
     u = torch.zeros(D, dtype=torch.float64, device="cuda:0", requires_grad=True)
     with pytest.raises(RuntimeError):
         mean_prop_torch(T(Kinv), T(lam2), u, T(0.1 * np.eye(D)), T(X), T(y), 1.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# Round 2: full-covariance rollout (BASELINE configs[3])
+# ------------------------------------------------------------------------------------------------
+def _fullcov_dynamics(gp, g, name):
+    """Two outputs trained on the SAME targets (the reference's covariance_prop takes one target vector)."""
+    X, y, lam, sn = g[f"{name}_X"], g[f"{name}_y"], g[f"{name}_lam"], g[f"{name}_sn"]
+    dyn = gp.Dynamics(2, 1)
+    for a in range(2):
+        dyn.gpr_err[a].set_lambdas(np.asarray(lam[a], dtype=np.float64)); dyn.gpr_err[a].set_sigma_n(np.float64(sn[a]))
+    dyn.append_train_data(X[:, :2], X[:, 2:], np.stack([y, y], axis=1))
+    return dyn
+
+
+@pytest.mark.parametrize("name", ["fc1", "fc2"])
+def test_full_covariance_rollout_vs_reference_numpy_functions(gp, name):
+    """Rollouts assembled from the reference's OWN NumPy mean_prop / variance_prop / covariance_prop (tests/golden/
+    make_golden.py: fullcov_cases) and its NumPy cost on the full Sigma; fc1 = shared length-scales (symmetric sweep),
+    fc2 = distinct ARD length-scales (all n x n tiles)."""
+    g = golden("fullcov")
+    dyn = _fullcov_dynamics(gp, g, name)
+    H = g[f"{name}_U"].shape[0]
+    means, covs = dyn.forward_propagate_full(H, g[f"{name}_x0"], g[f"{name}_U"])
+    norm_close(means, g[f"{name}_means"], 1e-8)
+    assert np.max(np.abs(covs - g[f"{name}_covs"])) <= RTOL * max(np.max(np.abs(g[f"{name}_covs"])), 1e-3)
+    for key, gamma in (("cost_gm1", -1.0), ("cost_gp07", 0.7)):
+        br = gp.BatchedRollouts(dyn, g[f"{name}_Q"], g[f"{name}_R"], x_ref=g[f"{name}_xref"], u_ref=g[f"{name}_uref"], full=True)
+        c, _ = br.cost_and_grad(g[f"{name}_x0"], g[f"{name}_U"][None], gamma, host_out=True)
+        close(c[0], float(g[f"{name}_{key}"]), RTOL)
+
+
+@pytest.mark.parametrize("case", ["ard_E3_m2", "shared_E4_m1", "mixed_E3_m1"])
+def test_full_covariance_cost_gradient_vs_oracle_and_finite_differences(gp, case):
+    """Cost and gradient of the full-covariance rollout: values against the NumPy/C oracle (oracle.rollout_full_cost),
+    the adjoint against central differences of the ORACLE cost (a few components) and of the device cost (all)."""
+    from oracle import oracle as orc
+    rng = np.random.default_rng({"ard_E3_m2": 1, "shared_E4_m1": 2, "mixed_E3_m1": 3}[case])
+    if case == "ard_E3_m2":
+        n, E, m, H, B = 150, 3, 2, 4, 5
+        lam = rng.uniform(1.0, 3.0, (E, E + m)); sf = rng.uniform(0.8, 1.3, E); sn = rng.uniform(0.08, 0.2, E)
+        Qm = rng.normal(size=(E, E)) * 0.3; Q = Qm @ Qm.T + 1.5 * np.eye(E)
+        Rm = rng.normal(size=(m, m)) * 0.1; R = Rm @ Rm.T + 0.05 * np.eye(m)
+        Rd = 0.3 * np.eye(m) + 0.05
+    elif case == "shared_E4_m1":
+        n, E, m, H, B = 333, 4, 1, 5, 40           # 40 rollouts: two 32-lane chunks, the second ragged
+        lam = np.full((E, E + m), 2.0); sf = np.ones(E); sn = np.full(E, 0.1)
+        Q = 2.0 * np.eye(E); R = 0.01 * np.eye(m); Rd = None
+    else:
+        n, E, m, H, B = 97, 3, 1, 3, 3             # outputs 0 and 2 share their length-scales, output 1 differs
+        l0 = rng.uniform(1.0, 3.0, E + m)
+        lam = np.stack([l0, rng.uniform(1.0, 3.0, E + m), l0]); sf = np.array([1.0, 1.2, 0.9]); sn = np.array([0.1, 0.15, 0.2])
+        Q = 2.0 * np.eye(E); R = 0.01 * np.eye(m); Rd = None
+    S, A, nxt, _ = _synth(n, E, m, seed=17)
+    dyn = gp.Dynamics(E, m)
+    for a in range(E):
+        dyn.gpr_err[a].set_lambdas(lam[a].astype(np.float64)); dyn.gpr_err[a].set_sigma_f(np.float64(sf[a]))
+        dyn.gpr_err[a].set_sigma_n(np.float64(sn[a]))
+    dyn.append_train_data(S, A, nxt)
+    X = np.concatenate([S, A], 1)
+    fits = [orc.fit(X, nxt[:, a], lam[a], sf[a], float(np.float32(sn[a] ** 2)) ** 0.5) for a in range(E)]
+    Kis = [f["Ky_inv"] for f in fits]; betas = [f["beta"] for f in fits]
+    x0 = rng.uniform(-0.5, 0.5, (B, E)); U = rng.uniform(-0.3, 0.3, (B, H, m))
+    gamma = np.where(np.arange(B) % 2 == 0, -1.0, 0.6)
+    xref = rng.uniform(-0.2, 0.2, E); uref = rng.uniform(-0.1, 0.1, m)
+    last_u = rng.uniform(-0.3, 0.3, (B, m)) if Rd is not None else None
+    br = gp.BatchedRollouts(dyn, Q, R, Rd, xref, uref, full=True)
+    cost, grad = br.cost_and_grad(x0, U, gamma, last_u, host_out=True)
+    _, _, means, covs = dyn._bundle.cost_grad(x0, U, gamma, Q, R, Rd, last_u, xref, uref, want_traj=True, full=True)
+
+    def oracle_cost(b, Ub):
+        return orc.rollout_full_cost(X, Kis, betas, lam, sf, x0[b], Ub, gamma[b], Q, R, Rd, None if last_u is None else last_u[b],
+                                     xref, uref, use_c=True)
+    for b in ([0, 1, B - 1] if B > 3 else range(B)):
+        c, mo, co = oracle_cost(b, U[b])
+        norm_close(means[b], mo, 1e-8)
+        assert np.max(np.abs(covs[b] - co)) <= RTOL * max(np.max(np.abs(co)), 1e-3)
+        close(cost[b], c, RTOL)
+    # adjoint vs central differences of the ORACLE (rollout 0, two components)
+    h = 1e-5
+    for idx in [(0, 0), (H - 1, m - 1)]:
+        Up, Um = U[0].copy(), U[0].copy()
+        Up[idx] += h; Um[idx] -= h
+        fd = (oracle_cost(0, Up)[0] - oracle_cost(0, Um)[0]) / (2 * h)
+        assert abs(grad[0][idx] - fd) <= 1e-5 * max(1.0, np.max(np.abs(grad[0]))), (idx, grad[0][idx], fd)
+    # adjoint vs central differences of the device cost (rollout 1, every component)
+    b = 1
+    Upm = np.repeat(U[b:b + 1], 2 * H * m, axis=0)
+    for k in range(H * m):
+        Upm[2 * k].reshape(-1)[k] += h; Upm[2 * k + 1].reshape(-1)[k] -= h
+    rep = lambda v: np.repeat(v[b:b + 1], 2 * H * m, axis=0)          # noqa: E731
+    cp, _ = br.cost_and_grad(rep(x0), Upm, rep(gamma), None if last_u is None else rep(last_u), host_out=True)
+    fd = (cp[0::2] - cp[1::2]) / (2 * h)
+    norm_close(grad[b].reshape(-1), fd, 2e-5)
+    # determinism and independence of the batch neighbours
+    cost2, grad2 = br.cost_and_grad(x0, U, gamma, last_u, host_out=True)
+    assert np.array_equal(cost, cost2) and np.array_equal(grad, grad2)
+    c1, g1 = br.cost_and_grad(x0[1:2], U[1:2], gamma[1:2], None if last_u is None else last_u[1:2], host_out=True)
+    close(c1, cost[1:2], 1e-11); norm_close(g1, grad[1:2], 1e-10)
+
+
+def test_full_covariance_autograd_through_forward_propagate_torch(gp):
+    """forward_propagate_torch(..., full=True): autograd from a scalar function of ALL means and covariances flows to the
+    actions and the initial state through gpmpc_rollout_full_vjp; checked against central differences."""
+    n, E, m, H = 120, 3, 1, 3
+    dyn, S, A, nxt, rng = _synth_dynamics(gp, n, E, m, seed=23, lam=1.7)
+    Wm = rng.normal(size=(H + 1, E)); Wc = rng.normal(size=(H + 1, E, E))
+
+    def loss_np(x0, U):
+        means, covs = dyn.forward_propagate_full(H, x0, U)
+        return float(np.sum(Wm * means) + np.sum(Wc * covs))
+    x0 = rng.uniform(-0.4, 0.4, E); U = rng.uniform(-0.3, 0.3, (H, m))
+    xt = T(x0).requires_grad_(True); Ut = T(U).requires_grad_(True)
+    means, covs = dyn.forward_propagate_torch(H, xt, Ut, full=True)
+    loss = sum((T(Wm[t]) * means[t]).sum() + (T(Wc[t]) * covs[t]).sum() for t in range(H + 1))
+    close(loss.item(), loss_np(x0, U), 1e-10)
+    loss.backward()
+    h = 1e-5
+    for k in range(H * m):
+        d = np.zeros(H * m); d[k] = h
+        fd = (loss_np(x0, U + d.reshape(H, m)) - loss_np(x0, U - d.reshape(H, m))) / (2 * h)
+        assert abs(Ut.grad.reshape(-1)[k].item() - fd) <= 2e-6 * max(1.0, abs(fd)), (k, Ut.grad.reshape(-1)[k].item(), fd)
+    for k in range(E):
+        d = np.zeros(E); d[k] = h
+        # covs[0] = 1e-3 I and means[0] = x0 itself: the t = 0 terms contribute Wm[0] directly
+        fd = (loss_np(x0 + d, U) - loss_np(x0 - d, U)) / (2 * h)
+        assert abs(xt.grad[k].item() - fd) <= 2e-6 * max(1.0, abs(fd)), (k, xt.grad[k].item(), fd)
+
+
+def test_batched_full_covariance_moment_matching_vs_oracle(gp):
+    """gpmpc_moment_match_cov: 70 Gaussian inputs with full covariances in one batched call against the oracle."""
+    from oracle import oracle as orc
+    n, E, m, B = 210, 3, 2, 70
+    D = E + m
+    rng = np.random.default_rng(29)
+    S, A, nxt, _ = _synth(n, E, m, seed=29)
+    lam = rng.uniform(0.8, 2.5, (E, D)); sf = np.array([1.0, 1.1, 0.9]); sn = np.full(E, 0.15)
+    dyn = gp.Dynamics(E, m)
+    for a in range(E):
+        dyn.gpr_err[a].set_lambdas(lam[a]); dyn.gpr_err[a].set_sigma_f(np.float64(sf[a])); dyn.gpr_err[a].set_sigma_n(np.float64(sn[a]))
+    dyn.append_train_data(S, A, nxt)
+    X = np.concatenate([S, A], 1)
+    fits = [orc.fit(X, nxt[:, a], lam[a], sf[a], float(np.float32(sn[a] ** 2)) ** 0.5) for a in range(E)]
+    U = rng.uniform(-0.5, 0.5, (B, D))
+    Am = rng.normal(size=(B, D, D)) * 0.15
+    Sin = Am @ np.transpose(Am, (0, 2, 1)) + 0.01 * np.eye(D)
+    mean, cov = dyn._bundle.moment_match_cov(U, Sin)
+    mean_v, var_v = dyn._bundle.moment_match(U, Sin, out_device=False)          # full S, variances only
+    for b in (0, 31, 32, 69):
+        mo, co = orc.moment_match_full(X, [f["Ky_inv"] for f in fits], [f["beta"] for f in fits], lam, sf, U[b], Sin[b], use_c=True)
+        norm_close(mean[b], mo, 1e-8)
+        assert np.max(np.abs(cov[b] - co)) <= RTOL * max(np.max(np.abs(co)), 1e-3)
+    assert np.array_equal(mean_v, mean) and np.array_equal(var_v, np.einsum("baa->ba", cov))
+
+
+def test_config4_full_covariance_step_n16384(gp):
+    """configs[3] size: one full-covariance step (H = 1) at n = 16384, E = 4, 32 rollouts, against the C oracle's literal
+    double loops (host LU inverse), plus the gradient of the H = 2 cost against central differences."""
+    from oracle import oracle as orc
+    n, E, m = 16384, 4, 1
+    dyn, S, A, nxt, rng = _synth_dynamics(gp, n, E, m, seed=0)
+    X = np.concatenate([S, A], 1)
+    lam = np.full((E, E + m), 2.0)
+    Kinv = np.linalg.inv(_host_gram(X, lam[0], 1.0, float(np.float32(0.1 ** 2))))
+    betas = [Kinv @ nxt[:, a] for a in range(E)]
+    B = 32
+    x0 = rng.uniform(-0.5, 0.5, (B, E)); U = rng.uniform(-0.3, 0.3, (B, 2, m))
+    Q = 2 * np.eye(E); R = 0.01 * np.eye(m)
+    br = gp.BatchedRollouts(dyn, Q, R, full=True)
+    means, covs = dyn._bundle.rollout_full(x0, U[:, :1], out_device=False)
+    for b in (0, 31):
+        u = np.concatenate([x0[b], U[b, 0]])
+        Sin = np.diag(np.concatenate([np.full(E, 1e-3), np.full(m, float(np.float32(1e-3)))]))
+        mo, co = orc.moment_match_full(X, [Kinv] * E, betas, lam, np.ones(E), u, Sin, use_c=True)
+        norm_close(means[b, 1], mo, 1e-8)
+        assert np.max(np.abs(covs[b, 1] - co)) <= RTOL * max(np.max(np.abs(co)), 1e-3)
+    cost, grad = br.cost_and_grad(x0, U, -1.0, host_out=True)
+    h = 1e-4
+    d = rng.normal(size=(2, m)); d /= np.linalg.norm(d)
+    cpm, _ = br.cost_and_grad(x0[:2].repeat(2, axis=0)[[0, 1]] * 0 + x0[0], np.stack([U[0] + h * d, U[0] - h * d]), -1.0, host_out=True)
+    fd = (cpm[0] - cpm[1]) / (2 * h)
+    an = float(np.sum(grad[0] * d))
+    assert abs(fd - an) <= 1e-4 * max(1.0, abs(an)), (fd, an)

@@ -77,7 +77,7 @@ class _FakeBundle:
         self.calls = 0
 
     def cost_grad(self, x0, U, gamma, Q, R, R_delta=None, last_u=None, x_ref=None, u_ref=None, want_grad=True,
-                  want_traj=False, host_out=True):
+                  want_traj=False, host_out=True, full=False):
         self.calls += 1
         U = np.asarray(U); x0 = np.asarray(x0)
         return (U ** 2).sum(axis=(1, 2)) + x0.sum(axis=1), 2 * U, None, None
