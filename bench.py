@@ -32,9 +32,26 @@ if ROOT not in sys.path:
 
 METRIC = "gp_mpc_rollout_cost_grad_evals_per_sec"
 UNIT = "evals/s"
-# FP64-pipe instructions per pair for D=5 with 4 outputs sharing one exp ("pair kernel"):
-# 14 (q, q^2, sum) + 11 (table exp) + 4 * 12 (w, T, N1[5], N2[5])
-OPS_PER_PAIR_GROUP4 = 14 + 11 + 4 * 12
+
+
+def pair_ops_per_eval(D, E, m, H, first_step_const=True):
+    """FP64-pipe instructions per (rollout, pair) of one H-step evaluation for outputs sharing one exp:
+    chain (D adds, D squares, D-1 adds) + 11 (table exp) per pair, and per output w, T, N1_k (every input dimension)
+    and N2_k (state dimensions only); the first step keeps only N1 of the action dimensions (x0, Sigma_0 constant)."""
+    chain = 3 * D - 1 + 11
+    full = chain + E * (2 + D + (D - m))
+    first = chain + E * (2 + m) if first_step_const else full
+    return first + (H - 1) * full if H >= 1 else 0
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, taken from the committed ncu capture that
+    profiles/ncu_traffic.json points at (never a constant typed into this file)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel]
+        return t["dram_bytes_per_launch"], t["source"]
+    except Exception:
+        return None, None
 
 
 def synth(n, E, m, seed=0):
@@ -298,8 +315,15 @@ def run_ours(args):
     bundle.set_pair_timing(False)                          # armed timers synchronise after every horizon step
     fma_tflops, exp_gops = bundle.measure_fp64_peak()
     pairs = pair_evals / E                                 # (rollout, pair) evaluations, 4 outputs each
-    achieved_tflops = pairs * OPS_PER_PAIR_GROUP4 * 2.0 / (pair_ms * 1e-3) / 1e12
+    pairs_per_rollout_step = n * (n + 1) / 2
+    assert abs(pairs - Bl * H * pairs_per_rollout_step) < 1e-6 * pairs
+    ops = pair_ops_per_eval(D, E, m, H) if not args.ard else H * (3 * D - 1 + 11 + 2 + D + (D - m)) * E
+    achieved_tflops = Bl * pairs_per_rollout_step * ops * 2.0 / (pair_ms * 1e-3) / 1e12
     bytes_algo = H * E * (n * (n + 1) / 2) * 8.0           # Wt upper triangle once per step and output
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    nominal_tflops = sms * 64 * 2 * sm_mhz * 1e6 / 1e12      # 64 FP64 FMA / clk / SM at the sampled SM clock
+    traffic, traffic_src = ncu_traffic("mm_pairs_batch")
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -309,10 +333,14 @@ def run_ours(args):
     roofline = {
         "bound": "fp64_pipe", "kernel": "mm_pairs_batch<5,4,grad>", "achieved": achieved_tflops, "peak": fma_tflops,
         "unit": "TFLOP/s", "frac": achieved_tflops / fma_tflops if fma_tflops else None,
-        "traffic": 460.8e6,       # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/r01e_*)
-        "note": "FP64-pipe instructions (x2 flop) per launch / CUDA-event duration of the pair kernel; peak = DFMA rate "
-                "measured live by gpmpc_measure_fp64_peak (MEASURED_PEAKS.json has no fp64 figure); this kernel is "
-                "neither HBM- nor tensor-bound (see DESIGN.md)",
+        "peak_nominal": nominal_tflops, "frac_nominal": achieved_tflops / nominal_tflops,
+        "traffic": traffic, "traffic_source": traffic_src,
+        "fp64_instr_per_pair_per_eval": ops,
+        "survey_convention": {"flop_per_pair": 36, "achieved": Bl * H * E * pairs_per_rollout_step * 36 / (pair_ms * 1e-3) / 1e12,
+                              "unit": "TFLOP/s", "note": "SURVEY 8(d): P = H E n(n+1)/2 pairs x 36 flop (exp counted as 1)"},
+        "note": "executed FP64-pipe instructions (x2 flop) per launch / CUDA-event duration of the pair kernel; `peak` = DFMA "
+                "rate measured live by gpmpc_measure_fp64_peak (MEASURED_PEAKS.json has no fp64 figure), `peak_nominal` = "
+                "SMs x 64 FMA x 2 x sampled SM clock; this kernel is neither HBM- nor tensor-bound (see DESIGN.md)",
         "pair_kernel_ms_per_eval": pair_ms, "pair_kernel_share_of_step": pair_ms / (ms / args.steps),
         "launches_per_eval": H, "fp64_exp_gops_measured": exp_gops,
         "hbm": {"achieved": bytes_algo / (pair_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -363,13 +391,14 @@ def run_ours(args):
         line["roofline_single"] = {
             "bound": "hbm", "kernel": "mm_step_single<5,4,grad> (B=1: one fused launch per horizon step)",
             "achieved": bytes_algo / (single_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-            "frac": bytes_algo / (single_ms * 1e-3) / 1e9 / hbm_peak, "traffic": 271.0e6,
+            "frac": bytes_algo / (single_ms * 1e-3) / 1e9 / hbm_peak,
+            "traffic": ncu_traffic("mm_step_single")[0], "traffic_source": ncu_traffic("mm_step_single")[1],
             "ms_per_launch": single_ms / H,
             "note": "algorithmic bytes = H*E*n(n+1)/2*8 (Wt upper triangle once per step) / CUDA-event time of the H "
                     "launches of one B=1 evaluation (events on the library stream, programmatic dependent launch off "
-                    "between timed launches); traffic = dram__bytes_read+write per launch from profiles/r01d_*"}
+                    "between timed launches)"}
         line["single_solve"] = {"objective_plus_gradient_ms": 1e3 * float(np.median(lat)),
-                                "solve_p50_ms": 1e3 * float(np.median([t for t, _ in solves])),
+                                "solve_p50_ms_lbfgsb_surrogate": 1e3 * float(np.median([t for t, _ in solves])),
                                 "evals_per_solve": [k for _, k in solves], "solver": solver,
                                 "note": "B=1 path (one fused launch per horizon step), wall clock incl. host<->device copies"}
 
@@ -431,10 +460,206 @@ def run_ours(args):
             cpu_baseline_section()
         except Exception as ex:
             line["cpu_baseline"] = {"error": repr(ex)}
+    if rank == 0 and world == 1 and not args.no_extras:
+        # the other BASELINE configurations, in a subprocess: nothing that happens there can cost the headline line
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--section", "extras"], capture_output=True, text=True,
+                               timeout=900)
+            ex = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+            line["configs"] = {k: ex[k] for k in ("1", "2", "4", "5") if k in ex}
+            line["fit"] = ex.get("fit")
+        except Exception as ex:                  # noqa: BLE001
+            line["configs"] = {"error": repr(ex)[-400:]}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def make_dynamics(gp, n, E, m, ard=False, seed=0):
+    S, A, nxt, rng = synth(n, E, m, seed)
+    dyn = gp.Dynamics(E, m)
+    for a in range(E):
+        dyn.gpr_err[a].set_lambdas(np.full(E + m, 2.0 + (0.1 * a if ard else 0.0))); dyn.gpr_err[a].set_sigma_n(np.float64(0.1))
+    t0 = time.perf_counter()
+    dyn.append_train_data(S, A, nxt)
+    dyn._bundle.synchronize()
+    return dyn, (S, A, nxt), rng, time.perf_counter() - t0
+
+
+def run_config5(args):
+    """BASELINE configs[4]: a gamma sweep x initial states, every (gamma, x0) an independent MPC problem (n=4096, H=30),
+    solved in lock step per GPU by BatchedSolver and partitioned over the ranks (GP replicated, one all-gather of the
+    solutions).  Prints one JSON line: solves/s (whole job) and the rollout evaluations/s behind it."""
+    import torch
+    import gpmpc_b200 as gp
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    n, E, m, H = args.n, 4, 1, args.H
+    dyn, _, rng, t_fit = make_dynamics(gp, n, E, m)
+    Q = 2 * np.eye(E); R = 0.01 * np.eye(m)
+    gammas = np.array([-2.0, -1.0, 0.5, 1.0])
+    n_x0 = args.instances // len(gammas)
+    starts = rng.uniform(-0.5, 0.5, (n_x0, E))
+    G, I = np.meshgrid(gammas, np.arange(n_x0), indexing="ij")
+    gam = G.reshape(-1); x0 = starts[I.reshape(-1)]
+    B = gam.size
+    br = gp.BatchedRollouts(dyn, Q, R)
+    # warm-up: one batched evaluation of this rank's shard size (kernel selection, workspaces)
+    nb = len(gp.shard_indices(B, world, rank))
+    br.cost_and_grad(x0[:nb], np.zeros((nb, H, m)), gam[:nb], host_out=True)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    solver = gp.BatchedSolver(br, H, m, lb=[-1.0], ub=[1.0], max_iter=40, gtol=1e-4)
+    if world > 1:
+        sol = solver.solve_sharded(x0, gam)
+    else:
+        r = solver.solve(x0, gam)
+        sol = {"U": r["U"], "cost": r["cost"], "converged": r["converged"], "iters_per_rank": np.array([r["iters"]]),
+               "rollout_evals": r["rollout_evals"]}
+    e1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        print(json.dumps({
+            "metric": "gp_mpc_closed_form_solves_per_sec", "value": B / (ms * 1e-3), "unit": "solves/s", "n_gpus": world,
+            "ms_total": ms, "higher_is_better": True, "scaling": "strong", "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"config5: gamma sweep {gammas.tolist()} x {n_x0} initial states = {B} MPC instances, n={n} "
+                                   f"E=4 m=1 H={H}, projected L-BFGS in lock step per GPU (gtol 1e-4, max 40 iterations)",
+                       "sharding": f"instances interleaved over {world} rank(s), GP replicated, one all-gather of U/cost"},
+            "rollout_evals_per_sec": sol["rollout_evals"] / (ms * 1e-3),
+            "rollout_evals_per_instance": sol["rollout_evals"] / B,
+            "converged_fraction": float(np.mean(sol["converged"])), "iterations_per_rank": sol["iters_per_rank"].tolist(),
+            "fit_s": t_fit}), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_extras(args):
+    """The other BASELINE configurations and the "next" rows on ONE GPU (run as a subprocess of the default bench so that
+    a failure here can never cost the headline line).  Prints one JSON dict."""
+    import torch
+    import gpmpc_b200 as gp
+    torch.cuda.set_device(0)
+    out = {}
+
+    def timed(fn, reps=2):
+        fn(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter(); fn(); torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
+        return min(ts)
+
+    def section(name, fn):
+        try:
+            out[name] = fn()
+        except Exception as ex:                  # noqa: BLE001
+            out[name] = {"error": repr(ex)[-400:]}
+        torch.cuda.empty_cache()
+
+    def config1():
+        g = np.load(os.path.join(ROOT, "tests", "golden", "shipped.npz"))
+        mpc = gp.RiskSensitiveMPC(-1, 6, 2, 2, 2 * np.identity(2), np.zeros((2, 2)), None)
+        for i in range(2):
+            mpc.dynamics.gpr_err[i].set_sigma_n(np.float64(g["ship_sn"][i]))
+            mpc.dynamics.gpr_err[i].set_lambdas(np.asarray(g["ship_lam"][i], dtype=np.float64))
+            mpc.dynamics.gpr_err[i].set_sigma_f(np.float64(g["ship_sf"][i]))
+        mpc.dynamics.append_train_data(g["ship_S"], g["ship_A"], g["ship_next"])
+        mpc.set_xref(np.array([0., 0.])); mpc.set_uref(np.array([0., 0.])); mpc.set_lb([-1.0, -1.0]); mpc.set_ub([1.0, 1.0])
+        mpc.curr_state = torch.tensor(g["ship_x0"], device="cuda")
+        x = g["ship_U0"].reshape(-1).copy()
+        for _ in range(3):
+            mpc.objective(x); mpc.gradient(x)
+        ts = []
+        for i in range(50):
+            xi = x + 1e-4 * i
+            t0 = time.perf_counter(); mpc.objective(xi); mpc.gradient(xi); ts.append(time.perf_counter() - t0)
+        st = []
+        for i in range(5):
+            n0 = mpc.n_evals; t0 = time.perf_counter(); mpc.get_optimal_trajectory(g["ship_x0"]); st.append((time.perf_counter() - t0, mpc.n_evals - n0))
+        return {"workload": "the reference's own experiment (shipped data): n=400 E=2 m=2 H=6 gamma=-1",
+                "objective_plus_gradient_ms": 1e3 * float(np.median(ts)),
+                "solve_p50_ms_lbfgsb_surrogate": 1e3 * float(np.median([t for t, _ in st])), "evals_per_solve": [k for _, k in st]}
+
+    def config2():
+        dyn, _, rng, tf = make_dynamics(gp, 2048, 4, 1)
+        U = torch.tensor(rng.uniform(-0.5, 0.5, (8192, 5)), device="cuda"); Sd = torch.tensor(rng.uniform(1e-3, 5e-2, (8192, 5)), device="cuda")
+        t = timed(lambda: dyn._bundle.moment_match(U, Sd, out_device=True), 3)
+        return {"workload": "n=2048 D=5 E=4, 8192 uncertain inputs (mean + variance)", "ms_per_batch": 1e3 * t,
+                "inputs_per_sec": 8192 / t, "fit_s_cold": tf}
+
+    def config4():
+        dyn, _, rng, tf = make_dynamics(gp, 16384, 4, 1)
+        t0 = time.perf_counter(); dyn._fit_all(); dyn._bundle.synchronize(); t_fit = time.perf_counter() - t0
+        Q = 2 * np.eye(4); R = 0.01 * np.eye(1)
+        H = 20
+        res = {"workload": "n=16384 E=4 m=1 H=20", "fit_s_warm": t_fit, "fit_s_cold": tf}
+        for B, full in ((128, True), (256, False)):
+            U = torch.tensor(rng.uniform(-0.3, 0.3, (B, H, 1)), device="cuda"); x0 = torch.tensor(rng.uniform(-0.5, 0.5, (B, 4)), device="cuda")
+            gm = torch.full((B,), -1.0, dtype=torch.float64, device="cuda")
+            t = timed(lambda: dyn._bundle.cost_grad(x0, U, gm, Q, R, host_out=False, full=full), 1)
+            key = "full_covariance" if full else "variance_only"
+            res[key] = {"B": B, "s_per_eval_batch": t, "evals_per_sec": B / t}
+            if full:
+                # FP64-pipe instructions per (rollout, pair) and step, D=5, 10 pair-outputs sharing one exp (DESIGN.md 5.6):
+                # forward 14 + 11 + 10, backward 14 + 11 + 10 + 1 + 5 + 5 + 15 (the z_i / z_j transforms are extra)
+                ops = (35 + 61) * H
+                pairs = 16384 * 16385 / 2
+                tf64 = B * pairs * ops * 2 / t / 1e12
+                peak, _ = dyn._bundle.measure_fp64_peak()
+                res[key].update({"fp64_tflops": tf64, "fp64_peak_measured": peak, "fp64_frac": tf64 / peak,
+                                 "fp64_frac_nominal": tf64 / 37.2, "fp64_instr_per_pair_step": 96})
+        return res
+
+    def config5():
+        dyn, _, rng, tf = make_dynamics(gp, 4096, 4, 1)
+        br = gp.BatchedRollouts(dyn, 2 * np.eye(4), 0.01 * np.eye(1))
+        gammas = np.array([-2.0, -1.0, 0.5, 1.0]); starts = rng.uniform(-0.5, 0.5, (128, 4))
+        G, I = np.meshgrid(gammas, np.arange(128), indexing="ij")
+        solver = gp.BatchedSolver(br, 30, 1, lb=[-1.0], ub=[1.0], max_iter=40, gtol=1e-4)
+        t0 = time.perf_counter(); sol = solver.solve(starts[I.reshape(-1)], G.reshape(-1)); t = time.perf_counter() - t0
+        return {"workload": "512 MPC instances (4 gammas x 128 x0), n=4096 H=30, lock-step projected L-BFGS, one GPU",
+                "solves_per_sec": G.size / t, "s_total": t, "rollout_evals_per_instance": sol["rollout_evals"] / G.size,
+                "converged_fraction": float(sol["converged"].mean())}
+
+    def fit_n2_n3():
+        res = {}
+        for ard in (False, True):
+            dyn, _, rng, tf = make_dynamics(gp, 4096, 4, 1, ard=ard)
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter(); dyn._fit_all(); dyn._bundle.synchronize(); ts.append(time.perf_counter() - t0)
+            key = "distinct_hypers" if ard else "shared_hypers"
+            # DMMA work counted as n^3 per factorisation (Cholesky n^3/3 + triangular inverse n^3/3 + Z^T Z n^3/3)
+            nfac = 4 if ard else 1
+            res[key] = {"n": 4096, "outputs": 4, "warm_ms": 1e3 * min(ts), "factorisations": nfac,
+                        "dmma_frac_of_nominal": nfac * 4096.0 ** 3 / min(ts) / 37.2e12}
+        ts = []
+        for _ in range(5):
+            s = rng.uniform(-1, 1, 4); a = rng.uniform(-1, 1, 1)
+            t0 = time.perf_counter(); dyn.append_train_data(s, a, 0.9 * s); dyn._bundle.synchronize(); ts.append(time.perf_counter() - t0)
+        res["n2_append_ms"] = 1e3 * float(np.median(ts))
+        g = dyn.gpr_err[0]
+        t0 = time.perf_counter(); g.update_hyperparams(num_iters=5, verbose=False); dyn._bundle.synchronize()
+        res["n3_adam_step_ms"] = 1e3 * (time.perf_counter() - t0) / 5
+        return res
+
+    section("1", config1); section("2", config2); section("4", config4); section("5", config5); section("fit", fit_n2_n3)
+    print(json.dumps(out), flush=True)
 
 
 def main():
@@ -449,9 +674,17 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--ard", action="store_true", help="distinct length-scales per output (not the headline workload)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configurations (configs 1, 2, 4, 5, fit)")
+    ap.add_argument("--section", default="", choices=["", "extras"], help="internal: run one secondary section and print its JSON")
+    ap.add_argument("--config", type=int, default=3, choices=[3, 5], help="3 = headline rollout benchmark, 5 = sharded MPC solves")
+    ap.add_argument("--instances", type=int, default=2048, help="--config 5: number of MPC instances (4 gammas x instances/4 x0)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.section == "extras":
+        run_extras(args)
+    elif args.config == 5:
+        run_config5(args)
     else:
         run_ours(args)
 

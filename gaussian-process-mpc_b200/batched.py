@@ -16,6 +16,13 @@ import torch
 from .backend import F64
 
 
+def shard_indices(B: int, world: int, rank: int):
+    """Interleaved shard of B problems for `rank`: problems rank, rank + world, ...  Used for SOLVES, whose cost
+    varies from problem to problem (a gamma sweep laid out gamma-major would otherwise give one rank all the hard
+    ones); rollout evaluations cost the same and use the contiguous `shard_range`."""
+    return np.arange(int(rank), int(B), int(world))
+
+
 def shard_range(B: int, world: int, rank: int):
     """Contiguous shard [lo, hi) of B rollouts for `rank` of `world`; the first B % world ranks get one more."""
     base, extra = divmod(int(B), int(world))
@@ -229,3 +236,44 @@ class BatchedSolver:
             active &= ~(stalled | small)
         return {"U": X.reshape(B, self.H, self.m), "cost": F, "iters": it, "evals": self.n_evals,
                 "rollout_evals": self.n_rollout_evals, "converged": converged}
+
+    def solve_sharded(self, x0, gamma, U0=None, last_u=None, group=None):
+        """Many independent MPC problems over the ranks of a process group (BASELINE configs[4]: a gamma sweep x initial
+        states "partitioned across the 8 GPUs"): every rank passes the SAME problem list, solves its interleaved shard
+        with its own replica of the GP (no communication while solving: the problems are independent, so the lock
+        step is per shard and a slow problem never stalls another GPU), and ONE all-gather returns U, cost and the
+        convergence flags of all problems on every rank."""
+        import torch.distributed as dist
+        x0 = np.asarray(x0, dtype=np.float64)
+        gamma = np.asarray(gamma, dtype=np.float64)
+        B = x0.shape[0] if x0.ndim == 2 else int(gamma.size)
+        if x0.ndim == 1:
+            x0 = np.broadcast_to(x0, (B, x0.shape[0])).copy()
+        gamma = np.broadcast_to(gamma, (B,)).copy()
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        idx = shard_indices(B, world, rank)
+        n = self.H * self.m
+        per = (B + world - 1) // world
+        on_gpu = dist.get_backend(group) == "nccl"
+        dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
+        packed = torch.zeros((per, n + 4), dtype=F64)          # [U | cost | converged | iterations | rollout evals]
+        if idx.size:
+            sol = self.solve(x0[idx], gamma[idx], None if U0 is None else np.asarray(U0)[idx],
+                             None if last_u is None else np.asarray(last_u)[idx])
+            packed[:idx.size, :n] = torch.from_numpy(sol["U"].reshape(idx.size, n))
+            packed[:idx.size, n] = torch.from_numpy(sol["cost"])
+            packed[:idx.size, n + 1] = torch.from_numpy(sol["converged"].astype(np.float64))
+            packed[:idx.size, n + 2] = float(sol["iters"])
+            packed[:idx.size, n + 3] = float(sol["rollout_evals"]) / idx.size
+        packed = packed.to(dev)
+        gathered = torch.empty((world * per, n + 4), dtype=F64, device=dev)
+        dist.all_gather_into_tensor(gathered, packed, group=group)
+        g = gathered.cpu().numpy().reshape(world, per, n + 4)
+        U = np.zeros((B, n)); cost = np.zeros(B); conv = np.zeros(B, dtype=bool); iters = np.zeros(world); revals = 0.0
+        for r in range(world):
+            ir = shard_indices(B, world, r)
+            U[ir] = g[r, :ir.size, :n]; cost[ir] = g[r, :ir.size, n]; conv[ir] = g[r, :ir.size, n + 1] > 0.5
+            if ir.size:
+                iters[r] = g[r, 0, n + 2]; revals += g[r, 0, n + 3] * ir.size
+        return {"U": U.reshape(B, self.H, self.m), "cost": cost, "converged": conv, "iters_per_rank": iters,
+                "rollout_evals": revals}

@@ -175,6 +175,52 @@ def test_sharded_gather_world2_gloo(B):
     assert out[0][1] + out[1][1] == B        # shards cover the batch exactly once
 
 
+def _solve_rank_main(rank, world, port, B, out):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from gpmpc_b200 import BatchedRollouts, BatchedSolver, shard_indices
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    H, m = 3, 2
+    n = H * m
+    rng = np.random.default_rng(0)
+    A = rng.normal(size=(B, n, n)); Q = np.einsum("bij,bkj->bik", A, A) + 0.5 * np.eye(n)
+    c = rng.normal(size=(B, n)) * 3
+    seen = []
+
+    def fake(x0, U, gamma, last_u=None, host_out=True, want_grad=True):
+        ids = np.rint(x0[:, 0]).astype(int)            # the problem index travels in x0
+        seen.extend(ids.tolist())
+        u = U.reshape(len(ids), n)
+        QX = np.einsum("bij,bj->bi", Q[ids], u)
+        return 0.5 * np.einsum("bi,bi->b", u, QX) + np.einsum("bi,bi->b", c[ids], u), (QX + c[ids]).reshape(U.shape)
+
+    x0 = np.repeat(np.arange(B, dtype=np.float64)[:, None], 2, axis=1)
+    mk = lambda: BatchedSolver(BatchedRollouts(evaluate_fn=fake), H, m, lb=[-1, -1], ub=[1, 1], max_iter=200, gtol=1e-8)   # noqa: E731
+    sharded = mk().solve_sharded(x0, np.full(B, -1.0))
+    mine = set(seen)
+    single = mk().solve(x0, np.full(B, -1.0))
+    ok = (np.allclose(sharded["cost"], single["cost"], rtol=0, atol=1e-9) and np.allclose(sharded["U"], single["U"], atol=1e-5)
+          and bool(sharded["converged"].all()) and mine == set(shard_indices(B, world, rank).tolist()))
+    out[rank] = ok
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B", [7, 10])
+def test_sharded_solver_world2_gloo(B):
+    """BatchedSolver.solve_sharded: each rank solves only its interleaved shard, one all-gather returns every solution."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_solve_rank_main, args=(r, 2, port, B, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert out[0] and out[1]
+
+
 def test_batched_solver_matches_lbfgsb_on_box_constrained_quadratics():
     """N1 driver (lock-step projected L-BFGS over many problems) against scipy on a fake evaluator."""
     from scipy.optimize import minimize
