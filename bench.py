@@ -415,7 +415,7 @@ def run_ours(args):
                           f"measured per-step increment to {ex['t_full_s']:.1f} s"}
             try:
                 # context only: the same unmodified reference on THIS GPU (it picks cuda:0 when it sees one, src/gpr.py:22)
-                resg = run_ref_runner("cuda", n, [1, 2], 2, 1)
+                resg = run_ref_runner("cuda", n, [1, 2], 3, 3)      # 3 warm-up calls: cuBLAS / cuSOLVER initialisation
                 exg = extrapolate_reference(resg, H)
                 line["reference_on_this_gpu"] = {
                     "value": 1.0 / exg["t_full_s"], "unit": UNIT, "kind": "reference", "linearity": exg,

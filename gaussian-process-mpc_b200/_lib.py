@@ -18,6 +18,7 @@ SIGNATURES = {
     "gpmpc_last_error": (c_char_p, [_P]),
     "gpmpc_set_stream": (c_int, [_P, _P]),
     "gpmpc_synchronize": (c_int, [_P]),
+    "gpmpc_set_option": (c_int, [_P, c_char_p, c_int]),
     "gpmpc_num_train": (c_int, [_P]),
     "gpmpc_fit": (c_int, [_P, c_int, _P, _P, _P, _P, _P]),
     "gpmpc_refit_output": (c_int, [_P, c_int, _P, _P, c_double, c_double]),

@@ -71,6 +71,9 @@ class GPBundle:
         st = torch.cuda.current_stream(self.device).cuda_stream
         check(self.h, self.lib.gpmpc_set_stream(self.h, ctypes.c_void_p(st)), "gpmpc_set_stream")
 
+    def set_option(self, name, value):
+        check(self.h, self.lib.gpmpc_set_option(self.h, name.encode(), int(value)), "gpmpc_set_option")
+
     def synchronize(self):
         check(self.h, self.lib.gpmpc_synchronize(self.h), "gpmpc_synchronize")
 

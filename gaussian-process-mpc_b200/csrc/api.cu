@@ -84,6 +84,13 @@ extern "C" int gpmpc_synchronize(gpmpc_handle h)
     return GPMPC_OK;
 }
 
+extern "C" int gpmpc_set_option(gpmpc_handle h, const char *name, int value)
+{
+    if (!h || !name) return GPMPC_ERR_INVALID;
+    if (std::strcmp(name, "persistent_single") == 0) { h->opt_persistent = value != 0; return GPMPC_OK; }
+    return fail(h, GPMPC_ERR_INVALID, std::string("gpmpc_set_option: unknown option ") + name);
+}
+
 extern "C" int gpmpc_num_train(gpmpc_handle h) { return h ? h->n : GPMPC_ERR_INVALID; }
 
 extern "C" long long gpmpc_launch_count(gpmpc_handle h) { return h ? h->launches : 0; }

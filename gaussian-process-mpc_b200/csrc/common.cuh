@@ -87,6 +87,9 @@ struct gpmpc_ctx {
     gpmpc::DevBuf Wx, fc_plan, fc_mu, fc_cov, fc_cst, fc_raw, fc_part, fc_red, fc_gbar, fc_seed, fc_carry, fc_io;
     int fc_B = 0, fc_H = 0;        // shape of the full-covariance tape held from the last gpmpc_rollout_full
 
+    // gpmpc_set_option
+    bool opt_persistent = true;    // single rollouts: whole horizon in one persistent cooperative launch
+
     // auxiliary streams / events: independent outputs are fitted concurrently (fit.cu)
     std::vector<cudaStream_t> aux_streams;
     std::vector<cudaEvent_t> aux_events;

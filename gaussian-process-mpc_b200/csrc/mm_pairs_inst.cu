@@ -2,6 +2,7 @@
 // D = 2..8 with -DGPMPC_INST_D=<D> so that the seven translation units build in parallel).
 #include "mm_pairs.cuh"
 #include "mm_step_single.cuh"
+#include "mm_rollout_single.cuh"
 #include <type_traits>
 
 #ifndef GPMPC_INST_D
@@ -98,6 +99,39 @@ static cudaError_t launch_any(int EG, int grad_mode, int ns, const Args &a, dim3
     return cudaErrorInvalidValue;
 }
 
+// Persistent whole-horizon kernel (mm_rollout_single.cuh): cooperative launch; returns cudaErrorCooperativeLaunchTooLarge
+// when the grid cannot be co-resident (the caller then falls back to one launch per step).
+template <int D, int EG, int NS>
+static cudaError_t launch_rollout_single_one(const RolloutSingleArgs &a, dim3 grid, cudaStream_t st)
+{
+    const size_t smem = single_smem_bytes<D, EG>();
+    static bool configured[kMaxDevices] = {};
+    static int capacity[kMaxDevices] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= kMaxDevices) dev = 0;
+    if (first_use_on_device(configured)) {
+        cudaError_t e = cudaFuncSetAttribute(mm_rollout_single<D, EG, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int occ = 0, sms = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mm_rollout_single<D, EG, NS>, SINGLE_THREADS, smem);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        capacity[dev] = occ * sms;
+    }
+    if ((long long)grid.x * grid.y > capacity[dev]) return cudaErrorCooperativeLaunchTooLarge;
+    RolloutSingleArgs args = a;
+    void *params[] = {&args};
+    return cudaLaunchCooperativeKernel((const void *)mm_rollout_single<D, EG, NS>, grid, dim3(SINGLE_THREADS), params, smem, st);
+}
+
+template <int D, int EG>
+static cudaError_t launch_rollout_single_eg(int ns, const RolloutSingleArgs &a, dim3 grid, cudaStream_t st)
+{
+    if constexpr (D >= 2) { if (ns == D - 1) return launch_rollout_single_one<D, EG, D - 1>(a, grid, st); }
+    if constexpr (D >= 3) { if (ns == D - 2) return launch_rollout_single_one<D, EG, D - 2>(a, grid, st); }
+    return launch_rollout_single_one<D, EG, D>(a, grid, st);
+}
+
 #define GPMPC_CAT2(a, b) a##b
 #define GPMPC_CAT(a, b) GPMPC_CAT2(a, b)
 cudaError_t GPMPC_CAT(launch_pairs_batch_D, GPMPC_INST_D)(int EG, int grad_mode, int ns, const PairArgs &a,
@@ -109,6 +143,17 @@ cudaError_t GPMPC_CAT(launch_step_single_D, GPMPC_INST_D)(int EG, int grad_mode,
                                                           dim3 grid, cudaStream_t st)
 {
     return launch_any<GPMPC_INST_D, true>(EG, grad_mode, ns, a, grid, st);
+}
+
+cudaError_t GPMPC_CAT(launch_rollout_single_D, GPMPC_INST_D)(int EG, int ns, const RolloutSingleArgs &a, dim3 grid, cudaStream_t st)
+{
+    switch (EG) {
+        case 1: return launch_rollout_single_eg<GPMPC_INST_D, 1>(ns, a, grid, st);
+        case 2: return launch_rollout_single_eg<GPMPC_INST_D, 2>(ns, a, grid, st);
+        case 3: return launch_rollout_single_eg<GPMPC_INST_D, 3>(ns, a, grid, st);
+        case 4: return launch_rollout_single_eg<GPMPC_INST_D, 4>(ns, a, grid, st);
+    }
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace gpmpc

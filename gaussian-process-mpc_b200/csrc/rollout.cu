@@ -18,11 +18,13 @@
 #include "small_linalg.cuh"
 #include "mm_pairs.cuh"
 #include "mm_step_single.cuh"
+#include "mm_rollout_single.cuh"
 
 namespace gpmpc {
 
 #define DECL_LAUNCH(D) cudaError_t launch_pairs_batch_D##D(int, int, int, const PairArgs &, dim3, cudaStream_t); \
-                       cudaError_t launch_step_single_D##D(int, int, int, const SingleStepArgs &, dim3, cudaStream_t);
+                       cudaError_t launch_step_single_D##D(int, int, int, const SingleStepArgs &, dim3, cudaStream_t); \
+                       cudaError_t launch_rollout_single_D##D(int, int, const RolloutSingleArgs &, dim3, cudaStream_t);
 DECL_LAUNCH(2) DECL_LAUNCH(3) DECL_LAUNCH(4) DECL_LAUNCH(5) DECL_LAUNCH(6) DECL_LAUNCH(7) DECL_LAUNCH(8)
 #undef DECL_LAUNCH
 
@@ -50,6 +52,21 @@ static pair_launch_fn single_launcher(int D)
     }
     return nullptr;
 }
+
+typedef cudaError_t (*rollout_single_fn)(int, int, const RolloutSingleArgs &, dim3, cudaStream_t);
+static rollout_single_fn rollout_single_launcher(int D)
+{
+    switch (D) {
+        case 2: return launch_rollout_single_D2; case 3: return launch_rollout_single_D3;
+        case 4: return launch_rollout_single_D4; case 5: return launch_rollout_single_D5;
+        case 6: return launch_rollout_single_D6; case 7: return launch_rollout_single_D7;
+        case 8: return launch_rollout_single_D8;
+    }
+    return nullptr;
+}
+
+// up to this many rollouts the whole horizon runs in one persistent cooperative launch (mm_rollout_single.cuh)
+constexpr int kPersistMaxB = 1;
 
 // below this many rollouts the lanes<->pairs kernel (one rollout per CTA column) replaces the lanes<->rollouts one:
 // measured on B200 at n=4096 it costs 1.55 ms per rollout and evaluation, the batched kernel 174 ms per started
@@ -247,6 +264,11 @@ __global__ void to_external_kernel(const double *__restrict__ src, int B, int Bp
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int e = blockIdx.y;
     if (b < B) dst[(size_t)b * inner + e] = src[(size_t)e * Bpad + b];
+}
+__global__ void poison_on_error_kernel(const int *__restrict__ error, double *__restrict__ mu, double *__restrict__ var, size_t n)
+{
+    if (*error == 0) return;
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) { mu[i] = nan(""); var[i] = nan(""); }
 }
 __global__ void init_state_kernel(const double *__restrict__ x0int, int B, int Bpad, int E, double *__restrict__ mu,
                                   double *__restrict__ var, double var0)
@@ -695,7 +717,8 @@ static int reserve_rollout(gpmpc_ctx *h, int B, int H, RolloutWork &w)
     pair_geometry(h, B, w.total_tiles, w.ctas, w.P);
     const bool few = B < kSingleMaxB;
     const size_t n_groups = (size_t)(w.P + SINGLE_GROUP - 1) / SINGLE_GROUP;
-    const size_t n_tickets = few ? (size_t)B * (1 + n_groups) : (size_t)((B + PAIR_THREADS - 1) / PAIR_THREADS);
+    // few rollouts: [B][1 + groups] arrival counters, then [B] completed steps and one error flag of the persistent kernel
+    const size_t n_tickets = few ? (size_t)B * (1 + n_groups) + B + 1 : (size_t)((B + PAIR_THREADS - 1) / PAIR_THREADS);
     GP_CUDA(h, h->tickets.reserve(n_tickets * sizeof(int)));
     if (few) GP_CUDA(h, cudaMemsetAsync(h->tickets.as<int>(), 0, n_tickets * sizeof(int), h->stream));
     const size_t Bp = d.Bpad;
@@ -753,6 +776,53 @@ static int forward(gpmpc_ctx *h, int B, int H, const double *x0_dev, const doubl
     h->last_pair_ms = 0.0; h->last_pair_evals = 0;
     // few rollouts and one lambda group: the step kernel itself prepares the constants of the following step
     const bool fused_prep = B < kSingleMaxB && d.G == 1;
+    // a single rollout: the whole horizon in one persistent cooperative launch
+    static const bool no_persist = getenv("GPMPC_NO_PERSISTENT") != nullptr || getenv("GPMPC_STEP_DEBUG") != nullptr;
+    if (fused_prep && B <= kPersistMaxB && H >= 2 && !no_persist && h->opt_persistent) {
+        prep_step_kernel<<<dim3((B + 127) / 128, d.G), blk, 0, h->stream>>>(d, 1, h->mu.as<double>(), h->var.as<double>(),
+                                                                             w.Uint, w.lamg, w.us, w.cst, act_var);
+        GP_LAUNCH_CHECK(h);
+        const LambdaGroup &grp = h->groups[0];
+        RolloutSingleArgs ra;
+        for (int i = 0; i < kGroupMax; ++i) {
+            const int o = grp.outputs[i < grp.count ? i : 0];
+            ra.Wt[i] = h->Wt.as<double>() + (size_t)o * wt_doubles(h->ld);
+            ra.beta[i] = h->beta.as<double>() + (size_t)o * h->ld;
+            ra.out_idx[i] = o;
+        }
+        const size_t n_groups = (size_t)(w.P + SINGLE_GROUP - 1) / SINGLE_GROUP;
+        ra.X = h->X.as<double>(); ra.cst = w.cst; ra.us = w.us; ra.spart = h->part.as<double>();
+        ra.tickets = h->tickets.as<int>();
+        ra.step_done = ra.tickets + (size_t)B * (1 + n_groups); ra.error = ra.step_done + B;
+        ra.ld = h->ld; ra.ntile = h->ld / PT; ra.total_tiles = (int)w.total_tiles; ra.H = H; ra.d = d;
+        ra.hyp = h->hyp.as<double>(); ra.mu = h->mu.as<double>(); ra.var = h->var.as<double>(); ra.tape = h->tape.as<double>();
+        ra.want_grad = want_grad ? 1 : 0; ra.first_mode = need_gx0 ? 1 : 2;
+        ra.Uint = w.Uint; ra.lam_group = w.lamg; ra.act_var = act_var;
+        GP_CUDA(h, cudaMemsetAsync(ra.step_done, 0, (size_t)(B + 1) * sizeof(int), h->stream));
+        if (h->time_pairs) cudaEventRecord(h->ev0, h->stream);
+        cudaError_t e = rollout_single_launcher(d.D)(grp.count, d.E, ra, dim3(B, w.ctas), h->stream);
+        if (e == cudaSuccess) {
+            h->launches++;
+            if (h->time_pairs) {
+                cudaEventRecord(h->ev1, h->stream);
+                GP_CUDA(h, cudaEventSynchronize(h->ev1));
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+                h->last_pair_ms = ms;
+                h->last_pair_evals = (long long)H * B * d.E * ((long long)h->n * (h->n + 1) / 2);
+            }
+            // a spin wait that ran out of budget leaves garbage behind: turn it into NaN, which the caller sees as data
+            poison_on_error_kernel<<<1, 128, 0, h->stream>>>(ra.error, h->mu.as<double>() + (size_t)d.E * d.Bpad,
+                                                            h->var.as<double>() + (size_t)d.E * d.Bpad, (size_t)H * d.E * d.Bpad);
+            GP_LAUNCH_CHECK(h);
+            h->tape_B = (want_grad && need_gx0) ? B : 0;
+            h->tape_H = (want_grad && need_gx0) ? H : 0;
+            return GPMPC_OK;
+        }
+        if (e != cudaErrorCooperativeLaunchTooLarge)
+            return fail(h, GPMPC_ERR_CUDA, std::string("mm_rollout_single: ") + cudaGetErrorString(e));
+        cudaGetLastError();                            // the grid does not fit: one launch per step instead
+    }
     for (int t = 1; t <= H; ++t) {
         if (!fused_prep || t == 1) {
             prep_step_kernel<<<dim3((B + 127) / 128, d.G), blk, 0, h->stream>>>(d, t, h->mu.as<double>(), h->var.as<double>(),

@@ -64,13 +64,16 @@ __device__ __forceinline__ void finalize_math(const StepDims &d, int t, int a, i
 __device__ __forceinline__ void finalize_math_lanes(const StepDims &d, int t, int a, int b, int lane, const double *accN,
                                                     const double *accM, const double *__restrict__ us,
                                                     const double *__restrict__ hyp, double *__restrict__ mu,
-                                                    double *__restrict__ var, double *__restrict__ tape, int want_grad)
+                                                    double *__restrict__ var, double *__restrict__ tape, int want_grad,
+                                                    const double *s_local = nullptr)
 {
+    // s_local: the D input variances of this rollout in shared memory; the persistent rollout kernel passes them because
+    // `us` changes while it runs (a __restrict__ const global load may take the non-coherent path)
     const int D = d.D;
     const int k = lane < D ? lane : 0;               // idle lanes mirror lane 0
     const double lamk = hyp[(size_t)a * D + k];
     const double sf = hyp[(size_t)d.E * D + a];
-    const double sk = us[(size_t)(D + k) * d.Bpad + b];
+    const double sk = s_local ? s_local[k] : us[(size_t)(D + k) * d.Bpad + b];
     const double fm = 1.0 + sk / lamk;               // |Lam^-1 S + I| factor     uncertainty_prop.py:335
     const double fv = 1.0 + 2.0 * sk / lamk;         // |2 Lam^-1 S + I| factor   uncertainty_prop.py:377
     double detm = 1.0, detv = 1.0;

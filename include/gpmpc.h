@@ -54,6 +54,10 @@ int gpmpc_destroy(gpmpc_handle h);
 const char *gpmpc_last_error(gpmpc_handle h);   /* h may be NULL: message of the last failed create */
 int gpmpc_set_stream(gpmpc_handle h, void *cuda_stream);   /* cudaStream_t; NULL = legacy default  */
 int gpmpc_synchronize(gpmpc_handle h);
+/* Tuning switches (all default to the fastest path).
+ *   "persistent_single" (1): a single rollout (B = 1, one IPOPT callback, src/mpc.py:202-255) runs its whole horizon in
+ *                            one persistent cooperative launch; 0 = one fused launch per horizon step.            */
+int gpmpc_set_option(gpmpc_handle h, const char *name, int value);
 int gpmpc_num_train(gpmpc_handle h);
 
 /* Fit: Gram matrix, blocked Cholesky, Ky^-1, beta and the moment-matching weight matrices.

@@ -1214,3 +1214,45 @@ def test_config4_full_covariance_step_n16384(gp):
     fd = (cpm[0] - cpm[1]) / (2 * h)
     an = float(np.sum(grad[0] * d))
     assert abs(fd - an) <= 1e-4 * max(1.0, abs(an)), (fd, an)
+
+
+def test_persistent_single_rollout_matches_stepwise_path(gp):
+    """B = 1: the whole horizon in one persistent cooperative launch (mm_rollout_single) against one fused launch per
+    step (mm_step_single): same tile ranges and reduction order, so they agree to rounding; both against the C oracle."""
+    from oracle import oracle as orc
+    for n, E, m, H in ((700, 4, 1, 6), (333, 3, 2, 5), (4096, 4, 1, 30)):
+        dyn, S, A, nxt, rng = _synth_dynamics(gp, n, E, m, seed=12)
+        Q = 2 * np.eye(E); R = 0.01 * np.eye(m)
+        br = gp.BatchedRollouts(dyn, Q, R)
+        x0 = rng.uniform(-0.5, 0.5, E); U = rng.uniform(-0.3, 0.3, (1, H, m))
+        dyn._bundle.set_option("persistent_single", 1)
+        l0 = dyn._bundle.launch_count()
+        cp, gpers = br.cost_and_grad(x0, U, -1.0, host_out=True)
+        lp = dyn._bundle.launch_count() - l0
+        cp2, gpers2 = br.cost_and_grad(x0, U, -1.0, host_out=True)
+        assert np.array_equal(cp, cp2) and np.array_equal(gpers, gpers2)          # deterministic
+        dyn._bundle.set_option("persistent_single", 0)
+        l0 = dyn._bundle.launch_count()
+        cs, gs = br.cost_and_grad(x0, U, -1.0, host_out=True)
+        ls = dyn._bundle.launch_count() - l0
+        dyn._bundle.set_option("persistent_single", 1)
+        assert lp < ls and lp <= 8, (lp, ls)                                      # one launch for the horizon instead of H
+        close(cp, cs, 1e-12); norm_close(gpers, gs, 1e-11)
+        if n <= 1000:
+            X = np.concatenate([S, A], 1)
+            lam = np.full((E, E + m), 2.0)
+            fits = [orc.fit(X, nxt[:, a], lam[a], 1.0, float(np.float32(0.1 ** 2)) ** 0.5) for a in range(E)]
+            c, gr, _, _ = orc.c_rollout_cost_grad(X, [f["Ky_inv"] for f in fits], [f["beta"] for f in fits], lam, np.ones(E),
+                                                  x0, U[0], -1.0, Q, R)
+            close(cp[0], c, RTOL); norm_close(gpers[0], gr, RTOL)
+        # the autograd path (d/dx0 requested: step 1 keeps all moments) through the same kernel
+        xt = T(x0).requires_grad_(True); Ut = T(U[0]).requires_grad_(True)
+        means, covs = dyn.forward_propagate_torch(H, xt, Ut)
+        (means[-1].sum() + covs[-1].diagonal().sum()).backward()
+        dyn._bundle.set_option("persistent_single", 0)
+        xt2 = T(x0).requires_grad_(True); Ut2 = T(U[0]).requires_grad_(True)
+        means2, covs2 = dyn.forward_propagate_torch(H, xt2, Ut2)
+        (means2[-1].sum() + covs2[-1].diagonal().sum()).backward()
+        dyn._bundle.set_option("persistent_single", 1)
+        norm_close(Ut.grad.cpu().numpy(), Ut2.grad.cpu().numpy(), 1e-11)
+        norm_close(xt.grad.cpu().numpy(), xt2.grad.cpu().numpy(), 1e-11)
