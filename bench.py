@@ -549,6 +549,68 @@ def run_config5(args):
         dist.destroy_process_group()
 
 
+def run_split(args):
+    """ONE control sequence (B = 1, the IPOPT callback) whose every horizon step is split over the GPUs of the node:
+    each rank sweeps 1/N of the pair space in the persistent kernel and the kernels exchange their per-step sums over
+    NVLink (peer-mapped mailboxes, no NCCL call per step).  Prints one JSON line: ms per objective+gradient evaluation."""
+    import torch
+    import gpmpc_b200 as gp
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    n, E, m, H = args.n, 4, 1, args.H
+    dyn, _, rng, t_fit = make_dynamics(gp, n, E, m)
+    Q = 2 * np.eye(E); R = 0.01 * np.eye(m)
+    bundle = dyn._bundle
+    x0 = torch.tensor(rng.uniform(-0.5, 0.5, (1, E)), device=dev); U = torch.tensor(rng.uniform(-0.3, 0.3, (1, H, m)), device=dev)
+    g = torch.full((1,), -1.0, dtype=torch.float64, device=dev)
+    ref_cost, ref_grad, _, _ = bundle.cost_grad(x0, U, g, Q, R, host_out=True)       # single-GPU result (every rank, identical)
+    if world > 1:
+        bundle.split_connect()
+    def one():
+        return bundle.cost_grad(x0, U, g, Q, R, host_out=False)
+    for _ in range(args.warmup):
+        one()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        cost, grad, _, _ = one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    exch = (0.0, 0.0)
+    if world > 1:
+        bundle.set_option("split_timeline", 1)
+        one(); torch.cuda.synchronize()
+        exch = bundle.split_last_exchange_us()
+        bundle.set_option("split_timeline", 0)
+        t = torch.tensor([ms, exch[0], exch[1]], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, exch = float(t[0]), (float(t[1]), float(t[2]))
+    err_c = abs(float(cost[0]) - float(ref_cost[0])) / max(1.0, abs(float(ref_cost[0])))
+    err_g = float(np.max(np.abs(grad.cpu().numpy() - ref_grad))) / max(1e-300, float(np.max(np.abs(ref_grad))))
+    bytes_algo = H * E * (n * (n + 1) / 2) * 8.0
+    if rank == 0:
+        print(json.dumps({
+            "metric": "gp_mpc_single_rollout_cost_grad_ms", "value": ms, "unit": "ms", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": False, "scaling": "strong", "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"one control sequence (B=1), n={n} E=4 m=1 H={H}: objective + gradient, every step's pair space "
+                                   f"split over {world} GPU(s)"},
+            "us_per_horizon_step": 1e3 * ms / H, "aggregate_wt_stream_GBs": bytes_algo / (ms * 1e-3) / 1e9,
+            "exchange_us_per_step_mean": exch[0], "exchange_us_per_step_max": exch[1],
+            "vs_single_gpu_result": {"cost_rel_err": err_c, "grad_err_over_max": err_g}, "fit_s": t_fit}), flush=True)
+    if dist is not None:
+        bundle.split_disconnect()
+        dist.destroy_process_group()
+
+
 def run_extras(args):
     """The other BASELINE configurations and the "next" rows on ONE GPU (run as a subprocess of the default bench so that
     a failure here can never cost the headline line).  Prints one JSON dict."""
@@ -676,7 +738,8 @@ def main():
     ap.add_argument("--ard", action="store_true", help="distinct length-scales per output (not the headline workload)")
     ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configurations (configs 1, 2, 4, 5, fit)")
     ap.add_argument("--section", default="", choices=["", "extras"], help="internal: run one secondary section and print its JSON")
-    ap.add_argument("--config", type=int, default=3, choices=[3, 5], help="3 = headline rollout benchmark, 5 = sharded MPC solves")
+    ap.add_argument("--config", type=int, default=3, choices=[3, 5, 7],
+                    help="3 = headline rollout benchmark, 5 = sharded MPC solves, 7 = one rollout split over the GPUs (latency)")
     ap.add_argument("--instances", type=int, default=2048, help="--config 5: number of MPC instances (4 gammas x instances/4 x0)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -685,6 +748,8 @@ def main():
         run_extras(args)
     elif args.config == 5:
         run_config5(args)
+    elif args.config == 7:
+        run_split(args)
     else:
         run_ours(args)
 

@@ -41,6 +41,11 @@ SIGNATURES = {
     "gpmpc_rollout": (c_int, [_P, c_int, c_int, _P, _P, _P, _P]),
     "gpmpc_rollout_vjp": (c_int, [_P, c_int, c_int, _P, _P, _P, _P]),
     "gpmpc_rollout_cost_grad": (c_int, [_P, c_int, c_int] + [_P] * 13),
+    "gpmpc_split_export": (c_int, [_P, _P]),
+    "gpmpc_split_connect": (c_int, [_P, c_int, c_int, _P]),
+    "gpmpc_split_connect_local": (c_int, [_P, c_int, c_int, POINTER(c_void_p)]),
+    "gpmpc_split_disconnect": (c_int, [_P]),
+    "gpmpc_split_last_exchange_us": (c_int, [_P, POINTER(c_double), POINTER(c_double)]),
     "gpmpc_launch_count": (c_longlong, [_P]),
     "gpmpc_last_pair_kernel_ms": (c_int, [_P, POINTER(c_double), POINTER(c_longlong)]),
     "gpmpc_set_pair_timing": (c_int, [_P, c_int]),

@@ -71,6 +71,40 @@ class GPBundle:
         st = torch.cuda.current_stream(self.device).cuda_stream
         check(self.h, self.lib.gpmpc_set_stream(self.h, ctypes.c_void_p(st)), "gpmpc_set_stream")
 
+    # ---- one rollout split over several GPUs (include/gpmpc.h: gpmpc_split_*) -------------------------------
+    def split_connect(self, group=None):
+        """One process per GPU (torch.distributed): exchange the mailboxes' CUDA IPC handles and connect.  Afterwards a
+        B = 1 evaluation that EVERY rank calls with the same arguments is split over the ranks' GPUs (each must have
+        fitted the same data); the kernels exchange their per-step sums over NVLink themselves."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        buf = (ctypes.c_ubyte * 64)()
+        check(self.h, self.lib.gpmpc_split_export(self.h, ctypes.cast(buf, ctypes.c_void_p)), "gpmpc_split_export")
+        on_gpu = dist.get_backend(group) == "nccl"
+        mine = torch.tensor(list(buf), dtype=torch.uint8, device=self.device if on_gpu else "cpu")
+        allh = torch.empty(world * 64, dtype=torch.uint8, device=mine.device)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        raw = bytes(allh.cpu().numpy().tobytes())
+        dist.barrier(group)                      # every rank has created (and zeroed) its mailbox before anyone connects
+        check(self.h, self.lib.gpmpc_split_connect(self.h, rank, world, ctypes.c_char_p(raw)), "gpmpc_split_connect")
+        dist.barrier(group)
+
+    @staticmethod
+    def split_connect_local(bundles):
+        """Bundles on different devices of THIS process (one host thread per bundle must then call concurrently)."""
+        world = len(bundles)
+        arr = (ctypes.c_void_p * world)(*[b.h for b in bundles])
+        for r, b in enumerate(bundles):
+            check(b.h, b.lib.gpmpc_split_connect_local(b.h, r, world, arr), "gpmpc_split_connect_local")
+
+    def split_last_exchange_us(self):
+        a = ctypes.c_double(0.0); b = ctypes.c_double(0.0)
+        check(self.h, self.lib.gpmpc_split_last_exchange_us(self.h, ctypes.byref(a), ctypes.byref(b)), "split timeline")
+        return a.value, b.value
+
+    def split_disconnect(self):
+        check(self.h, self.lib.gpmpc_split_disconnect(self.h), "gpmpc_split_disconnect")
+
     def set_option(self, name, value):
         check(self.h, self.lib.gpmpc_set_option(self.h, name.encode(), int(value)), "gpmpc_set_option")
 

@@ -31,7 +31,7 @@ def _nvcc():
 
 def _jobs():
     jobs = []
-    for name in ("api", "fit", "gemm", "rollout", "fullcov"):
+    for name in ("api", "fit", "gemm", "rollout", "fullcov", "split"):
         jobs.append((os.path.join(CSRC, name + ".cu"), os.path.join(OBJ, name + ".o"), []))
     for d in PAIR_DIMS:
         jobs.append((os.path.join(CSRC, "mm_pairs_inst.cu"), os.path.join(OBJ, f"mm_pairs_D{d}.o"),

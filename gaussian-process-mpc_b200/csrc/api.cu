@@ -62,6 +62,8 @@ extern "C" int gpmpc_destroy(gpmpc_handle h)
         b->release();
     for (cudaStream_t st : h->aux_streams) cudaStreamDestroy(st);
     for (cudaEvent_t ev : h->aux_events) cudaEventDestroy(ev);
+    gpmpc_split_disconnect(h);
+    h->split_buf.release();
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -88,7 +90,16 @@ extern "C" int gpmpc_set_option(gpmpc_handle h, const char *name, int value)
 {
     if (!h || !name) return GPMPC_ERR_INVALID;
     if (std::strcmp(name, "persistent_single") == 0) { h->opt_persistent = value != 0; return GPMPC_OK; }
+    if (std::strcmp(name, "split_timeline") == 0) { h->opt_split_timeline = value != 0; return GPMPC_OK; }
     return fail(h, GPMPC_ERR_INVALID, std::string("gpmpc_set_option: unknown option ") + name);
+}
+
+extern "C" int gpmpc_split_last_exchange_us(gpmpc_handle h, double *mean_us, double *max_us)
+{
+    if (!h) return GPMPC_ERR_INVALID;
+    if (mean_us) *mean_us = h->split_exchange_mean_us;
+    if (max_us) *max_us = h->split_exchange_max_us;
+    return GPMPC_OK;
 }
 
 extern "C" int gpmpc_num_train(gpmpc_handle h) { return h ? h->n : GPMPC_ERR_INVALID; }

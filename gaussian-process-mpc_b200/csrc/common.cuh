@@ -16,6 +16,8 @@ constexpr int kPairTile = 32;      // pair-space tile rows of the moment-matchin
 constexpr int kMaxD = GPMPC_MAX_D;
 constexpr int kMaxE = GPMPC_MAX_E;
 constexpr int kGroupMax = 4;       // outputs evaluated per pair-kernel pass (sharing one exp)
+constexpr int kSplitMaxWorld = 8;  // GPUs one rollout can be split over
+constexpr int kSplitNV = 2 * kGroupMax * (1 + 2 * GPMPC_MAX_D);   // doubles one rank contributes per step (pair + mean sums)
 
 // Wt storage: only the upper-triangular 32x32 tiles, each tile contiguous (8 KB, row-major inside), tiles in
 // row-major order of (I, J >= I).  A contiguous range of the tile list is a contiguous range of memory, which is
@@ -89,6 +91,16 @@ struct gpmpc_ctx {
 
     // gpmpc_set_option
     bool opt_persistent = true;    // single rollouts: whole horizon in one persistent cooperative launch
+
+    // a single rollout split over several GPUs (gpmpc_split_*): mailbox of per-step sums written by the peers' kernels
+    int split_world = 1, split_rank = 0;
+    long long split_seq = 0;       // step sequence number, advanced identically on every rank
+    gpmpc::DevBuf split_buf;       // local mailbox: [8 ranks][2 slots][kSplitNV] doubles, then [8][2] 64-bit flags
+    double *peer_mail[8] = {};     // every rank's mailbox as mapped into this process (own entry = split_buf)
+    unsigned long long *peer_flags[8] = {};
+    bool split_ipc[8] = {};        // entries opened with cudaIpcOpenMemHandle (to be closed)
+    bool opt_split_timeline = false;   // stamp the exchange of every step (synchronises after the launch)
+    double split_exchange_mean_us = 0.0, split_exchange_max_us = 0.0;
 
     // auxiliary streams / events: independent outputs are fitted concurrently (fit.cu)
     std::vector<cudaStream_t> aux_streams;

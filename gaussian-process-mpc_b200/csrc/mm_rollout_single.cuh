@@ -42,6 +42,14 @@ struct RolloutSingleArgs {
     const double *Uint;            // actions [H*m][Bpad]
     const double *lam_group;       // [D] of the (single) lambda group
     double act_var;
+    // one rollout split over `world` GPUs (gpmpc_split_*): rank r sweeps tiles [T r / world, T (r+1) / world) and the
+    // matching slice of the training set; after every step the ranks exchange their sums through peer-mapped
+    // mailboxes written from inside the kernel (NVLink P2P stores + a release/acquire flag per rank and step)
+    int world, rank;
+    long long seq0;                // sequence number of step 0 of this call (identical on all ranks)
+    double *peer_mail[kSplitMaxWorld];            // [rank r] -> r's mailbox [kSplitMaxWorld][2][kSplitNV]
+    unsigned long long *peer_flags[kSplitMaxWorld];   // [rank r] -> r's flags [kSplitMaxWorld][2]
+    unsigned long long *xstamp;    // optional [H][2] %globaltimer stamps around the exchange (gpmpc_set_option "split_timeline")
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int *p)
@@ -53,6 +61,22 @@ __device__ __forceinline__ int ld_acquire_gpu(const int *p)
 __device__ __forceinline__ void st_release_gpu(int *p, int v)
 {
     asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double *p)
+{
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];\n" : "=d"(v) : "l"(p) : "memory");
+    return v;
 }
 
 template <int D, int EG, int NS>
@@ -83,8 +107,10 @@ mm_rollout_single(const RolloutSingleArgs a)
     }
     __syncthreads();
 
-    const int t_begin = (int)((long long)a.total_tiles * bx / P);
-    const int t_end = (int)((long long)a.total_tiles * (bx + 1) / P);
+    // this GPU's share of the tile list, then this CTA's share of that
+    const long long T_lo = (long long)a.total_tiles * a.rank / a.world, T_hi = (long long)a.total_tiles * (a.rank + 1) / a.world;
+    const int t_begin = (int)(T_lo + (T_hi - T_lo) * bx / P);
+    const int t_end = (int)(T_lo + (T_hi - T_lo) * (bx + 1) / P);
     const int nt_cta = t_end - t_begin;                  // tiles of this CTA per step
     const long long g_total = (long long)nt_cta * a.H;   // tiles over the whole rollout
     int I0 = 0, J0 = 0;                                  // first tile of the share
@@ -117,8 +143,8 @@ mm_rollout_single(const RolloutSingleArgs a)
     }
 
     // mean sums: this CTA's slice of the training set stays in registers (warp 0, one point per lane and round)
-    const int per = (a.ld + P - 1) / P;
-    const int j_begin = bx * per;
+    const int per = (a.ld + a.world * P - 1) / (a.world * P);
+    const int j_begin = (a.rank * P + bx) * per;
     const int j_end = min(a.ld, j_begin + per);
     constexpr int MR = 2;                                // rounds held in registers (per <= 64 at P >= ld / 64)
     double xpre[MR][D], bpre[MR][EG];
@@ -350,6 +376,34 @@ mm_rollout_single(const RolloutSingleArgs a)
             fin[v] = sacc;
         }
         __syncthreads();
+        if (a.world > 1) {
+            // ---- exchange with the other GPUs: publish this GPU's sums to every rank's mailbox, collect theirs ----
+            const unsigned long long seq = (unsigned long long)(a.seq0 + t);
+            const int slot = (int)(seq & 1);
+            if (a.xstamp && tid == 0) a.xstamp[(size_t)(t - 1) * 2] = gtime();
+            for (int r = 0; r < a.world; ++r)
+                for (int v = tid; v < NV; v += SINGLE_THREADS)
+                    a.peer_mail[r][((size_t)a.rank * 2 + slot) * kSplitNV + v] = fin[v];
+            __threadfence_system();
+            __syncthreads();
+            if (tid < a.world) {
+                st_release_sys(a.peer_flags[tid] + a.rank * 2 + slot, seq);
+                long long spins = 0;
+                while (ld_acquire_sys(a.peer_flags[a.rank] + tid * 2 + slot) < seq) {
+                    if (++spins > (1ll << 26)) { atomicExch(a.error, 1); break; }
+                    __nanosleep(20);
+                }
+            }
+            __syncthreads();
+            const double *mail = a.peer_mail[a.rank];
+            for (int v = tid; v < NV; v += SINGLE_THREADS) {
+                double sacc = 0.0;
+                for (int r = 0; r < a.world; ++r) sacc += ld_relaxed_sys(mail + ((size_t)r * 2 + slot) * kSplitNV + v);   // rank order: same on every GPU
+                fin[v] = sacc;
+            }
+            __syncthreads();
+            if (a.xstamp && tid == 0) a.xstamp[(size_t)(t - 1) * 2 + 1] = gtime();
+        }
         if (wid < EG)
             finalize_math_lanes(a.d, t, a.out_idx[wid], b, lane, &fin[wid * NA], &fin[EG * NA + wid * NA], a.us, a.hyp,
                                 a.mu, a.var, a.tape, a.want_grad, s_in);

@@ -798,9 +798,23 @@ static int forward(gpmpc_ctx *h, int B, int H, const double *x0_dev, const doubl
         ra.hyp = h->hyp.as<double>(); ra.mu = h->mu.as<double>(); ra.var = h->var.as<double>(); ra.tape = h->tape.as<double>();
         ra.want_grad = want_grad ? 1 : 0; ra.first_mode = need_gx0 ? 1 : 2;
         ra.Uint = w.Uint; ra.lam_group = w.lamg; ra.act_var = act_var;
+        // one rollout split over several GPUs (split.cu): this rank sweeps 1/world of the tiles with as many CTAs as fit
+        ra.world = h->split_world; ra.rank = h->split_rank; ra.seq0 = h->split_seq;
+        for (int r = 0; r < kSplitMaxWorld; ++r) { ra.peer_mail[r] = h->peer_mail[r]; ra.peer_flags[r] = h->peer_flags[r]; }
+        int ctas = w.ctas;
+        if (ra.world > 1) {
+            const long long local = w.total_tiles * (ra.rank + 1) / ra.world - w.total_tiles * ra.rank / ra.world;
+            if (local < ctas) ctas = (int)(local > 0 ? local : 1);
+            h->split_seq += H;                          // every rank advances identically (same calls in the same order)
+        }
+        ra.xstamp = nullptr;
+        if (ra.world > 1 && h->opt_split_timeline) {
+            GP_CUDA(h, h->dbg.reserve((size_t)H * 2 * sizeof(unsigned long long)));
+            ra.xstamp = h->dbg.as<unsigned long long>();
+        }
         GP_CUDA(h, cudaMemsetAsync(ra.step_done, 0, (size_t)(B + 1) * sizeof(int), h->stream));
         if (h->time_pairs) cudaEventRecord(h->ev0, h->stream);
-        cudaError_t e = rollout_single_launcher(d.D)(grp.count, d.E, ra, dim3(B, w.ctas), h->stream);
+        cudaError_t e = rollout_single_launcher(d.D)(grp.count, d.E, ra, dim3(B, ctas), h->stream);
         if (e == cudaSuccess) {
             h->launches++;
             if (h->time_pairs) {
@@ -810,6 +824,14 @@ static int forward(gpmpc_ctx *h, int B, int H, const double *x0_dev, const doubl
                 cudaEventElapsedTime(&ms, h->ev0, h->ev1);
                 h->last_pair_ms = ms;
                 h->last_pair_evals = (long long)H * B * d.E * ((long long)h->n * (h->n + 1) / 2);
+            }
+            if (ra.xstamp) {                             // development / bench aid: time from "sums ready" to "all peers' sums read"
+                std::vector<unsigned long long> st((size_t)H * 2);
+                GP_CUDA(h, cudaMemcpyAsync(st.data(), ra.xstamp, st.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+                GP_CUDA(h, cudaStreamSynchronize(h->stream));
+                double sum = 0.0, mx = 0.0;
+                for (int t = 0; t < H; ++t) { const double us = (double)(st[2 * t + 1] - st[2 * t]) * 1e-3; sum += us; if (us > mx) mx = us; }
+                h->split_exchange_mean_us = sum / H; h->split_exchange_max_us = mx;
             }
             // a spin wait that ran out of budget leaves garbage behind: turn it into NaN, which the caller sees as data
             poison_on_error_kernel<<<1, 128, 0, h->stream>>>(ra.error, h->mu.as<double>() + (size_t)d.E * d.Bpad,

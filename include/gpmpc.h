@@ -56,7 +56,8 @@ int gpmpc_set_stream(gpmpc_handle h, void *cuda_stream);   /* cudaStream_t; NULL
 int gpmpc_synchronize(gpmpc_handle h);
 /* Tuning switches (all default to the fastest path).
  *   "persistent_single" (1): a single rollout (B = 1, one IPOPT callback, src/mpc.py:202-255) runs its whole horizon in
- *                            one persistent cooperative launch; 0 = one fused launch per horizon step.            */
+ *                            one persistent cooperative launch; 0 = one fused launch per horizon step.
+ *   "split_timeline" (0):    stamp the inter-GPU exchange of every step (see gpmpc_split_last_exchange_us).           */
 int gpmpc_set_option(gpmpc_handle h, const char *name, int value);
 int gpmpc_num_train(gpmpc_handle h);
 
@@ -186,6 +187,24 @@ int gpmpc_rollout_cost_grad(gpmpc_handle h, int B, int H, const double *x0, cons
                             const double *gamma, const double *Q, const double *R, const double *Rdelta,
                             const double *last_u, const double *xref, const double *uref, double *cost,
                             double *grad, double *means, double *vars);
+
+/* ONE rollout split over several GPUs of a node (the only split that shortens a single IPOPT callback,
+ * src/mpc.py:202-255).  Every rank fits the same GP (replica), connects once, and from then on a B = 1 call of
+ * gpmpc_rollout_cost_grad / gpmpc_rollout made by ALL ranks with the same arguments (same calls, same order) sweeps 1/world
+ * of every step's pair space per GPU; the per-step sums are exchanged by the kernels themselves through peer-mapped
+ * mailboxes (NVLink P2P stores + release/acquire flags) and every rank returns the same result.
+ *   gpmpc_split_export        creates this handle's mailbox and returns its CUDA IPC handle (GPMPC_IPC_HANDLE_BYTES bytes)
+ *   gpmpc_split_connect       all_handles = the `world` exported handles in rank order (other processes' mailboxes)
+ *   gpmpc_split_connect_local same for handles living in THIS process (peers[r] for r != rank, one device each)
+ *   gpmpc_split_disconnect    back to single-GPU evaluation                                                       */
+#define GPMPC_IPC_HANDLE_BYTES 64
+int gpmpc_split_export(gpmpc_handle h, void *ipc_handle_out);
+int gpmpc_split_connect(gpmpc_handle h, int rank, int world, const void *all_handles);
+int gpmpc_split_connect_local(gpmpc_handle h, int rank, int world, gpmpc_handle *peers);
+int gpmpc_split_disconnect(gpmpc_handle h);
+/* With gpmpc_set_option(h, "split_timeline", 1): per-step time (us, %globaltimer) this rank spent between "local sums
+ * ready" and "all ranks' sums read" in the last split evaluation: mean and maximum over the horizon steps.         */
+int gpmpc_split_last_exchange_us(gpmpc_handle h, double *mean_us, double *max_us);
 
 /* Introspection for benchmarks: kernels launched by this handle since creation, and the device time
  * (ms, CUDA events on the handle's stream) of the last pair-sum kernel sequence.                      */
