@@ -191,7 +191,7 @@ mm_rollout_single(const RolloutSingleArgs a)
                 // one acquire fence once the value is there
                 long long spins = 0;
                 while (ld_relaxed_gpu(a.step_done + b) < t - 1) {
-                    if (++spins > (1ll << 28)) { s_bail = 1; atomicExch(a.error, 1); break; }
+                    if (++spins > (1ll << 22)) { s_bail = 1; atomicExch(a.error, 1); break; }     // ~2 s: never hang the GPU
                 }
                 asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
             }
@@ -320,8 +320,9 @@ mm_rollout_single(const RolloutSingleArgs a)
             if (lane == 0) mbar_arrive(&empty[slot]);
             ++J;
             if (J == a.ntile) { ++I; J = I; }
+            ++g_cons; pslot = slot; ppar = par;
+            if (++slot == SINGLE_STAGES) { slot = 0; par ^= 1u; }
         }
-
         };
         if (mode == 1) tile_loop(std::integral_constant<int, 1>{});
         else if (mode == 2) tile_loop(std::integral_constant<int, 2>{});
@@ -388,26 +389,25 @@ mm_rollout_single(const RolloutSingleArgs a)
         if (a.world > 1) {
             // ---- exchange with the other GPUs: publish this GPU's sums to every rank's mailbox, collect theirs ----
             const unsigned long long seq = (unsigned long long)(a.seq0 + t);
-            const int slot = (int)(seq & 1);
+            const int mslot = (int)(seq & 1);
             if (a.xstamp && tid == 0) a.xstamp[(size_t)(t - 1) * 2] = gtime();
             for (int r = 0; r < a.world; ++r)
                 for (int v = tid; v < NV; v += SINGLE_THREADS)
-                    a.peer_mail[r][((size_t)a.rank * 2 + slot) * kSplitNV + v] = fin[v];
+                    a.peer_mail[r][((size_t)a.rank * 2 + mslot) * kSplitNV + v] = fin[v];
             __threadfence_system();
             __syncthreads();
             if (tid < a.world) {
-                st_release_sys(a.peer_flags[tid] + a.rank * 2 + slot, seq);
+                st_release_sys(a.peer_flags[tid] + a.rank * 2 + mslot, seq);
                 long long spins = 0;
-                while (ld_acquire_sys(a.peer_flags[a.rank] + tid * 2 + slot) < seq) {
-                    if (++spins > (1ll << 26)) { atomicExch(a.error, 1); break; }
-                    __nanosleep(20);
+                while (ld_acquire_sys(a.peer_flags[a.rank] + tid * 2 + mslot) < seq) {
+                    if (++spins > (1ll << 22)) { atomicExch(a.error, 1); break; }                 // a missing peer: ~2-4 s, then NaN
                 }
             }
             __syncthreads();
             const double *mail = a.peer_mail[a.rank];
             for (int v = tid; v < NV; v += SINGLE_THREADS) {
                 double sacc = 0.0;
-                for (int r = 0; r < a.world; ++r) sacc += ld_relaxed_sys(mail + ((size_t)r * 2 + slot) * kSplitNV + v);   // rank order: same on every GPU
+                for (int r = 0; r < a.world; ++r) sacc += ld_relaxed_sys(mail + ((size_t)r * 2 + mslot) * kSplitNV + v);   // rank order: same on every GPU
                 fin[v] = sacc;
             }
             __syncthreads();

@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x -k "persistent or config3_full_size_rollout or shipped or kernel_switch or determinism" > gpurun_out/r2d_pytest.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/r2d_pytest.txt
+timeout 240 python -m pytest tests -m gpu -q -x -k "persistent or config3_full_size_rollout or shipped or kernel_switch or determinism" > gpurun_out/r2d_pytest.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/r2d_pytest.txt
 tail -5 gpurun_out/r2d_pytest.txt
 timeout 300 python tools/b1_eval.py 20 > gpurun_out/r2d_b1.txt 2>&1
 GPMPC_NO_PERSISTENT=1 timeout 300 python tools/b1_eval.py 20 >> gpurun_out/r2d_b1.txt 2>&1
