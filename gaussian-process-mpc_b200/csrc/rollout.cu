@@ -778,7 +778,7 @@ static int forward(gpmpc_ctx *h, int B, int H, const double *x0_dev, const doubl
     const bool fused_prep = B < kSingleMaxB && d.G == 1;
     // a single rollout: the whole horizon in one persistent cooperative launch
     static const bool no_persist = getenv("GPMPC_NO_PERSISTENT") != nullptr || getenv("GPMPC_STEP_DEBUG") != nullptr;
-    if (fused_prep && B <= kPersistMaxB && H >= 2 && !no_persist && h->opt_persistent) {
+    if (fused_prep && B <= kPersistMaxB && H >= 2 && !no_persist && (h->opt_persistent || h->split_world > 1)) {
         prep_step_kernel<<<dim3((B + 127) / 128, d.G), blk, 0, h->stream>>>(d, 1, h->mu.as<double>(), h->var.as<double>(),
                                                                              w.Uint, w.lamg, w.us, w.cst, act_var);
         GP_LAUNCH_CHECK(h);

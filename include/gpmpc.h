@@ -55,8 +55,9 @@ const char *gpmpc_last_error(gpmpc_handle h);   /* h may be NULL: message of the
 int gpmpc_set_stream(gpmpc_handle h, void *cuda_stream);   /* cudaStream_t; NULL = legacy default  */
 int gpmpc_synchronize(gpmpc_handle h);
 /* Tuning switches (all default to the fastest path).
- *   "persistent_single" (1): a single rollout (B = 1, one IPOPT callback, src/mpc.py:202-255) runs its whole horizon in
- *                            one persistent cooperative launch; 0 = one fused launch per horizon step.
+ *   "persistent_single" (0): 1 = a single rollout (B = 1, one IPOPT callback, src/mpc.py:202-255) runs its whole horizon
+ *                            in one persistent cooperative launch; 0 = one fused launch per horizon step (measured faster
+ *                            on one GPU).  A rollout split over several GPUs (gpmpc_split_*) always uses the persistent kernel.
  *   "split_timeline" (0):    stamp the inter-GPU exchange of every step (see gpmpc_split_last_exchange_us).           */
 int gpmpc_set_option(gpmpc_handle h, const char *name, int value);
 int gpmpc_num_train(gpmpc_handle h);
