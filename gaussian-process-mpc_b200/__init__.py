@@ -5,4 +5,4 @@ from ._lib import GpmpcError, LIB_PATH, SIGNATURES  # noqa: F401
 from .gpr import GaussianProcessRegression  # noqa: F401
 from .dynamics import Dynamics  # noqa: F401
 from .mpc import RiskSensitiveMPC  # noqa: F401
-from .batched import BatchedRollouts, BatchedSolver, shard_range, shard_indices  # noqa: F401
+from .batched import BatchedRollouts, BatchedSolver, BatchedSimulator, shard_range, shard_indices  # noqa: F401

@@ -277,3 +277,48 @@ class BatchedSolver:
                 iters[r] = g[r, 0, n + 2]; revals += g[r, 0, n + 3] * ir.size
         return {"U": U.reshape(B, self.H, self.m), "cost": cost, "converged": conv, "iters_per_rank": iters,
                 "rollout_evals": revals}
+
+
+class BatchedSimulator:
+    """Closed loop for MANY independent MPC instances at once: the batched counterpart of the reference's
+    `Simulator.run` (`src/simulator.py:37-60`: reset -> loop { solve, env.step(first action), append data }).
+
+    Every iteration solves all instances in lock step with `BatchedSolver` (warm-started from the previous solution
+    shifted by one step), applies the first action of each plan to the plant `step_fn(x[B,E], u[B,m]) -> x_next[B,E]`
+    (a vectorised plant model; the reference's gym environments are out of scope) and, if `learn_every` > 0, appends
+    the observed transitions of instance 0..k to the SHARED dynamics model every `learn_every` iterations (the
+    reference appends after every step of its single instance; with many instances sharing one GP the model update
+    is a batch append + refit).  Instances are independent, so under `torchrun` each rank runs its own shard."""
+
+    def __init__(self, solver, step_fn, num_iters=50, learn_every=0, learn_instances=1):
+        self.solver, self.step_fn = solver, step_fn
+        self.num_iters, self.learn_every, self.learn_instances = int(num_iters), int(learn_every), int(learn_instances)
+
+    def run(self, x0, gamma):
+        """x0 [B,E], gamma [B] -> dict(states [T+1,B,E], actions [T,B,m], costs [T,B], solves, rollout_evals)."""
+        x = np.array(x0, dtype=np.float64)
+        B = x.shape[0]
+        gamma = np.broadcast_to(np.asarray(gamma, dtype=np.float64), (B,)).copy()
+        H, m = self.solver.H, self.solver.m
+        states, actions, costs = [x.copy()], [], []
+        U = np.zeros((B, H, m))
+        buf_s, buf_a, buf_n = [], [], []
+        e0 = self.solver.n_rollout_evals
+        for it in range(self.num_iters):
+            sol = self.solver.solve(x, gamma, U0=U)
+            U = sol["U"]
+            a = U[:, 0, :]
+            xn = np.asarray(self.step_fn(x, a), dtype=np.float64).reshape(B, -1)
+            actions.append(a.copy()); costs.append(sol["cost"].copy())
+            if self.learn_every > 0:
+                k = min(self.learn_instances, B)
+                buf_s.append(x[:k].copy()); buf_a.append(a[:k].copy()); buf_n.append(xn[:k].copy())
+                if (it + 1) % self.learn_every == 0:
+                    dyn = self.solver.rollouts.dynamics
+                    dyn.append_train_data(np.concatenate(buf_s), np.concatenate(buf_a), np.concatenate(buf_n))
+                    buf_s, buf_a, buf_n = [], [], []
+            x = xn
+            states.append(x.copy())
+            U = np.concatenate([U[:, 1:], U[:, -1:]], axis=1)          # shifted warm start
+        return {"states": np.stack(states), "actions": np.stack(actions), "costs": np.stack(costs),
+                "solves": B * self.num_iters, "rollout_evals": self.solver.n_rollout_evals - e0}

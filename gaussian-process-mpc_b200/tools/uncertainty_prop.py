@@ -100,7 +100,7 @@ def covariance_prop_torch(lambdas1, lambdas2, u, S, X_train, mean1, mean2, beta1
 # ---- NumPy-interface twins (reference `src/tools/uncertainty_prop.py:6-44,91-136,187-236`) -------------------------
 # The reference's versions are O(n^2) Python loops kept as test oracles (sigma_f = 1, they take the evidence matrix
 # K = Ky rather than its inverse).  Same signatures and return types here, evaluated by the same device kernels as
-# the torch functions above.  (The Monte-Carlo checkers `*_mc` are not provided: they are test utilities.)
+# the torch functions above.
 def _inv_dev(K, dev):
     return torch.linalg.inv(torch.as_tensor(np.asarray(K, dtype=np.float64), device=dev))
 
@@ -129,3 +129,52 @@ def covariance_prop(K1, K2, Lambda1, Lambda2, u, S, X_train, y_train):
     m1, p1 = mean_prop_torch(_inv_dev(K1, dev), lam1, u, S, X_train, y_train, 1.0)
     m2, p2 = mean_prop_torch(_inv_dev(K2, dev), lam2, u, S, X_train, y_train, 1.0)
     return float(covariance_prop_torch(lam1, lam2, u, S, X_train, m1, m2, p1['beta'], p2['beta'], 1.0, 1.0).item())
+
+
+# ---- Monte-Carlo checkers (reference `src/tools/uncertainty_prop.py:47-88,139-184,239-292`) ---------------------------
+# Test utilities in the reference (T = 10 000 samples, Python loops over samples and training points); same signatures
+# and estimators here, vectorised with torch on the device (plain library ops: they are checkers, not on the hot path).
+_MC_SAMPLES = 10000
+
+
+def _mc_posterior(K, Lambda, X_star, X_train, y_train, sigma_f, dev):
+    """Posterior mean [T] and variance [T] of the GP at the sampled inputs (`:76-86`, `:170-182`)."""
+    lam = torch.as_tensor(np.diag(np.asarray(Lambda, dtype=np.float64)).copy(), device=dev)
+    X = torch.as_tensor(np.asarray(X_train, dtype=np.float64), device=dev)
+    y = torch.as_tensor(np.asarray(y_train, dtype=np.float64).reshape(-1), device=dev)
+    Kinv = _inv_dev(K, dev)
+    d2 = torch.cdist(X_star / torch.sqrt(lam), X / torch.sqrt(lam)).square()
+    kv = sigma_f ** 2 * torch.exp(-0.5 * d2)                       # [T, n]
+    mu = kv @ (Kinv @ y)
+    sig2 = sigma_f ** 2 - ((kv @ Kinv) * kv).sum(dim=1)
+    return mu, sig2
+
+
+def _mc_inputs(u, S, dev, samples):
+    xs = np.random.multivariate_normal(np.asarray(u, dtype=np.float64), np.asarray(S, dtype=np.float64), size=samples)
+    return torch.as_tensor(xs, device=dev)
+
+
+def mean_prop_mc(K, Lambda, u, S, X_train, y_train, sigma_f=1):
+    """Monte-Carlo estimate of the mean of the GP output for x ~ N(u, S)."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    mu, _ = _mc_posterior(K, Lambda, _mc_inputs(u, S, dev, _MC_SAMPLES), X_train, y_train, sigma_f, dev)
+    return float(mu.mean().item())
+
+
+def variance_prop_mc(K, Lambda, u, S, X_train, y_train, sigma_f=1):
+    """Monte-Carlo estimate of the variance: E[sigma^2(x)] + Var[mu(x)] (law of total variance, `:184`)."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    mu, sig2 = _mc_posterior(K, Lambda, _mc_inputs(u, S, dev, _MC_SAMPLES), X_train, y_train, sigma_f, dev)
+    return float(sig2.mean().item() + mu.var(unbiased=False).item())
+
+
+def covariance_prop_mc(K1, K2, Lambda1, Lambda2, u, S, X_train, y_train, sigma_f1=1, sigma_f2=1):
+    """Monte-Carlo estimate of the covariance of two GP outputs: sample x, then f1, f2 independently given x (`:276-292`)."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    xs = _mc_inputs(u, S, dev, _MC_SAMPLES)
+    mu1, s1 = _mc_posterior(K1, Lambda1, xs, X_train, y_train, sigma_f1, dev)
+    mu2, s2 = _mc_posterior(K2, Lambda2, xs, X_train, y_train, sigma_f2, dev)
+    f1 = mu1.cpu().numpy() + np.sqrt(np.maximum(s1.cpu().numpy(), 0.0)) * np.random.standard_normal(_MC_SAMPLES)
+    f2 = mu2.cpu().numpy() + np.sqrt(np.maximum(s2.cpu().numpy(), 0.0)) * np.random.standard_normal(_MC_SAMPLES)
+    return float(np.cov(f1, f2)[0, 1])

@@ -9,4 +9,4 @@ from ._lib import GpmpcError, LIB_PATH, SIGNATURES  # noqa: E402,F401
 from .gpr import GaussianProcessRegression  # noqa: E402,F401
 from .dynamics import Dynamics  # noqa: E402,F401
 from .mpc import RiskSensitiveMPC  # noqa: E402,F401
-from .batched import BatchedRollouts, BatchedSolver, shard_range, shard_indices  # noqa: E402,F401
+from .batched import BatchedRollouts, BatchedSolver, BatchedSimulator, shard_range, shard_indices  # noqa: E402,F401

@@ -1256,3 +1256,56 @@ def test_persistent_single_rollout_matches_stepwise_path(gp):
         dyn._bundle.set_option("persistent_single", 1)
         norm_close(Ut.grad.cpu().numpy(), Ut2.grad.cpu().numpy(), 1e-8)
         norm_close(xt.grad.cpu().numpy(), xt2.grad.cpu().numpy(), 1e-8)
+
+
+def test_monte_carlo_checkers_agree_with_the_exact_moments(gp):
+    """The reference's own test strategy (src/test/tools/test_uncertainty_prop.py:62-69,113-120,173-180): the analytic
+    mean / variance / covariance against the Monte-Carlo checkers (T = 10 000), within its 2 % / 5 % / 2 %-style bands
+    (covariance: absolute band, it can be close to 0)."""
+    from gpmpc_b200.tools.uncertainty_prop import (mean_prop, variance_prop, covariance_prop, mean_prop_mc, variance_prop_mc,
+                                                   covariance_prop_mc)
+    np.random.seed(5)
+    rng = np.random.default_rng(5)
+    n, D = 100, 2
+    X = rng.multivariate_normal([2.0, 1.0], [[1.0, 0.5], [0.5, 2.0]], size=n)
+    y = (X ** 2).sum(1) + rng.normal(0, 0.5, n)
+    Lam1, Lam2 = np.diag([1.0, 1.0]), np.diag([2.0, 2.0])
+
+    def gram(Lam):
+        d = X[:, None, :] - X[None, :, :]
+        return np.exp(-0.5 * np.einsum("ijk,k,ijk->ij", d, 1.0 / np.diag(Lam), d)) + 0.25 * np.eye(n)
+    K1, K2 = gram(Lam1), gram(Lam2)
+    u = np.array([2.0, 1.0]); S = np.array([[0.2, 0.05], [0.05, 0.1]])
+    m_exact, _ = mean_prop(K1, Lam1, u, S, X, y)
+    m_mc = mean_prop_mc(K1, Lam1, u, S, X, y)
+    assert abs(m_mc - m_exact) <= 0.02 * abs(m_exact), (m_mc, m_exact)
+    v_exact = variance_prop(K1, Lam1, u, S, X, y)
+    v_mc = variance_prop_mc(K1, Lam1, u, S, X, y)
+    assert abs(v_mc - v_exact) <= 0.05 * abs(v_exact), (v_mc, v_exact)
+    c_exact = covariance_prop(K1, K2, Lam1, Lam2, u, S, X, y)
+    c_mc = covariance_prop_mc(K1, K2, Lam1, Lam2, u, S, X, y)
+    assert abs(c_mc - c_exact) <= 0.05 * max(abs(c_exact), v_exact), (c_mc, c_exact)
+
+
+def test_batched_closed_loop_simulator_on_the_device(gp):
+    """BatchedSimulator: 12 closed-loop MPC instances (gamma sweep x initial states) for 6 steps on the synthetic
+    contracting plant the GP was trained on; the controller must drive every state norm down, and a shared model update
+    (batch append of observed transitions) must go through."""
+    n, E, m, H = 300, 2, 1, 5
+    S, A, nxt, rng = _synth(n, E, m, seed=33)
+    Wm = np.random.default_rng(33)                       # same generator stream as _synth: rebuild its plant matrix
+    Wm.uniform(-1, 1, (n, E)); Wm.uniform(-1, 1, (n, m)); W = Wm.normal(0, 0.3, (E + m, E))
+    plant = lambda x, u: 0.9 * x + 0.2 * np.tanh(np.concatenate([x, u], 1) @ W)          # noqa: E731
+    assert np.allclose(plant(S, A), nxt)
+    dyn = gp.Dynamics(E, m)
+    for a in range(E):
+        dyn.gpr_err[a].set_lambdas(np.full(E + m, 2.0)); dyn.gpr_err[a].set_sigma_n(np.float64(0.1))
+    dyn.append_train_data(S, A, nxt)
+    br = gp.BatchedRollouts(dyn, 2 * np.eye(E), 0.01 * np.eye(m))
+    solver = gp.BatchedSolver(br, H, m, lb=[-1.0], ub=[1.0], max_iter=30, gtol=1e-5)
+    sim = gp.BatchedSimulator(solver, plant, num_iters=6, learn_every=3, learn_instances=2)
+    gam = np.repeat([-1.0, 0.5, 1.0], 4); x0 = np.tile(rng.uniform(-0.8, 0.8, (4, E)), (3, 1))
+    out = sim.run(x0, gam)
+    assert out["states"].shape == (7, 12, E) and np.all(np.isfinite(out["costs"]))
+    assert np.all(np.linalg.norm(out["states"][-1], axis=1) < np.linalg.norm(out["states"][0], axis=1))
+    assert dyn.gpr_err[0].num_train == n + 2 * 6

@@ -276,3 +276,33 @@ def test_bench_reference_arm_prints_the_contract_line():
         lin = d["cpu_baseline"]["linearity"]
         assert lin["t_H1_s"] > 0 and lin["t_H2_s"] > 0 and lin["t_full_s"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_batched_simulator_closed_loop_on_a_fake_plant():
+    """BatchedSimulator (the many-instance counterpart of src/simulator.py:37-60): solve -> apply first action -> next
+    state, warm-started; on a linear plant with a quadratic stage cost every instance must be driven towards 0."""
+    from gpmpc_b200 import BatchedRollouts, BatchedSolver, BatchedSimulator
+    H, m, E, B = 4, 1, 1, 5
+    a_coef, b_coef = 0.9, 0.5
+
+    def fake(x0, U, gamma, last_u=None, host_out=True, want_grad=True):
+        # cost = sum_t x_t^2 + 0.01 u_t^2 with x_{t+1} = a x_t + b u_t (exact gradient by the adjoint recursion)
+        Bn = U.shape[0]
+        xs = np.zeros((Bn, H + 1)); xs[:, 0] = x0[:, 0]
+        for t in range(H):
+            xs[:, t + 1] = a_coef * xs[:, t] + b_coef * U[:, t, 0]
+        cost = (xs[:, 1:] ** 2).sum(1) + 0.01 * (U[:, :, 0] ** 2).sum(1)
+        lam = np.zeros(Bn); grad = np.zeros_like(U)
+        for t in range(H - 1, -1, -1):
+            lam = 2 * xs[:, t + 1] + a_coef * lam
+            grad[:, t, 0] = b_coef * lam + 0.02 * U[:, t, 0]
+        return cost, grad
+
+    solver = BatchedSolver(BatchedRollouts(evaluate_fn=fake), H, m, lb=[-1.0], ub=[1.0], max_iter=100, gtol=1e-8)
+    sim = BatchedSimulator(solver, lambda x, u: a_coef * x + b_coef * u, num_iters=12)
+    x0 = np.linspace(-1.5, 1.5, B)[:, None]
+    out = sim.run(x0, np.full(B, -1.0))
+    assert out["states"].shape == (13, B, E) and out["actions"].shape == (12, B, m) and out["solves"] == 12 * B
+    assert np.all(np.abs(out["states"][-1]) < 1e-2) and np.all(np.abs(out["actions"]) <= 1.0 + 1e-12)
+    far = np.abs(x0[:, 0]) > 0.1
+    assert np.all(np.abs(out["states"][3, far, 0]) < 0.5 * np.abs(x0[far, 0]))                    # the controller, not the plant's 0.9
