@@ -730,7 +730,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=4096)
+    ap.add_argument("--n", "--ntrain", dest="n", type=int, default=4096,
+                    help="training points (use --ntrain under torchrun: its own parser claims the abbreviation --n)")
     ap.add_argument("--H", type=int, default=30)
     ap.add_argument("--B", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")

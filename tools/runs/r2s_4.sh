@@ -1,7 +1,7 @@
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29541"
-timeout 600 $TR bench.py --config 7 --gpus 4 --n 16384 --H 20 --steps 5 --warmup 2 > gpurun_out/r2s_split16k_n4.txt 2>&1
-timeout 300 $TR bench.py --config 7 --gpus 4 --n 4096 --H 30 --steps 20 --warmup 3 > gpurun_out/r2s_split4k_n4.txt 2>&1
+timeout 600 $TR bench.py --config 7 --gpus 4 --ntrain 16384 --H 20 --steps 5 --warmup 2 > gpurun_out/r2s_split16k_n4.txt 2>&1
+timeout 300 $TR bench.py --config 7 --gpus 4 --ntrain 4096 --H 30 --steps 20 --warmup 3 > gpurun_out/r2s_split4k_n4.txt 2>&1
 timeout 900 $TR bench.py --config 5 --gpus 4 --instances 2048 > gpurun_out/r2s_cfg5_n4.txt 2>&1
 timeout 600 $TR bench.py --gpus 4 --steps 5 --warmup 3 > gpurun_out/r2s_bench_n4.txt 2>&1
 tail -n 2 gpurun_out/r2s_split16k_n4.txt gpurun_out/r2s_split4k_n4.txt gpurun_out/r2s_cfg5_n4.txt gpurun_out/r2s_bench_n4.txt | cut -c1-600
