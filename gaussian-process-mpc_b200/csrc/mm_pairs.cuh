@@ -39,6 +39,12 @@ namespace gpmpc {
 #ifndef GPMPC_DYNAMIC
 #define GPMPC_DYNAMIC 1          // 1: CTAs draw work items from a ticket counter; 0: item = CTA index
 #endif
+#ifndef GPMPC_ROWSUM
+#define GPMPC_ROWSUM 0           // 1: N1 = sum w (z_i + z_j) through row sums (per RI x 32 strip) and column sums (per RI x CJ
+#endif                           //    micro-tile) of w instead of D FMAs per pair and output
+#ifndef GPMPC_CJ
+#define GPMPC_CJ 1               // columns of the register micro-tile (GPMPC_ROWSUM=1 only)
+#endif
 #ifndef GPMPC_MINBLOCKS
 #define GPMPC_MINBLOCKS 2        // CTAs per SM promised to ptxas
 #endif
@@ -337,6 +343,76 @@ mm_pairs_batch(const PairArgs a)
             const double *xj = xi + PT * D;
 
             if (warp_active) {
+#if GPMPC_ROWSUM
+            if constexpr (GRAD != 0) {
+            // N1_k = sum w (z_ik + z_jk) = sum_i z_ik R_i + sum_j z_jk C_j with R_i / C_j the row / column sums of w inside the
+            // strip / micro-tile: 1 + 1 + D / RI adds and FMAs per pair and output instead of 1 + D.
+            constexpr int CJ = GPMPC_CJ;
+#pragma unroll 1
+            for (int r0 = 0; r0 < PT; r0 += RI) {
+                double zi[RI][D], rs[RI][EG];
+#pragma unroll
+                for (int r = 0; r < RI; ++r) {
+#pragma unroll
+                    for (int k = 0; k < D; ++k) zi[r][k] = fma(-GP_C(k), xi[(r0 + r) * D + k], GP_CU(k));
+#pragma unroll
+                    for (int g = 0; g < EG; ++g) rs[r][g] = 0.0;
+                }
+#pragma unroll 1
+                for (int j = 0; j < PTJ; j += CJ) {
+                    double zj[CJ][D], cs_[CJ][EG];
+#pragma unroll
+                    for (int c = 0; c < CJ; ++c)
+#pragma unroll
+                        for (int k = 0; k < D; ++k) zj[c][k] = fma(-GP_C(k), xj[(j + c) * D + k], GP_CU(k));
+#pragma unroll
+                    for (int r = 0; r < RI; ++r) {
+#pragma unroll
+                        for (int c = 0; c < CJ; ++c) {
+                            double q[D], qq[D];
+#pragma unroll
+                            for (int k = 0; k < D; ++k) { q[k] = zi[r][k] + zj[c][k]; qq[k] = q[k] * q[k]; }
+                            double S = qq[0];
+                            if (D >= 4) {
+                                double S2 = qq[2] + qq[3];
+                                S += qq[1];
+#pragma unroll
+                                for (int k = 4; k < D; k += 2) { S += qq[k]; if (k + 1 < D) S2 += qq[k + 1]; }
+                                S += S2;
+                            } else {
+#pragma unroll
+                                for (int k = 1; k < D; ++k) S += qq[k];
+                            }
+                            const double e = exp_neg(S, tab);
+#pragma unroll
+                            for (int g = 0; g < EG; ++g) {
+                                const double w = Ws[(size_t)g * PT * PTJ + (r0 + r) * PTJ + j + c] * e;
+                                rs[r][g] += w;
+                                if (r == 0) cs_[c][g] = w; else cs_[c][g] += w;
+#pragma unroll
+                                for (int k = 0; k < K2; ++k) acc2[g][k] = fma(w, qq[k], acc2[g][k]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < CJ; ++c)
+#pragma unroll
+                        for (int g = 0; g < EG; ++g)
+#pragma unroll
+                            for (int k = K1; k < D; ++k) acc1[g][k] = fma(cs_[c][g], zj[c][k], acc1[g][k]);
+                }
+#pragma unroll
+                for (int r = 0; r < RI; ++r)
+#pragma unroll
+                    for (int g = 0; g < EG; ++g) {
+                        accT[g] += rs[r][g];
+#pragma unroll
+                        for (int k = K1; k < D; ++k) acc1[g][k] = fma(rs[r][g], zi[r][k], acc1[g][k]);
+                    }
+            }
+            } else
+#endif
+            {
             // RI-row register micro-tile per column: RI independent q -> q^2 -> sum -> exp chains (15 deep each) and
             // RI x EG x (1 + moments) independent accumulation FMAs per basic block, interleaved by the compiler.
 #pragma unroll 1
@@ -381,6 +457,7 @@ mm_pairs_batch(const PairArgs a)
                         }
                     }
                 }
+            }
             }
             }
             __syncthreads();

@@ -1309,3 +1309,24 @@ def test_batched_closed_loop_simulator_on_the_device(gp):
     assert out["states"].shape == (7, 12, E) and np.all(np.isfinite(out["costs"]))
     assert np.all(np.linalg.norm(out["states"][-1], axis=1) < np.linalg.norm(out["states"][0], axis=1))
     assert dyn.gpr_err[0].num_train == n + 2 * 6
+
+
+def test_single_rollout_split_over_two_gpus(gp):
+    """One rollout split over the GPUs of the node (gpmpc_split_*, one process per GPU under torchrun): the kernels
+    exchange their per-step sums through peer-mapped mailboxes; every rank must reproduce the single-GPU cost and
+    gradient.  Needs two devices (skipped on a one-GPU box)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29547", os.path.join(root, "bench.py"), "--config", "7", "--gpus", "2", "--ntrain", "1500", "--H", "6",
+           "--steps", "2", "--warmup", "1"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-1500:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert d["n_gpus"] == 2 and d["vs_single_gpu_result"]["cost_rel_err"] <= 1e-9
+    assert d["vs_single_gpu_result"]["grad_err_over_max"] <= 1e-8
