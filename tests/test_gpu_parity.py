@@ -1330,3 +1330,39 @@ def test_single_rollout_split_over_two_gpus(gp):
     d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
     assert d["n_gpus"] == 2 and d["vs_single_gpu_result"]["cost_rel_err"] <= 1e-9
     assert d["vs_single_gpu_result"]["grad_err_over_max"] <= 1e-8
+
+
+@pytest.mark.parametrize("E,m", [(1, 1), (2, 2), (5, 1), (6, 2)])
+def test_full_covariance_dimension_sweep_vs_oracle(gp, E, m):
+    """Every compiled input dimension of the full-covariance kernels (D = 2, 4, 6, 8; pieces of 1, 3, 10 + 4 + 1 and 10 + 10 + 1
+    pair-outputs): means, covariances and cost against the oracle, gradient against central differences."""
+    from oracle import oracle as orc
+    n, H, B = 90, 3, 3
+    D = E + m
+    S, A, nxt, rng = _synth(n, E, m, seed=40 + D)
+    lam = np.full((E, D), 1.8); sf = np.ones(E); sn = np.full(E, 0.12)
+    if E >= 5:
+        lam[E - 1] = rng.uniform(1.0, 3.0, D)            # one output with its own length-scales: a non-symmetric unit
+    dyn = gp.Dynamics(E, m)
+    for a in range(E):
+        dyn.gpr_err[a].set_lambdas(lam[a]); dyn.gpr_err[a].set_sigma_n(np.float64(sn[a]))
+    dyn.append_train_data(S, A, nxt)
+    X = np.concatenate([S, A], 1)
+    fits = [orc.fit(X, nxt[:, a], lam[a], sf[a], float(np.float32(sn[a] ** 2)) ** 0.5) for a in range(E)]
+    Kis = [f["Ky_inv"] for f in fits]; betas = [f["beta"] for f in fits]
+    Q = 2.0 * np.eye(E); R = 0.01 * np.eye(m)
+    x0 = rng.uniform(-0.5, 0.5, (B, E)); U = rng.uniform(-0.3, 0.3, (B, H, m))
+    br = gp.BatchedRollouts(dyn, Q, R, full=True)
+    cost, grad = br.cost_and_grad(x0, U, -1.0, host_out=True)
+    _, _, means, covs = dyn._bundle.cost_grad(x0, U, np.full(B, -1.0), Q, R, want_traj=True, full=True)
+    for b in range(B):
+        c, mo, co = orc.rollout_full_cost(X, Kis, betas, lam, sf, x0[b], U[b], -1.0, Q, R, use_c=True)
+        norm_close(means[b], mo, 1e-8)
+        assert np.max(np.abs(covs[b] - co)) <= RTOL * max(np.max(np.abs(co)), 1e-3)
+        close(cost[b], c, RTOL)
+    h = 1e-5
+    Upm = np.repeat(U[:1], 2 * H * m, axis=0)
+    for k in range(H * m):
+        Upm[2 * k].reshape(-1)[k] += h; Upm[2 * k + 1].reshape(-1)[k] -= h
+    cp, _ = br.cost_and_grad(np.repeat(x0[:1], 2 * H * m, axis=0), Upm, -1.0, host_out=True)
+    norm_close(grad[0].reshape(-1), (cp[0::2] - cp[1::2]) / (2 * h), 2e-5)
