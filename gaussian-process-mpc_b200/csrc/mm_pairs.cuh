@@ -40,10 +40,13 @@ namespace gpmpc {
 #define GPMPC_DYNAMIC 1          // 1: CTAs draw work items from a ticket counter; 0: item = CTA index
 #endif
 #ifndef GPMPC_ROWSUM
-#define GPMPC_ROWSUM 0           // 1: N1 = sum w (z_i + z_j) through row sums (per RI x 32 strip) and column sums (per RI x CJ
-#endif                           //    micro-tile) of w instead of D FMAs per pair and output
+#define GPMPC_ROWSUM 1           // 1: gradient variants form N1 = sum w (z_i + z_j) from row sums (per strip) and column sums (per
+#endif                           //    micro-tile) of w instead of D FMAs per pair and output (round 2: 40.6 -> 37.0 ms per launch)
+#ifndef GPMPC_RS_RI
+#define GPMPC_RS_RI 2            // rows x columns of the register micro-tile of the row/column-sum form: 2 x 2 = four independent
+#endif                           // exp chains like the 4 x 1 tile, but half the row sums (4 x 1: 47.8 ms, registers; 2 x 1: 39.2 ms)
 #ifndef GPMPC_CJ
-#define GPMPC_CJ 1               // columns of the register micro-tile (GPMPC_ROWSUM=1 only)
+#define GPMPC_CJ 2
 #endif
 #ifndef GPMPC_MINBLOCKS
 #define GPMPC_MINBLOCKS 2        // CTAs per SM promised to ptxas
@@ -346,13 +349,13 @@ mm_pairs_batch(const PairArgs a)
 #if GPMPC_ROWSUM
             if constexpr (GRAD != 0) {
             // N1_k = sum w (z_ik + z_jk) = sum_i z_ik R_i + sum_j z_jk C_j with R_i / C_j the row / column sums of w inside the
-            // strip / micro-tile: 1 + 1 + D / RI adds and FMAs per pair and output instead of 1 + D.
-            constexpr int CJ = GPMPC_CJ;
+            // strip / micro-tile: 1 + 1/2 + D/2 adds and FMAs per pair and output (2 x 2 tile) instead of 1 + D.
+            constexpr int CJ = GPMPC_CJ, RSR = GPMPC_RS_RI;
 #pragma unroll 1
-            for (int r0 = 0; r0 < PT; r0 += RI) {
-                double zi[RI][D], rs[RI][EG];
+            for (int r0 = 0; r0 < PT; r0 += RSR) {
+                double zi[RSR][D], rs[RSR][EG];
 #pragma unroll
-                for (int r = 0; r < RI; ++r) {
+                for (int r = 0; r < RSR; ++r) {
 #pragma unroll
                     for (int k = 0; k < D; ++k) zi[r][k] = fma(-GP_C(k), xi[(r0 + r) * D + k], GP_CU(k));
 #pragma unroll
@@ -366,7 +369,7 @@ mm_pairs_batch(const PairArgs a)
 #pragma unroll
                         for (int k = 0; k < D; ++k) zj[c][k] = fma(-GP_C(k), xj[(j + c) * D + k], GP_CU(k));
 #pragma unroll
-                    for (int r = 0; r < RI; ++r) {
+                    for (int r = 0; r < RSR; ++r) {
 #pragma unroll
                         for (int c = 0; c < CJ; ++c) {
                             double q[D], qq[D];
@@ -402,7 +405,7 @@ mm_pairs_batch(const PairArgs a)
                             for (int k = K1; k < D; ++k) acc1[g][k] = fma(cs_[c][g], zj[c][k], acc1[g][k]);
                 }
 #pragma unroll
-                for (int r = 0; r < RI; ++r)
+                for (int r = 0; r < RSR; ++r)
 #pragma unroll
                     for (int g = 0; g < EG; ++g) {
                         accT[g] += rs[r][g];

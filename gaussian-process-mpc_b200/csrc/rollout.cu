@@ -562,7 +562,8 @@ static void pair_geometry(gpmpc_ctx *h, int B, long long total_tiles, int &ctas_
     if (c > total_tiles) c = total_tiles;
     // few rollout chunks -> many CTAs per chunk and few tiles per CTA: fewer, larger items (per-item cost: a ticket,
     // two barriers and a partial-sum store); measured on B200 at n=4096, B=128: 2 items per CTA 628, 4 items 763, 8 items 712 evals/s
-    long long it = c * (chunks >= 4 ? kItemsPerCta : (chunks >= 2 ? 8 : 4));
+    // (round 2, faster kernel, tools/pair_bench.cu: B=256 -> 4 items 10.13 ms, 8 items 10.59; B=512 -> 16 items 20.00, 4 items 20.23)
+    long long it = c * (chunks >= 4 ? kItemsPerCta : 4);
     if (it > total_tiles) it = total_tiles;
     ctas_per_chunk = (int)c;
     n_items = (int)it;
