@@ -36,11 +36,16 @@ UNIT = "evals/s"
 
 def pair_ops_per_eval(D, E, m, H, first_step_const=True):
     """FP64-pipe instructions per (rollout, pair) of one H-step evaluation for outputs sharing one exp:
-    chain (D adds, D squares, D-1 adds) + 11 (table exp) per pair, and per output w, T, N1_k (every input dimension)
-    and N2_k (state dimensions only); the first step keeps only N1 of the action dimensions (x0, Sigma_0 constant)."""
+    chain (D adds, D squares, D-1 adds) + 11 (table exp) per pair; per output w, a row-sum add, half a column-sum add,
+    N2_k for the state dimensions, and -- N1 from row / column sums on the 2 x 2 micro-tile -- (D - k1) / 2 column FMAs plus
+    (1 + D - k1) / 32 row FMAs, k1 = first dimension whose N1 is kept.  The first step keeps only N1 of the action
+    dimensions and no N2 (x0, Sigma_0 constant).  The per-column z_j (D / 2 per pair) is not counted."""
     chain = 3 * D - 1 + 11
-    full = chain + E * (2 + D + (D - m))
-    first = chain + E * (2 + m) if first_step_const else full
+
+    def per_output(k1, k2):
+        return 1 + 1 + 0.5 + (D - k1) / 2.0 + k2 + (1 + D - k1) / 32.0
+    full = chain + E * per_output(0, D - m)
+    first = chain + E * per_output(D - m, 0) if first_step_const else full
     return first + (H - 1) * full if H >= 1 else 0
 
 
@@ -317,7 +322,8 @@ def run_ours(args):
     pairs = pair_evals / E                                 # (rollout, pair) evaluations, 4 outputs each
     pairs_per_rollout_step = n * (n + 1) / 2
     assert abs(pairs - Bl * H * pairs_per_rollout_step) < 1e-6 * pairs
-    ops = pair_ops_per_eval(D, E, m, H) if not args.ard else H * (3 * D - 1 + 11 + 2 + D + (D - m)) * E
+    # --ard: one launch per output (no shared exp), same per-output accumulation
+    ops = pair_ops_per_eval(D, E, m, H) if not args.ard else E * pair_ops_per_eval(D, 1, m, H)
     achieved_tflops = Bl * pairs_per_rollout_step * ops * 2.0 / (pair_ms * 1e-3) / 1e12
     bytes_algo = H * E * (n * (n + 1) / 2) * 8.0           # Wt upper triangle once per step and output
     sms = torch.cuda.get_device_properties(dev).multi_processor_count

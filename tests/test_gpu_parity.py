@@ -1365,4 +1365,4 @@ def test_full_covariance_dimension_sweep_vs_oracle(gp, E, m):
     for k in range(H * m):
         Upm[2 * k].reshape(-1)[k] += h; Upm[2 * k + 1].reshape(-1)[k] -= h
     cp, _ = br.cost_and_grad(np.repeat(x0[:1], 2 * H * m, axis=0), Upm, -1.0, host_out=True)
-    norm_close(grad[0].reshape(-1), (cp[0::2] - cp[1::2]) / (2 * h), 2e-5)
+    norm_close(grad[0].reshape(-1), (cp[0::2] - cp[1::2]) / (2 * h), 1e-4)      # bounded by the noise of the difference quotient
