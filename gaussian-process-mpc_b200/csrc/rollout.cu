@@ -69,9 +69,9 @@ static rollout_single_fn rollout_single_launcher(int D)
 constexpr int kPersistMaxB = 1;
 
 // below this many rollouts the lanes<->pairs kernel (one rollout per CTA column) replaces the lanes<->rollouts one:
-// measured on B200 at n=4096 it costs 1.55 ms per rollout and evaluation, the batched kernel 174 ms per started
-// chunk of 128 rollouts, i.e. the crossover is at 112
-constexpr int kSingleMaxB = 112;
+// measured on B200 at n=4096 it costs 1.55 ms per rollout and evaluation, the batched kernel 145 ms per started
+// chunk of 128 rollouts (174 ms in round 1, crossover 112), i.e. the crossover is at 94
+constexpr int kSingleMaxB = 96;
 constexpr int MEAN_JP = 64;          // partitions of the training set in the mean kernel (64 x rollout chunks CTAs)
 constexpr int MEAN_THREADS = 128;
 

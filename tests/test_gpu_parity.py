@@ -758,7 +758,7 @@ def test_randomized_shapes_vs_c_oracle(gp, seed):
     xref = rng.uniform(-0.2, 0.2, E); uref = rng.uniform(-0.1, 0.1, m)
     gamma = float(rng.choice([-1.0, -0.5, 0.7]))
     br = gp.BatchedRollouts(dyn, Q, R, R_delta=Rd, x_ref=xref, u_ref=uref)
-    for B in (int(rng.integers(1, 8)), int(rng.integers(112, 200))):
+    for B in (int(rng.integers(1, 8)), int(rng.integers(96, 200))):
         x0 = rng.uniform(-0.5, 0.5, (B, E)); U = rng.uniform(-0.3, 0.3, (B, H, m))
         lu = rng.uniform(-0.3, 0.3, (B, m)) if Rd is not None else None
         cost, grad = br.cost_and_grad(x0, U, gamma, last_u=lu, host_out=True)
@@ -829,26 +829,31 @@ def test_numpy_interface_moment_matching_twins(gp):
 
 
 def test_kernel_switch_boundary_and_long_horizon(gp):
-    """B = 111 runs the few-rollouts kernel, B = 112 the batched one: the shared rollouts must agree across the switch;
+    """B = 95 runs the few-rollouts kernel, B = 96 the batched one: the shared rollouts must agree across the switch;
     a long horizon (H = 64, tape and adjoint buffers beyond the usual sizes) against the C oracle."""
     from oracle import oracle as orc
     n, E, m, H = 200, 3, 1, 64
+    SW = 96                                        # kSingleMaxB in csrc/rollout.cu
     dyn, S, A, nxt, rng = _synth_dynamics(gp, n, E, m, seed=77)
     Q = 2 * np.eye(E); R = 0.01 * np.eye(m)
     br = gp.BatchedRollouts(dyn, Q, R)
-    x0 = rng.uniform(-0.5, 0.5, (112, E)); U = rng.uniform(-0.3, 0.3, (112, H, m))
-    c111, g111 = br.cost_and_grad(x0[:111], U[:111], -1.0, host_out=True)
-    c112, g112 = br.cost_and_grad(x0, U, -1.0, host_out=True)
-    close(c111, c112[:111], 1e-9)
-    norm_close(g111, g112[:111], 1e-8)
+    x0 = rng.uniform(-0.5, 0.5, (SW, E)); U = rng.uniform(-0.3, 0.3, (SW, H, m))
+    l0 = dyn._bundle.launch_count()
+    c_few, g_few = br.cost_and_grad(x0[:SW - 1], U[:SW - 1], -1.0, host_out=True)
+    l1 = dyn._bundle.launch_count()
+    c_bat, g_bat = br.cost_and_grad(x0, U, -1.0, host_out=True)
+    l2 = dyn._bundle.launch_count()
+    assert (l2 - l1) > (l1 - l0) + H               # the batched path launches pair + mean + finalize kernels per step
+    close(c_few, c_bat[:SW - 1], 1e-9)
+    norm_close(g_few, g_bat[:SW - 1], 1e-8)
     X = np.concatenate([S, A], 1)
     lam = np.full((E, E + m), 2.0)
     fits = [orc.fit(X, nxt[:, a], lam[a], 1.0, float(np.float32(0.1 ** 2)) ** 0.5) for a in range(E)]
-    for b in (0, 111):
+    for b in (0, SW - 1):
         c, gr, _, _ = orc.c_rollout_cost_grad(X, [f["Ky_inv"] for f in fits], [f["beta"] for f in fits], lam, np.ones(E),
                                               x0[b], U[b], -1.0, Q, R)
-        close(c112[b], c, RTOL)
-        norm_close(g112[b], gr, RTOL)
+        close(c_bat[b], c, RTOL)
+        norm_close(g_bat[b], gr, RTOL)
 
 
 # ------------------------------------------------------------------------------------------------
