@@ -89,6 +89,10 @@ struct gpmpc_ctx {
     gpmpc::DevBuf Wx, fc_plan, fc_mu, fc_cov, fc_cst, fc_raw, fc_part, fc_red, fc_gbar, fc_seed, fc_carry, fc_io;
     int fc_B = 0, fc_H = 0;        // shape of the full-covariance tape held from the last gpmpc_rollout_full
 
+    // L2 persistence for the few-rollouts kernels (rollout.cu): device limits, queried once
+    bool opt_l2_persist = true;
+    long long l2_persist_max = -1, l2_window_max = 0;
+
     // gpmpc_set_option
     bool opt_persistent = false;   // single rollouts: whole horizon in one persistent cooperative launch (measured 8 % slower
                                    // than one launch per step on one GPU; always used when the rollout is split over GPUs)

@@ -54,10 +54,19 @@ static cudaError_t launch_single_one(const SingleStepArgs &a, dim3 grid, cudaStr
     // TMA tile loads) with the previous grid's tail; the kernel orders itself with griddepcontrol.wait
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = dim3(SINGLE_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    if (a.l2_bytes > 0) {
+        attr[1].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[1].val.accessPolicyWindow.base_ptr = const_cast<void *>(a.l2_base);
+        attr[1].val.accessPolicyWindow.num_bytes = a.l2_bytes;
+        attr[1].val.accessPolicyWindow.hitRatio = a.l2_hit;
+        attr[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.numAttrs = 2;
+    }
     return cudaLaunchKernelEx(&cfg, mm_step_single<D, EG, GRAD, NS>, a);
 }
 

@@ -64,6 +64,10 @@ struct SingleStepArgs {
     double *us_w, *cst_w;
     double act_var;
     unsigned long long *dbg;       // optional [B*P][6] globaltimer stamps (GPMPC_STEP_DEBUG=1), else NULL
+    // host side only (launch attribute, not read by the kernel): L2 access-policy window over the weights.  Every step
+    // streams the same Wt; a plain LRU keeps none of a working set larger than L2 across steps, a persisting fraction
+    // that fits stays resident
+    const void *l2_base; size_t l2_bytes; float l2_hit;
 };
 
 __device__ __forceinline__ unsigned long long gtime()

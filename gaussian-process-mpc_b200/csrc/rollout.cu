@@ -620,6 +620,24 @@ static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int ctas, int P, lon
             sa.prep_next = (next.on && d.G == 1) ? 1 : 0;
             sa.Uint = next.Uint; sa.lam_group = next.lam_group; sa.us_w = us; sa.cst_w = cst; sa.act_var = next.act_var;
             sa.dbg = nullptr;
+            sa.l2_base = nullptr; sa.l2_bytes = 0; sa.l2_hit = 0.f;
+            if (h->opt_l2_persist) {
+                if (h->l2_persist_max < 0) {                 // first use: device limits, carve out the persisting part of L2
+                    int pm = 0, wm = 0;
+                    cudaDeviceGetAttribute(&pm, cudaDevAttrMaxPersistingL2CacheSize, h->device);
+                    cudaDeviceGetAttribute(&wm, cudaDevAttrMaxAccessPolicyWindowSize, h->device);
+                    h->l2_persist_max = pm; h->l2_window_max = wm;
+                    if (pm > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)pm);
+                }
+                const size_t wbytes = (size_t)d.E * wt_doubles(h->ld) * sizeof(double);
+                if (h->l2_persist_max > 0 && h->l2_window_max > 0 && wbytes > (size_t)h->l2_persist_max) {
+                    // a working set that fits L2 anyway needs no policy
+                    sa.l2_base = h->Wt.p;
+                    sa.l2_bytes = wbytes < (size_t)h->l2_window_max ? wbytes : (size_t)h->l2_window_max;
+                    const double hit = 0.9 * (double)h->l2_persist_max / (double)sa.l2_bytes;
+                    sa.l2_hit = (float)(hit > 1.0 ? 1.0 : hit);
+                }
+            }
             static const bool step_debug = getenv("GPMPC_STEP_DEBUG") != nullptr;
             if (step_debug) {                            // development aid: per-CTA phase stamps of every launch
                 GP_CUDA(h, h->dbg.reserve((size_t)d.B * ctas * 6 * sizeof(unsigned long long)));

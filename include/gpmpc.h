@@ -58,7 +58,9 @@ int gpmpc_synchronize(gpmpc_handle h);
  *   "persistent_single" (0): 1 = a single rollout (B = 1, one IPOPT callback, src/mpc.py:202-255) runs its whole horizon
  *                            in one persistent cooperative launch; 0 = one fused launch per horizon step (measured faster
  *                            on one GPU).  A rollout split over several GPUs (gpmpc_split_*) always uses the persistent kernel.
- *   "split_timeline" (0):    stamp the inter-GPU exchange of every step (see gpmpc_split_last_exchange_us).           */
+ *   "split_timeline" (0):    stamp the inter-GPU exchange of every step (see gpmpc_split_last_exchange_us).
+ *   "l2_persist" (1):        few-rollouts kernels launch with an L2 access-policy window over the weights so that the part
+ *                            of Wt that fits the persisting L2 carve-out stays resident from one horizon step to the next. */
 int gpmpc_set_option(gpmpc_handle h, const char *name, int value);
 int gpmpc_num_train(gpmpc_handle h);
 
