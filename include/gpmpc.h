@@ -59,8 +59,9 @@ int gpmpc_synchronize(gpmpc_handle h);
  *                            in one persistent cooperative launch; 0 = one fused launch per horizon step (measured faster
  *                            on one GPU).  A rollout split over several GPUs (gpmpc_split_*) always uses the persistent kernel.
  *   "split_timeline" (0):    stamp the inter-GPU exchange of every step (see gpmpc_split_last_exchange_us).
- *   "l2_persist" (1):        few-rollouts kernels launch with an L2 access-policy window over the weights so that the part
- *                            of Wt that fits the persisting L2 carve-out stays resident from one horizon step to the next. */
+ *   "l2_persist" (0):        1 = few-rollouts kernels launch with an L2 access-policy window over the weights so that the
+ *                            part of Wt that fits the persisting L2 carve-out stays resident from one horizon step to the
+ *                            next (measured: no effect on B200, the kernel is not bound by the stream alone).            */
 int gpmpc_set_option(gpmpc_handle h, const char *name, int value);
 int gpmpc_num_train(gpmpc_handle h);
 
