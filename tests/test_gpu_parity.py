@@ -1371,3 +1371,39 @@ def test_full_covariance_dimension_sweep_vs_oracle(gp, E, m):
         Upm[2 * k].reshape(-1)[k] += h; Upm[2 * k + 1].reshape(-1)[k] -= h
     cp, _ = br.cost_and_grad(np.repeat(x0[:1], 2 * H * m, axis=0), Upm, -1.0, host_out=True)
     norm_close(grad[0].reshape(-1), (cp[0::2] - cp[1::2]) / (2 * h), 1e-4)      # bounded by the noise of the difference quotient
+
+
+def test_full_covariance_on_the_shipped_experiment_incl_nan_semantics(gp):
+    """The reference's own experiment data (config 1, sigma_n = 1e-5) through the full-covariance rollout via the
+    cyipopt-protocol callbacks (`RiskSensitiveMPC.full_covariance = True`): cost against the oracle for the four shipped
+    control sequences, including those whose log(det(I + gamma Q Sigma)) is NaN (src/mpc.py:183) -- the NaN must come back
+    as data, exactly where the oracle has it."""
+    from oracle import oracle as orc
+    g = golden("shipped")
+    H = 6
+    mpc = gp.RiskSensitiveMPC(-1, H, 2, 2, 2 * np.identity(2), np.zeros((2, 2)), None)
+    for i in range(2):
+        mpc.dynamics.gpr_err[i].set_sigma_n(np.float64(g["ship_sn"][i]))
+        mpc.dynamics.gpr_err[i].set_lambdas(np.asarray(g["ship_lam"][i], dtype=np.float64))
+        mpc.dynamics.gpr_err[i].set_sigma_f(np.float64(g["ship_sf"][i]))
+    mpc.dynamics.append_train_data(g["ship_S"], g["ship_A"], g["ship_next"])
+    mpc.set_xref(np.array([0., 0.])); mpc.set_uref(np.array([0., 0.]))
+    mpc.curr_state = T(g["ship_x0"])
+    mpc.full_covariance = True
+    X = np.concatenate([g["ship_S"], g["ship_A"]], 1)
+    fits = [orc.fit(X, g["ship_next"][:, a], g["ship_lam"][a], float(g["ship_sf"][a]),
+                    float(np.float32(float(g["ship_sn"][a]) ** 2)) ** 0.5) for a in range(2)]
+    n_nan = 0
+    for i in range(4):
+        U = g[f"ship_U{i}"]
+        c = mpc.objective(U.reshape(-1).copy())
+        grad = np.asarray(mpc.gradient(U.reshape(-1).copy()))
+        ref, _, _ = orc.rollout_full_cost(X, [f["Ky_inv"] for f in fits], [f["beta"] for f in fits], g["ship_lam"], g["ship_sf"],
+                                          g["ship_x0"], U, -1.0, 2 * np.identity(2), np.zeros((2, 2)), use_c=True)
+        assert np.isnan(c) == np.isnan(ref), (i, c, ref)
+        assert grad.shape == (H, 2)
+        if np.isnan(ref):
+            n_nan += 1
+        else:
+            close(c, ref, 1e-5)          # cond(Ky) = 2.6e6 and an LU-inverse oracle vs the Cholesky-based device inverse
+    assert n_nan >= 1
