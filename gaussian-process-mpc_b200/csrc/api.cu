@@ -91,7 +91,6 @@ extern "C" int gpmpc_set_option(gpmpc_handle h, const char *name, int value)
     if (!h || !name) return GPMPC_ERR_INVALID;
     if (std::strcmp(name, "persistent_single") == 0) { h->opt_persistent = value != 0; return GPMPC_OK; }
     if (std::strcmp(name, "split_timeline") == 0) { h->opt_split_timeline = value != 0; return GPMPC_OK; }
-    if (std::strcmp(name, "single_split") == 0) { h->opt_single_split = value == 2 ? 2 : 1; return GPMPC_OK; }
     if (std::strcmp(name, "l2_persist") == 0) {
         h->opt_l2_persist = value != 0;
         if (!h->opt_l2_persist) { cudaSetDevice(h->device); cudaCtxResetPersistingL2Cache(); }

@@ -93,8 +93,6 @@ struct gpmpc_ctx {
     bool opt_l2_persist = false;   // measured on B200: no effect (2.139 vs 2.146 ms at n=4096, 18.8 vs 18.4 ms at n=16384)
     long long l2_persist_max = -1, l2_window_max = 0;
 
-    int opt_single_split = 1;      // ring granularity of the few-rollouts step kernel: 1 whole tiles, 2 half tiles
-
     // gpmpc_set_option
     bool opt_persistent = false;   // single rollouts: whole horizon in one persistent cooperative launch (measured 8 % slower
                                    // than one launch per step on one GPU; always used when the rollout is split over GPUs)

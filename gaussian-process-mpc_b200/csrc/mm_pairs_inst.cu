@@ -40,13 +40,13 @@ static cudaError_t launch_one(const PairArgs &a, dim3 grid, cudaStream_t st)
     return cudaGetLastError();
 }
 
-template <int D, int EG, int GRAD, int NS, int SPLIT>
-static cudaError_t launch_single_split(const SingleStepArgs &a, dim3 grid, cudaStream_t st)
+template <int D, int EG, int GRAD, int NS>
+static cudaError_t launch_single_one(const SingleStepArgs &a, dim3 grid, cudaStream_t st)
 {
-    const size_t smem = single_smem_bytes<D, EG, SPLIT>();
+    const size_t smem = single_smem_bytes<D, EG>();
     static bool configured[kMaxDevices] = {};
     if (first_use_on_device(configured)) {
-        cudaError_t e = cudaFuncSetAttribute(mm_step_single<D, EG, GRAD, NS, SPLIT>,
+        cudaError_t e = cudaFuncSetAttribute(mm_step_single<D, EG, GRAD, NS>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
@@ -67,13 +67,7 @@ static cudaError_t launch_single_split(const SingleStepArgs &a, dim3 grid, cudaS
         attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
         cfg.numAttrs = 2;
     }
-    return cudaLaunchKernelEx(&cfg, mm_step_single<D, EG, GRAD, NS, SPLIT>, a);
-}
-
-template <int D, int EG, int GRAD, int NS>
-static cudaError_t launch_single_one(const SingleStepArgs &a, dim3 grid, cudaStream_t st)
-{
-    return a.split == 2 ? launch_single_split<D, EG, GRAD, NS, 2>(a, grid, st) : launch_single_split<D, EG, GRAD, NS, 1>(a, grid, st);
+    return cudaLaunchKernelEx(&cfg, mm_step_single<D, EG, GRAD, NS>, a);
 }
 
 // Moment selection (mm_pairs.cuh): grad_mode 0 forward only, 1 all steps, 2 first step without d/dx0; ns = number of

@@ -68,7 +68,6 @@ struct SingleStepArgs {
     // streams the same Wt; a plain LRU keeps none of a working set larger than L2 across steps, a persisting fraction
     // that fits stays resident
     const void *l2_base; size_t l2_bytes; float l2_hit;
-    int split;                     // host side only: 1 = whole tiles per ring stage, 2 = 16-row slabs (twice the stages)
 };
 
 __device__ __forceinline__ unsigned long long gtime()
@@ -79,13 +78,10 @@ __device__ __forceinline__ unsigned long long gtime()
 }
 #define GP_STAMP(i) do { if (a.dbg && tid == 0) a.dbg[((size_t)b * P + bx) * 6 + (i)] = gtime(); } while (0)
 
-// SPLIT = row slabs per 32 x 32 tile that travel as separate ring stages (1: whole tiles, 3 slots; 2: 16-row slabs, 6 slots
-// in the same shared memory: finer-grained refills keep more bytes in flight while a slab is consumed)
-template <int SPLIT> __host__ __device__ constexpr int single_stages() { return SPLIT == 1 ? SINGLE_STAGES : SINGLE_STAGES * SPLIT; }
-template <int D, int EG, int SPLIT = 1>
-__host__ __device__ constexpr size_t single_stage_doubles() { return (size_t)EG * (PT / SPLIT) * PT + PT * D; }
-template <int D, int EG, int SPLIT = 1>
-__host__ __device__ constexpr size_t single_smem_bytes() { return single_stages<SPLIT>() * single_stage_doubles<D, EG, SPLIT>() * sizeof(double); }
+template <int D, int EG>
+__host__ __device__ constexpr size_t single_stage_doubles() { return (size_t)EG * PT * PT + PT * D; }
+template <int D, int EG>
+__host__ __device__ constexpr size_t single_smem_bytes() { return SINGLE_STAGES * single_stage_doubles<D, EG>() * sizeof(double); }
 
 __device__ __forceinline__ void mbar_arrive(void *bar)
 {
@@ -93,18 +89,15 @@ __device__ __forceinline__ void mbar_arrive(void *bar)
 }
 
 // GRAD / NS select the accumulated moments exactly as in mm_pairs_batch (mm_pairs.cuh).
-template <int D, int EG, int GRAD, int NS, int SPLIT = 1>
+template <int D, int EG, int GRAD, int NS>
 __global__ void __launch_bounds__(SINGLE_THREADS, SINGLE_CTAS_PER_SM)
 mm_step_single(const SingleStepArgs a)
 {
-    constexpr int NSTAGE = single_stages<SPLIT>();
-    constexpr int SR = PT / SPLIT;               // rows per stage
-    constexpr int SROWS = SR / SINGLE_WARPS;     // rows of a stage handled by one thread
     constexpr int K1 = GRAD == 2 ? NS : 0;       // N1_k for k in [K1, D)
     constexpr int K2 = GRAD == 1 ? NS : 0;       // N2_k for k in [0, K2)
     constexpr int NA = 1 + 2 * D;
     constexpr int NV = 2 * EG * NA;
-    constexpr size_t STAGE = single_stage_doubles<D, EG, SPLIT>();
+    constexpr size_t STAGE = single_stage_doubles<D, EG>();
     constexpr unsigned STAGE_BYTES = (unsigned)(STAGE * sizeof(double));
     extern __shared__ __align__(128) double smem[];      // [slot][ Wt[EG][32*32] | x_j[32*D] ]
     __shared__ double tab[16];
@@ -112,7 +105,7 @@ mm_step_single(const SingleStepArgs a)
     __shared__ double ziw[SINGLE_WARPS][SINGLE_ROWS * D];   // z_i of the 8 rows each warp handles
     __shared__ double red[SINGLE_WARPS][EG * NA];
     __shared__ double fin[NV];
-    __shared__ __align__(8) unsigned long long full[NSTAGE], empty[NSTAGE];
+    __shared__ __align__(8) unsigned long long full[SINGLE_STAGES], empty[SINGLE_STAGES];
     __shared__ int s_last;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     // grid (B, P): the rollout index is the FAST block index, so the CTAs that are resident together work on the
@@ -127,7 +120,7 @@ mm_step_single(const SingleStepArgs a)
     if (tid < 16) tab[tid] = kExp2Tab[tid];
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], SINGLE_WARPS); }
+        for (int s = 0; s < SINGLE_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], SINGLE_WARPS); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -150,28 +143,24 @@ mm_step_single(const SingleStepArgs a)
         while (rem >= a.ntile - row) { rem -= a.ntile - row; ++row; }
         I = row; J = row + rem;
     }
-    // stages are row slabs of SR rows: slab number s = SPLIT * tile + slab-in-tile, counted from s_begin
-    const int s_begin = t_begin * SPLIT, s_end = t_end * SPLIT;
-    int Ii = I, Ji = J, issued = s_begin;                // next slab to issue (thread 0 only); Ii is not needed for Wt
+    int Ii = I, Ji = J, issued = t_begin;                // next tile to issue (thread 0 only); Ii is not needed for Wt
     (void)Ii;
-    auto issue_next = [&]() {                            // thread 0: slab `issued` -> slot (issued - s_begin) % NSTAGE
-        const int slot = (issued - s_begin) % NSTAGE;
+    auto issue_next = [&]() {                            // thread 0: tile `issued` -> slot (issued - t_begin) % STAGES
+        const int slot = (issued - t_begin) % SINGLE_STAGES;
         double *base = smem + (size_t)slot * STAGE;
         void *bar = &full[slot];
         mbar_expect_tx(bar, STAGE_BYTES);
-        // tile-major Wt: tile t is one contiguous 8 KB block, its slab h the contiguous rows [h SR, (h+1) SR)
-        const size_t src = (size_t)(issued / SPLIT) * PT * PT + (size_t)(issued % SPLIT) * SR * PT;
 #pragma unroll
-        for (int g = 0; g < EG; ++g)
-            bulk_load_1d(base + (size_t)g * SR * PT, a.Wt[g] + src, SR * PT * sizeof(double), bar);
-        bulk_load_1d(base + (size_t)EG * SR * PT, a.X + (size_t)Ji * PT * D, PT * D * sizeof(double), bar);
-        ++issued;
-        if (issued % SPLIT == 0) { ++Ji; if (Ji == a.ntile) { ++Ii; Ji = Ii; } }
+        for (int g = 0; g < EG; ++g)             // tile-major Wt: tile number `issued` is one contiguous 8 KB block
+            bulk_load_1d(base + (size_t)g * PT * PT, a.Wt[g] + (size_t)issued * PT * PT, PT * PT * sizeof(double), bar);
+        bulk_load_1d(base + (size_t)EG * PT * PT, a.X + (size_t)Ji * PT * D, PT * D * sizeof(double), bar);
+        ++issued; ++Ji;
+        if (Ji == a.ntile) { ++Ii; Ji = Ii; }
     };
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < NSTAGE - 1; ++s)
-            if (issued < s_end) issue_next();
+        for (int s = 0; s < SINGLE_STAGES - 1; ++s)
+            if (issued < t_end) issue_next();
     }
 
     // this thread's first training point of the mean sums (X and beta are constants of the fit: their global-load
@@ -201,7 +190,7 @@ mm_step_single(const SingleStepArgs a)
     // tiles land.  Scratch = the last ring slot (the prologue fills slots 0 .. STAGES-2 only).
     // p_k = cm_k (u_k - x_jk),  l_j = exp(-sum p_k^2),  M0 += beta_j l_j, M1_k += beta_j l_j p_k, M2_k += .. p_k^2
     {
-        double *scratch = smem + (size_t)(NSTAGE - 1) * STAGE;    // [thread][EG*NA]
+        double *scratch = smem + (size_t)(SINGLE_STAGES - 1) * STAGE;    // [thread][EG*NA]
         if (tid < rows) {
             double m0[EG], m1[EG][D], m2[EG][D];
 #pragma unroll
@@ -254,13 +243,12 @@ mm_step_single(const SingleStepArgs a)
 
     GP_STAMP(2);                                         // mean sums done, tile loop starts
     int curI = -1;
-    for (int sl = s_begin; sl < s_end; ++sl) {
-        const int it = sl - s_begin;
-        const int slot = it % NSTAGE;
-        const int half = SPLIT == 1 ? 0 : sl % SPLIT;    // slab inside the tile
-        // refill: slab sl + NSTAGE - 1 goes into the slot slab sl-1 used, once all four warps have released it
-        if (tid == 0 && issued < s_end) {
-            if (it > 0) mbar_wait(&empty[(it - 1) % NSTAGE], ((it - 1) / NSTAGE) & 1);
+    for (int t = t_begin; t < t_end; ++t) {
+        const int it = t - t_begin;
+        const int slot = it % SINGLE_STAGES;
+        // refill: tile t + STAGES - 1 goes into the slot tile t-1 used, once all four warps have released it
+        if (tid == 0 && issued < t_end) {
+            if (it > 0) mbar_wait(&empty[(it - 1) % SINGLE_STAGES], ((it - 1) / SINGLE_STAGES) & 1);
             issue_next();
         }
         if (I != curI) {                                 // new row block: this warp's z_i = c*u - c*x_i (rare)
@@ -272,20 +260,19 @@ mm_step_single(const SingleStepArgs a)
             __syncwarp();
             curI = I;
         }
-        mbar_wait(&full[slot], (it / NSTAGE) & 1);
+        mbar_wait(&full[slot], (it / SINGLE_STAGES) & 1);
 
         const double *Ws = smem + (size_t)slot * STAGE;
-        const double *xjs = Ws + (size_t)EG * SR * PT;
+        const double *xjs = Ws + (size_t)EG * PT * PT;
         double zj[D];
 #pragma unroll
         for (int k = 0; k < D; ++k) zj[k] = fma(-cs[k], xjs[lane * D + k], cs[D + k]);
 #pragma unroll
-        for (int m = 0; m < SROWS; ++m) {
-            const int r = wid + m * SINGLE_WARPS;        // row inside the slab; tile row = half * SR + r
-            const double *zi = &ziw[wid][(half * SROWS + m) * D];
+        for (int m = 0; m < SINGLE_ROWS; ++m) {
+            const int r = wid + m * SINGLE_WARPS;
             double q[D], qq[D];
 #pragma unroll
-            for (int k = 0; k < D; ++k) { q[k] = zi[k] + zj[k]; qq[k] = q[k] * q[k]; }
+            for (int k = 0; k < D; ++k) { q[k] = ziw[wid][m * D + k] + zj[k]; qq[k] = q[k] * q[k]; }
             double S = qq[0];
             if (D >= 4) {                                // pairwise tree: shorter dependency chain
                 double S2 = qq[2] + qq[3];
@@ -300,7 +287,7 @@ mm_step_single(const SingleStepArgs a)
             const double e = exp_neg(S, tab);
 #pragma unroll
             for (int g = 0; g < EG; ++g) {
-                const double w = Ws[(size_t)g * SR * PT + r * PT + lane] * e;
+                const double w = Ws[(size_t)g * PT * PT + r * PT + lane] * e;
                 accT[g] += w;
                 if (GRAD) {
 #pragma unroll
@@ -312,7 +299,8 @@ mm_step_single(const SingleStepArgs a)
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[slot]);        // this warp is done with the slot
-        if (half == SPLIT - 1) { ++J; if (J == a.ntile) { ++I; J = I; } }
+        ++J;
+        if (J == a.ntile) { ++I; J = I; }
     }
 
     GP_STAMP(3);                                         // tile loop done

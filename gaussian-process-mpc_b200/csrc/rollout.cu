@@ -621,7 +621,6 @@ static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int ctas, int P, lon
             sa.Uint = next.Uint; sa.lam_group = next.lam_group; sa.us_w = us; sa.cst_w = cst; sa.act_var = next.act_var;
             sa.dbg = nullptr;
             sa.l2_base = nullptr; sa.l2_bytes = 0; sa.l2_hit = 0.f;
-            sa.split = h->opt_single_split;
             if (h->opt_l2_persist) {
                 if (h->l2_persist_max < 0) {                 // first use: device limits, carve out the persisting part of L2
                     int pm = 0, wm = 0;

@@ -59,8 +59,6 @@ int gpmpc_synchronize(gpmpc_handle h);
  *                            in one persistent cooperative launch; 0 = one fused launch per horizon step (measured faster
  *                            on one GPU).  A rollout split over several GPUs (gpmpc_split_*) always uses the persistent kernel.
  *   "split_timeline" (0):    stamp the inter-GPU exchange of every step (see gpmpc_split_last_exchange_us).
- *   "single_split" (1):      ring granularity of the few-rollouts step kernel: 1 = whole 32x32 tiles (3 slots), 2 = 16-row
- *                            slabs (6 slots in the same shared memory).
  *   "l2_persist" (0):        1 = few-rollouts kernels launch with an L2 access-policy window over the weights so that the
  *                            part of Wt that fits the persisting L2 carve-out stays resident from one horizon step to the
  *                            next (measured: no effect on B200, the kernel is not bound by the stream alone).            */
