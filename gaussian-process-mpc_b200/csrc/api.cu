@@ -187,7 +187,7 @@ extern "C" int gpmpc_fit(gpmpc_handle h, int n, const double *X, const double *Y
     h->n = n;
     h->ld = round_up(n, kTile);
     h->fitted = false;
-    h->tape_B = h->tape_H = 0;
+    h->tape_B = h->tape_H = 0; h->fc_B = h->fc_H = 0;
     const int ld = h->ld;
     GP_CUDA(h, h->X.reserve((size_t)ld * D * sizeof(double)));
     GP_CUDA(h, h->Y.reserve((size_t)ld * E * sizeof(double)));
@@ -233,7 +233,7 @@ extern "C" int gpmpc_refit_output(gpmpc_handle h, int a, const double *y, const 
     if ((rc = upload_prop_hypers(h))) return rc;
     bool which[kMaxE];
     for (int i = 0; i < kMaxE; ++i) which[i] = i == a;
-    h->tape_B = h->tape_H = 0;
+    h->tape_B = h->tape_H = 0; h->fc_B = h->fc_H = 0;
     // a failed factorisation leaves Kinv / beta / Wt of this output half-written: the handle must not keep
     // reporting "fitted" (fit_all sets the flag again on success)
     h->fitted = false;
@@ -347,7 +347,7 @@ extern "C" int gpmpc_append_point(gpmpc_handle h, const double *x, const double 
         GP_LAUNCH_CHECK(h);
         if ((rc = derive_weights(h, a))) return rc;
     }
-    h->tape_B = h->tape_H = 0;
+    h->tape_B = h->tape_H = 0; h->fc_B = h->fc_H = 0;
     return GPMPC_OK;
 }
 
@@ -375,7 +375,7 @@ extern "C" int gpmpc_set_propagation_hypers(gpmpc_handle h, const double *lambda
     if (h->fitted)
         for (int a = 0; a < E; ++a)
             if (changed[a] && (rc = derive_weights(h, a))) return rc;
-    h->tape_B = h->tape_H = 0;
+    h->tape_B = h->tape_H = 0; h->fc_B = h->fc_H = 0;
     return GPMPC_OK;
 }
 

@@ -1,5 +1,5 @@
 """B=1 evaluation latency probe (development tool): python tools/b1_eval.py [reps] [n] [H]
-Times one objective+gradient evaluation of a single control sequence with the L2 access-policy window on and off."""
+Times one objective+gradient evaluation of a single control sequence (and of 2, 8, 32)."""
 import sys, os, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -17,20 +17,15 @@ for a in range(E):
 dyn.append_train_data(S, A, nxt)
 br = gp.BatchedRollouts(dyn, 2 * np.eye(E), 0.01 * np.eye(m))
 U = rng.uniform(-0.3, 0.3, (1, H, m))
-for opt in (1, 0, 1):
-    dyn._bundle.set_option("l2_persist", opt)
-    ts = []
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        c, g = br.cost_and_grad(np.zeros(E), U, -1.0, host_out=True)
-        ts.append(time.perf_counter() - t0)
-    print(f"n={n} H={H} l2_persist={opt}: cost {c[0]:.12g}  ms per eval: last {[round(1e3 * t, 3) for t in ts[-3:]]} "
-          f"median {1e3 * float(np.median(ts)):.3f}")
+ts = []
+for _ in range(reps):
+    t0 = time.perf_counter()
+    c, g = br.cost_and_grad(np.zeros(E), U, -1.0, host_out=True)
+    ts.append(time.perf_counter() - t0)
+print(f"n={n} H={H}: cost {c[0]:.12g}  ms per eval: last {[round(1e3 * t, 3) for t in ts[-3:]]} median {1e3 * float(np.median(ts)):.3f}")
 for B in (2, 8, 32):
     Ub = rng.uniform(-0.3, 0.3, (B, H, m))
-    for opt in (1, 0):
-        dyn._bundle.set_option("l2_persist", opt)
-        ts = []
-        for _ in range(max(3, reps // 4)):
-            t0 = time.perf_counter(); br.cost_and_grad(np.zeros(E), Ub, -1.0, host_out=True); ts.append(time.perf_counter() - t0)
-        print(f"  B={B} l2_persist={opt}: {1e3 * float(np.median(ts)):.3f} ms per evaluation of the batch")
+    ts = []
+    for _ in range(max(3, reps // 4)):
+        t0 = time.perf_counter(); br.cost_and_grad(np.zeros(E), Ub, -1.0, host_out=True); ts.append(time.perf_counter() - t0)
+    print(f"  B={B}: {1e3 * float(np.median(ts)):.3f} ms per evaluation of the batch")
