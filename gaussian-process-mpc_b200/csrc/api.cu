@@ -60,6 +60,10 @@ extern "C" int gpmpc_destroy(gpmpc_handle h)
                       &h->tickets, &h->dbg, &h->Wx, &h->fc_plan, &h->fc_mu, &h->fc_cov, &h->fc_cst, &h->fc_raw, &h->fc_part,
                       &h->fc_red, &h->fc_gbar, &h->fc_seed, &h->fc_carry, &h->fc_io})
         b->release();
+    for (gpmpc::LookAhead &l : h->la) {
+        if (l.side) cudaStreamDestroy(l.side);
+        for (cudaEvent_t e : l.ev) cudaEventDestroy(e);
+    }
     for (cudaStream_t st : h->aux_streams) cudaStreamDestroy(st);
     for (cudaEvent_t ev : h->aux_events) cudaEventDestroy(ev);
     gpmpc_split_disconnect(h);

@@ -46,6 +46,11 @@ struct DevBuf {                    // grow-only device buffer
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+struct LookAhead {                 // side stream + events of one factorisation slot (fit.cu: cholesky_inplace)
+    cudaStream_t side = nullptr;
+    std::vector<cudaEvent_t> ev;
+};
+
 struct LambdaGroup {               // outputs whose propagation length-scales are bit-identical
     int count = 0;
     int outputs[kMaxE];
@@ -111,6 +116,7 @@ struct gpmpc_ctx {
     std::vector<cudaStream_t> aux_streams;
     std::vector<cudaEvent_t> aux_events;
     cudaEvent_t ev_fork = nullptr;
+    std::vector<gpmpc::LookAhead> la;   // per concurrent factorisation: look-ahead side stream
 
     // timing of the last pair-kernel sequence
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -382,10 +382,25 @@ int upload_prop_hypers(gpmpc_ctx *h)
 // rank updates touch only the panel, the rest of the matrix gets ONE rank-NB2 update per outer step (4x fewer
 // passes over the trailing matrix, 16 k-steps per tensor-core tile instead of 4).
 constexpr int NB2 = 256;
-static int cholesky_inplace(gpmpc_ctx *h, double *L, double *ZT, int np, double *linv, int *info)
+// Look-ahead (round 2): the trailing update of outer step K is split into (1) the columns of the NEXT outer panel, which
+// stay on the factorisation's stream because the next diagonal chain needs them, and (2) the rest of the trailing matrix,
+// which runs on a side stream concurrently with that chain (the chain is ~4 x 55 us of tiny dependent kernels per outer
+// step; at n = 4096 it used to be followed by an idle-machine wait for a ~60 us GEMM, at n = 16384 the GEMMs dominate and
+// the chain hides behind them).  Orders: (2)_K after chain(K) [event]; (1)_K after (2)_{K-1} [event: both write the next
+// panel's columns]; (2) of consecutive steps in stream order.
+static int cholesky_inplace(gpmpc_ctx *h, double *L, double *ZT, int np, double *linv, int *info, LookAhead *la)
 {
     const int ld = h->ld;
-    for (int K0 = 0; K0 < np; K0 += NB2) {
+    cudaStream_t main_st = h->stream;
+    const int n_outer = (np + NB2 - 1) / NB2;
+    if (la) while ((int)la->ev.size() < 2 * n_outer) {
+        cudaEvent_t e;
+        GP_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        la->ev.push_back(e);
+    }
+    int step = 0;
+    bool side_pending = false;
+    for (int K0 = 0; K0 < np; K0 += NB2, ++step) {
         const int w = np - K0 < NB2 ? np - K0 : NB2;
         for (int k = K0; k < K0 + w; k += NB) {
             potrf_diag_kernel<<<1, 256, 0, h->stream>>>(L, ld, k, linv, ZT, ld, info);
@@ -407,10 +422,31 @@ static int cholesky_inplace(gpmpc_ctx *h, double *L, double *ZT, int np, double 
         if (rem2 > 0) {
             // trailing update with the whole outer panel: A[i,j] -= sum_p L[i,K0+p] L[j,K0+p], lower tiles only
             double *P = L + (size_t)(K0 + w) * ld + K0;
-            int rc = dgemm_nt(h, rem2, rem2, w, -1.0, P, ld, P, ld, 1.0, L + (size_t)(K0 + w) * ld + (K0 + w), ld, true, 0);
-            if (rc) return rc;
+            double *A22 = L + (size_t)(K0 + w) * ld + (K0 + w);
+            const int w2 = rem2 < NB2 ? rem2 : NB2;               // width of the next outer panel
+            if (!la || rem2 <= w2) {
+                if (la && side_pending) { GP_CUDA(h, cudaStreamWaitEvent(main_st, la->ev[2 * (step - 1) + 1], 0)); side_pending = false; }
+                int rc = dgemm_nt(h, rem2, rem2, w, -1.0, P, ld, P, ld, 1.0, A22, ld, true, 0);
+                if (rc) return rc;
+            } else {
+                GP_CUDA(h, cudaEventRecord(la->ev[2 * step], main_st));                 // chain(K) done: the panel is final
+                // (2): everything right of the next panel, on the side stream
+                GP_CUDA(h, cudaStreamWaitEvent(la->side, la->ev[2 * step], 0));
+                h->stream = la->side;
+                int rc = dgemm_nt(h, rem2 - w2, rem2 - w2, w, -1.0, P + (size_t)w2 * ld, ld, P + (size_t)w2 * ld, ld, 1.0,
+                                  A22 + (size_t)w2 * (ld + 1), ld, true, 0);
+                h->stream = main_st;
+                if (rc) return rc;
+                GP_CUDA(h, cudaEventRecord(la->ev[2 * step + 1], la->side));
+                // (1): the next panel's columns, after the previous step's (2) (same columns)
+                if (side_pending) GP_CUDA(h, cudaStreamWaitEvent(main_st, la->ev[2 * (step - 1) + 1], 0));
+                rc = dgemm_nt(h, rem2, w2, w, -1.0, P, ld, P, ld, 1.0, A22, ld, true, 0);
+                if (rc) return rc;
+                side_pending = true;
+            }
         }
     }
+    if (la && side_pending) GP_CUDA(h, cudaStreamWaitEvent(main_st, la->ev[2 * (step - 1) + 1], 0));
     return GPMPC_OK;
 }
 
@@ -518,7 +554,10 @@ int fit_all(gpmpc_ctx *h, const bool *which)
         dim3 blk(32, 8), grid((np + 31) / 32, (np + 7) / 8);
         gram_kernel<<<grid, blk, 0, st>>>(h->X.as<double>(), n, np, h->D, make_hyper(h, a, false), L, ld, 1);
         h->launches++;
-        if ((rc = cholesky_inplace(h, L, ZT, np, linv, info))) break;
+        if (h->la.size() <= s) h->la.resize(s + 1);
+        if (!h->la[s].side) GP_CUDA(h, cudaStreamCreateWithFlags(&h->la[s].side, cudaStreamNonBlocking));
+        static const bool no_lookahead = getenv("GPMPC_NO_LOOKAHEAD") != nullptr;
+        if ((rc = cholesky_inplace(h, L, ZT, np, linv, info, no_lookahead ? nullptr : &h->la[s]))) break;
         logdet_kernel<<<1, 1024, 0, st>>>(L, ld, n, linv + (size_t)NB * NB);
         h->launches++;
         if ((rc = invert_factor(h, L, ZT, Kinv, np))) break;        // Kinv doubles as workspace until the next line
