@@ -205,7 +205,6 @@ struct PairArgs {
     int *counters;                 // [rollout chunks] work-item tickets, zeroed before the launch
     int ld, ntile, B, Bpad, E, n_items, chunks;
     int total_tiles;
-    int cw;                        // host side only: rollouts per chunk, 128 (a warp <-> 32 rollouts) or 32 (all warps share them)
 #ifdef GPMPC_PAIR_TIMING
     unsigned long long *cta_times;   // [grid][3]: start, end (globaltimer ns), smid
 #endif
@@ -232,16 +231,10 @@ __host__ __device__ constexpr size_t pair_smem_bytes()
 //   GRAD = 2  first horizon step when d/dx0 is not requested: the state part of the input (x0, 1e-3 I) is a
 //             constant, so only N1_k of the action dimensions k >= NS is needed.
 // NS = D accumulates everything (the general moment-matching entry points).
-// CW = rollouts per chunk.  128: every warp owns 32 rollouts and sweeps all rows of a tile.  32: the four warps share the
-// same 32 rollouts and take every fourth row strip each (their sums are added in warp order when a work item ends), so that
-// batches that are not close to a multiple of 128 do not run with mostly idle lanes.
-template <int D, int EG, int GRAD, int NS, int CW = PAIR_THREADS>
+template <int D, int EG, int GRAD, int NS>
 __global__ void __launch_bounds__(PAIR_THREADS, GPMPC_MINBLOCKS)
 mm_pairs_batch(const PairArgs a)
 {
-    static_assert(CW == PAIR_THREADS || CW == 32, "chunk width");
-    constexpr int NWARP = PAIR_THREADS / 32;
-    constexpr int RSTEP = CW == 32 ? NWARP : 1;  // a warp takes every RSTEP-th row strip
     constexpr int K1 = GRAD == 2 ? NS : 0;       // N1_k for k in [K1, D)
     constexpr int K2 = GRAD == 1 ? NS : 0;       // N2_k for k in [0, K2)
     extern __shared__ __align__(128) double smem[];
@@ -250,10 +243,9 @@ mm_pairs_batch(const PairArgs a)
     // consecutive CTAs serve different rollout chunks, so that the early-launched (favoured) and late-launched
     // CTAs of the SMs are spread evenly over the chunks' ticket counters
     const int chunk_id = blockIdx.x % a.chunks;
-    const int wid = tid >> 5;
-    const int b = chunk_id * CW + (CW == 32 ? (tid & 31) : tid);
+    const int b = chunk_id * PAIR_THREADS + tid;
     const bool active = b < a.B;
-    const bool warp_active = CW == 32 || chunk_id * CW + (tid & ~31) < a.B;   // ragged last chunk: idle warps only keep the barriers
+    const bool warp_active = chunk_id * PAIR_THREADS + (tid & ~31) < a.B;   // ragged last chunk: idle warps only keep the barriers
     double *tab = smem + 2 * STAGE;
     if (tid < 16) tab[tid] = kExp2Tab[tid];      // visible after the first __syncthreads of the tile loop
 #ifdef GPMPC_PAIR_TIMING
@@ -313,12 +305,7 @@ mm_pairs_batch(const PairArgs a)
     __shared__ int s_item;
     for (;;) {
         __syncthreads();
-        if (tid == 0) {
-            // CW = 32: the stage buffers were last written through the generic proxy (reduction scratch); order those
-            // writes before the TMA (async proxy) writes of the next item
-            if (CW == 32) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-            s_item = atomicAdd(&a.counters[chunk_id], 1);
-        }
+        if (tid == 0) s_item = atomicAdd(&a.counters[chunk_id], 1);
         __syncthreads();
         const int item = s_item;
         if (item >= a.n_items) break;
@@ -365,7 +352,7 @@ mm_pairs_batch(const PairArgs a)
             // strip / micro-tile: 1 + 1/2 + D/2 adds and FMAs per pair and output (2 x 2 tile) instead of 1 + D.
             constexpr int CJ = GPMPC_CJ, RSR = GPMPC_RS_RI;
 #pragma unroll 1
-            for (int r0 = (CW == 32 ? wid * RSR : 0); r0 < PT; r0 += RSR * RSTEP) {
+            for (int r0 = 0; r0 < PT; r0 += RSR) {
                 double zi[RSR][D], rs[RSR][EG];
 #pragma unroll
                 for (int r = 0; r < RSR; ++r) {
@@ -432,7 +419,7 @@ mm_pairs_batch(const PairArgs a)
             // RI-row register micro-tile per column: RI independent q -> q^2 -> sum -> exp chains (15 deep each) and
             // RI x EG x (1 + moments) independent accumulation FMAs per basic block, interleaved by the compiler.
 #pragma unroll 1
-            for (int r0 = (CW == 32 ? wid * RI : 0); r0 < PT; r0 += RI * RSTEP) {
+            for (int r0 = 0; r0 < PT; r0 += RI) {
                 double zi[RI][D];
 #pragma unroll
                 for (int r = 0; r < RI; ++r)
@@ -480,31 +467,7 @@ mm_pairs_batch(const PairArgs a)
             stage ^= 1; I = In; J = Jn;
         }
 
-        if (CW == 32) {
-            // warps (row strips) are summed in index order through the (now idle) stage buffers
-            constexpr int NA = 1 + 2 * D, NVW = EG * NA;
-            static_assert((size_t)NWARP * NVW * 32 <= 2 * STAGE, "reduction scratch must fit in the tile stages");
-            double *scr = smem;                          // [NWARP][NVW][32]
-            const int lane = tid & 31;
-#pragma unroll
-            for (int g = 0; g < EG; ++g) {
-                scr[((size_t)wid * NVW + g * NA) * 32 + lane] = accT[g];
-#pragma unroll
-                for (int k = 0; k < D; ++k) {
-                    scr[((size_t)wid * NVW + g * NA + 1 + k) * 32 + lane] = (GRAD && k >= K1) ? acc1[g][k] : 0.0;
-                    scr[((size_t)wid * NVW + g * NA + 1 + D + k) * 32 + lane] = (GRAD && k < K2) ? acc2[g][k] : 0.0;
-                }
-            }
-            __syncthreads();
-            if (active)
-                for (int v = wid; v < NVW; v += NWARP) {
-                    double sacc = 0.0;
-#pragma unroll
-                    for (int w = 0; w < NWARP; ++w) sacc += scr[((size_t)w * NVW + v) * 32 + lane];
-                    const int g = v / NA, e = v - g * NA;
-                    a.part[(((size_t)item * a.E + a.out_idx[g]) * NA + e) * a.Bpad + b] = sacc;
-                }
-        } else if (active) {
+        if (active) {
             constexpr int NA = 1 + 2 * D;
 #pragma unroll
             for (int g = 0; g < EG; ++g) {

@@ -11,8 +11,8 @@
 
 namespace gpmpc {
 
-template <int D, int EG, int GRAD, int NS, int CW>
-static cudaError_t launch_one_cw(const PairArgs &a, dim3 grid, cudaStream_t st)
+template <int D, int EG, int GRAD, int NS>
+static cudaError_t launch_one(const PairArgs &a, dim3 grid, cudaStream_t st)
 {
     const size_t smem = pair_smem_bytes<D, EG>();
     static bool configured[kMaxDevices] = {};
@@ -21,11 +21,11 @@ static cudaError_t launch_one_cw(const PairArgs &a, dim3 grid, cudaStream_t st)
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= kMaxDevices) dev = 0;
     if (first_use_on_device(configured)) {
-        cudaError_t e = cudaFuncSetAttribute(mm_pairs_batch<D, EG, GRAD, NS, CW>,
+        cudaError_t e = cudaFuncSetAttribute(mm_pairs_batch<D, EG, GRAD, NS>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int occ = 0, sms = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mm_pairs_batch<D, EG, GRAD, NS, CW>, PAIR_THREADS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mm_pairs_batch<D, EG, GRAD, NS>, PAIR_THREADS, smem);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         resident[dev] = occ * sms;
     }
@@ -36,14 +36,8 @@ static cudaError_t launch_one_cw(const PairArgs &a, dim3 grid, cudaStream_t st)
         const int per_chunk = resident[dev] / a.chunks;
         if (per_chunk * a.chunks > (int)grid.x) grid.x = per_chunk * a.chunks;
     }
-    mm_pairs_batch<D, EG, GRAD, NS, CW><<<grid, PAIR_THREADS, smem, st>>>(a);
+    mm_pairs_batch<D, EG, GRAD, NS><<<grid, PAIR_THREADS, smem, st>>>(a);
     return cudaGetLastError();
-}
-
-template <int D, int EG, int GRAD, int NS>
-static cudaError_t launch_one(const PairArgs &a, dim3 grid, cudaStream_t st)
-{
-    return a.cw == 32 ? launch_one_cw<D, EG, GRAD, NS, 32>(a, grid, st) : launch_one_cw<D, EG, GRAD, NS, PAIR_THREADS>(a, grid, st);
 }
 
 template <int D, int EG, int GRAD, int NS>

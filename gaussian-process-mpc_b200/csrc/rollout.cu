@@ -72,22 +72,6 @@ constexpr int kPersistMaxB = 1;
 // measured on B200 at n=4096 it costs 1.55 ms per rollout and evaluation, the batched kernel 145 ms per started
 // chunk of 128 rollouts (174 ms in round 1, crossover 112), i.e. the crossover is at 94
 constexpr int kSingleMaxB = 96;
-
-// The batched kernel comes in two chunk widths (mm_pairs.cuh): 128 rollouts per chunk (a warp owns 32 of them) and 32 (the
-// four warps share them).  Measured per started chunk at n = 4096: 145 ms / 128 lanes, i.e. ~36 ms per 32 lanes for either
-// width, against 1.55 ms per rollout for the few-rollouts kernel.  Path of a batch of B rollouts:
-//   32-wide chunks when they waste fewer lanes than 128-wide ones and beat the few-rollouts kernel (36 ms ceil(B/32) < 1.55 ms B),
-//   else the few-rollouts kernel below kSingleMaxB, else 128-wide chunks.
-static inline int ceil_to(int x, int m) { return (x + m - 1) / m * m; }
-static int chunk_width(int B)
-{
-    const int c32 = ceil_to(B, 32), c128 = ceil_to(B, PAIR_THREADS);
-    static const bool no32 = getenv("GPMPC_NO_CHUNK32") != nullptr;
-    if (no32) return PAIR_THREADS;
-    if (c32 < c128 && 36.0 * (c32 / 32) < 1.55 * B) return 32;
-    return PAIR_THREADS;
-}
-static bool use_few(int B) { return B < kSingleMaxB && chunk_width(B) == PAIR_THREADS; }
 constexpr int MEAN_JP = 64;          // partitions of the training set in the mean kernel (64 x rollout chunks CTAs)
 constexpr int MEAN_THREADS = 128;
 
@@ -565,15 +549,14 @@ static void pair_geometry(gpmpc_ctx *h, int B, long long total_tiles, int &ctas_
 {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-    if (use_few(B)) {                            // mm_step_single: SINGLE_CTAS_PER_SM CTAs per SM and rollout, static tile ranges
+    if (B < kSingleMaxB) {                       // mm_step_single: SINGLE_CTAS_PER_SM CTAs per SM and rollout, static tile ranges
         long long c = (long long)SINGLE_CTAS_PER_SM * sms;
         if (c > total_tiles) c = total_tiles;
         ctas_per_chunk = (int)c;
         n_items = (int)c;
         return;
     }
-    const int cw = chunk_width(B);
-    const int chunks = (B + cw - 1) / cw;
+    const int chunks = (B + PAIR_THREADS - 1) / PAIR_THREADS;
     long long c = (2LL * sms) / chunks;          // floor: never spill into a second wave
     if (c < 1) c = 1;
     if (c > total_tiles) c = total_tiles;
@@ -614,7 +597,7 @@ static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int ctas, int P, lon
 {
     const bool want_grad = grad_mode != 0;
     const size_t mat = (size_t)h->ld * h->ld;
-    const bool few = use_few(d.B);
+    const bool few = d.B < kSingleMaxB;
     if (h->time_pairs) cudaEventRecord(h->ev0, h->stream);
     for (int g = 0; g < d.G; ++g) {
         const LambdaGroup &grp = h->groups[g];
@@ -709,9 +692,8 @@ static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int ctas, int P, lon
         pa.cst = cst + (size_t)g * 4 * d.D * d.Bpad;
         pa.part = h->part.as<double>();
         pa.ld = h->ld; pa.ntile = h->ld / PT; pa.B = d.B; pa.Bpad = d.Bpad; pa.E = d.E; pa.n_items = P;
-        pa.cw = chunk_width(d.B);
-        pa.total_tiles = (int)total_tiles; pa.chunks = (d.B + pa.cw - 1) / pa.cw;
-        const int chunks = pa.chunks;
+        pa.total_tiles = (int)total_tiles; pa.chunks = (d.B + PAIR_THREADS - 1) / PAIR_THREADS;
+        const int chunks = (d.B + PAIR_THREADS - 1) / PAIR_THREADS;
         pa.counters = h->tickets.as<int>();
         GP_CUDA(h, cudaMemsetAsync(pa.counters, 0, chunks * sizeof(int), h->stream));
         e = pair_launcher(d.D)(grp.count, grad_mode, d.E, pa, dim3(ctas * chunks), h->stream);
@@ -752,10 +734,10 @@ static int reserve_rollout(gpmpc_ctx *h, int B, int H, RolloutWork &w)
     const long long nt = h->ld / PT;
     w.total_tiles = nt * (nt + 1) / 2;
     pair_geometry(h, B, w.total_tiles, w.ctas, w.P);
-    const bool few = use_few(B);
+    const bool few = B < kSingleMaxB;
     const size_t n_groups = (size_t)(w.P + SINGLE_GROUP - 1) / SINGLE_GROUP;
     // few rollouts: [B][1 + groups] arrival counters, then [B] completed steps and one error flag of the persistent kernel
-    const size_t n_tickets = few ? (size_t)B * (1 + n_groups) + B + 1 : (size_t)((B + 31) / 32);
+    const size_t n_tickets = few ? (size_t)B * (1 + n_groups) + B + 1 : (size_t)((B + PAIR_THREADS - 1) / PAIR_THREADS);
     GP_CUDA(h, h->tickets.reserve(n_tickets * sizeof(int)));
     if (few) GP_CUDA(h, cudaMemsetAsync(h->tickets.as<int>(), 0, n_tickets * sizeof(int), h->stream));
     const size_t Bp = d.Bpad;
@@ -812,7 +794,7 @@ static int forward(gpmpc_ctx *h, int B, int H, const double *x0_dev, const doubl
     const double act_var = (double)1e-3f;          // fp32 eye in the action block, src/dynamics.py:162
     h->last_pair_ms = 0.0; h->last_pair_evals = 0;
     // few rollouts and one lambda group: the step kernel itself prepares the constants of the following step
-    const bool fused_prep = use_few(B) && d.G == 1;
+    const bool fused_prep = B < kSingleMaxB && d.G == 1;
     // a single rollout: the whole horizon in one persistent cooperative launch
     static const bool no_persist = getenv("GPMPC_NO_PERSISTENT") != nullptr || getenv("GPMPC_STEP_DEBUG") != nullptr;
     if (fused_prep && B <= kPersistMaxB && H >= 2 && !no_persist && (h->opt_persistent || h->split_world > 1)) {

@@ -307,10 +307,7 @@ def test_batched_rollouts_vs_c_oracle(gp):
     norm_close(grad_p, grad[perm], 1e-11)
     c1, g1 = br.cost_and_grad(x0[5:6], U[5:6], gamma[5:6], host_out=True)
     close(c1, cost[5:6], 1e-9)      # few rollouts run the lanes<->pairs kernel: different (fixed) summation order
-    c40, g40 = br.cost_and_grad(x0[:40], U[:40], gamma[:40], host_out=True)     # 40 rollouts: the lanes<->pairs kernel as well
-    close(c40, cost[:40], 1e-9)
-    norm_close(g40, grad[:40], 1e-8)
-    c70, g70 = br.cost_and_grad(x0[:70], U[:70], gamma[:70], host_out=True)     # 70 rollouts: three 32-wide chunks, the last ragged
+    c70, g70 = br.cost_and_grad(x0[:70], U[:70], gamma[:70], host_out=True)     # 70 rollouts: still the lanes<->pairs kernel
     close(c70, cost[:70], 1e-9)
     norm_close(g70, grad[:70], 1e-8)
 
@@ -832,33 +829,31 @@ def test_numpy_interface_moment_matching_twins(gp):
 
 
 def test_kernel_switch_boundary_and_long_horizon(gp):
-    """Path selection by batch size (csrc/rollout.cu: chunk_width / use_few): 46 rollouts run the few-rollouts kernel, 47 the
-    batched kernel with 32-wide chunks, 256 the batched kernel with 128-wide chunks: rollouts shared between the batches must
-    agree across the switches; a long horizon (H = 64, tape and adjoint buffers beyond the usual sizes) against the C oracle."""
+    """B = 95 runs the few-rollouts kernel, B = 96 the batched one: the shared rollouts must agree across the switch;
+    a long horizon (H = 64, tape and adjoint buffers beyond the usual sizes) against the C oracle."""
     from oracle import oracle as orc
     n, E, m, H = 200, 3, 1, 64
+    SW = 96                                        # kSingleMaxB in csrc/rollout.cu
     dyn, S, A, nxt, rng = _synth_dynamics(gp, n, E, m, seed=77)
     Q = 2 * np.eye(E); R = 0.01 * np.eye(m)
     br = gp.BatchedRollouts(dyn, Q, R)
-    x0 = rng.uniform(-0.5, 0.5, (256, E)); U = rng.uniform(-0.3, 0.3, (256, H, m))
+    x0 = rng.uniform(-0.5, 0.5, (SW, E)); U = rng.uniform(-0.3, 0.3, (SW, H, m))
     l0 = dyn._bundle.launch_count()
-    c_few, g_few = br.cost_and_grad(x0[:46], U[:46], -1.0, host_out=True)
+    c_few, g_few = br.cost_and_grad(x0[:SW - 1], U[:SW - 1], -1.0, host_out=True)
     l1 = dyn._bundle.launch_count()
-    c_32, g_32 = br.cost_and_grad(x0[:47], U[:47], -1.0, host_out=True)
+    c_bat, g_bat = br.cost_and_grad(x0, U, -1.0, host_out=True)
     l2 = dyn._bundle.launch_count()
-    c_128, g_128 = br.cost_and_grad(x0, U, -1.0, host_out=True)
-    assert (l2 - l1) > (l1 - l0) + H               # the batched paths launch pair + mean + finalize kernels per step
-    close(c_few, c_32[:46], 1e-9); norm_close(g_few, g_32[:46], 1e-8)
-    close(c_32, c_128[:47], 1e-9); norm_close(g_32, g_128[:47], 1e-8)
+    assert (l2 - l1) > (l1 - l0) + H               # the batched path launches pair + mean + finalize kernels per step
+    close(c_few, c_bat[:SW - 1], 1e-9)
+    norm_close(g_few, g_bat[:SW - 1], 1e-8)
     X = np.concatenate([S, A], 1)
     lam = np.full((E, E + m), 2.0)
     fits = [orc.fit(X, nxt[:, a], lam[a], 1.0, float(np.float32(0.1 ** 2)) ** 0.5) for a in range(E)]
-    for b in (0, 46, 255):
+    for b in (0, SW - 1):
         c, gr, _, _ = orc.c_rollout_cost_grad(X, [f["Ky_inv"] for f in fits], [f["beta"] for f in fits], lam, np.ones(E),
                                               x0[b], U[b], -1.0, Q, R)
-        close(c_128[b], c, RTOL)
-        norm_close(g_128[b], gr, RTOL)
-    close(c_32[46], c_128[46], 1e-9)
+        close(c_bat[b], c, RTOL)
+        norm_close(g_bat[b], gr, RTOL)
 
 
 # ------------------------------------------------------------------------------------------------

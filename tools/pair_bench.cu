@@ -7,9 +7,6 @@ using namespace gpmpc;
 #ifndef GPMPC_BENCH_GRAD
 #define GPMPC_BENCH_GRAD 1       // moment selection of mm_pairs.cuh: 0 forward, 1 all steps, 2 first step
 #endif
-#ifndef GPMPC_BENCH_CW
-#define GPMPC_BENCH_CW 128       // rollouts per chunk: 128 or 32 (mm_pairs.cuh)
-#endif
 #ifndef GPMPC_BENCH_NS
 #define GPMPC_BENCH_NS 4         // state dimensions (N2 only for k < NS); 5 = all moments (the round-1 kernel)
 #endif
@@ -66,7 +63,7 @@ int main(int argc, char **argv)
     for (int g = 0; g < EG; ++g) { cudaMalloc(&dW[g], hW.size() * 8); cudaMemcpy(dW[g], hW.data(), hW.size() * 8, cudaMemcpyHostToDevice); }
     cudaMalloc(&dc, hc.size() * 8); cudaMemcpy(dc, hc.data(), hc.size() * 8, cudaMemcpyHostToDevice);
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    const int chunks = (B + GPMPC_BENCH_CW - 1) / GPMPC_BENCH_CW;
+    const int chunks = (B + PAIR_THREADS - 1) / PAIR_THREADS;
     const long long nt = ld / PT, total = nt * (nt + 1) / 2;
 #ifndef GPMPC_CTAS_PER_SM
 #define GPMPC_CTAS_PER_SM 2
@@ -87,14 +84,14 @@ int main(int argc, char **argv)
     unsigned long long *dtimes; cudaMalloc(&dtimes, (size_t)ctas * chunks * 3 * 8); a.cta_times = dtimes;
 #endif
     const size_t smem = pair_smem_bytes<D, EG>();
-    cudaFuncSetAttribute(mm_pairs_batch<D, EG, GPMPC_BENCH_GRAD, GPMPC_BENCH_NS, GPMPC_BENCH_CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(mm_pairs_batch<D, EG, GPMPC_BENCH_GRAD, GPMPC_BENCH_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(ctas * chunks);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {
         cudaMemset(dcnt, 0, chunks * sizeof(int));
         cudaEventRecord(e0);
-        mm_pairs_batch<D, EG, GPMPC_BENCH_GRAD, GPMPC_BENCH_NS, GPMPC_BENCH_CW><<<grid, PAIR_THREADS, smem>>>(a);
+        mm_pairs_batch<D, EG, GPMPC_BENCH_GRAD, GPMPC_BENCH_NS><<<grid, PAIR_THREADS, smem>>>(a);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
     }
