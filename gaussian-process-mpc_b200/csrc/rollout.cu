@@ -300,11 +300,37 @@ struct CostArgs {
 // State cost of time t and its partials (src/mpc.py:179-185):
 //   c_t = 1/gamma log det(I + gamma Q Sigma_t) + e^T (Q^-1 + gamma Sigma_t)^-1 e,  e = mu_t - x_ref
 // d c_t / d mu = (G + G^T) e,  d c_t / d sigma_k^2 = (M^-1 Q)_kk - gamma (G^T e)_k (G e)_k
+// The two halves (the determinant term with M^-1 Q, the quadratic term with G) share nothing but Sigma_t: the
+// few-rollouts kernel runs them in different warps.
 template <int E>
-__device__ __forceinline__ double state_cost_terms_t(const CostArgs &a, int b, int t, double gamma, double *dmu, double *dvar)
+__device__ __forceinline__ double state_cost_det_t(const CostArgs &a, int b, int t, double gamma, double *mq)
 {
     const int Bp = a.d.Bpad;
-    double M[E * E], Minv[E * E], Gm[E * E], G[E * E], e[E], sg[E];
+    double M[E * E], Minv[E * E], sg[E];
+#pragma unroll
+    for (int k = 0; k < E; ++k) sg[k] = a.var[((size_t)t * E + k) * Bp + b];
+#pragma unroll
+    for (int r = 0; r < E; ++r)
+#pragma unroll
+        for (int k = 0; k < E; ++k) M[r * E + k] = (r == k ? 1.0 : 0.0) + gamma * a.Q[r * E + k] * sg[k];   // I + gamma Q Sigma
+    const double det = lu_det_inv_t<E>(M, a.want_grad ? Minv : nullptr);
+    if (a.want_grad) {
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+            double s = 0.0;
+#pragma unroll
+            for (int r = 0; r < E; ++r) s += Minv[k * E + r] * a.Q[r * E + k];
+            mq[k] = s;
+        }
+    }
+    return (1.0 / gamma) * log(det);                   // log of the determinant (NaN if det < 0), mpc.py:183
+}
+// Quadratic half: returns e^T G e; dmu = (G + G^T) e; gg_k = gamma (G^T e)_k (G e)_k.
+template <int E>
+__device__ __forceinline__ double state_cost_quad_t(const CostArgs &a, int b, int t, double gamma, double *dmu, double *gg)
+{
+    const int Bp = a.d.Bpad;
+    double Gm[E * E], G[E * E], e[E], sg[E];
 #pragma unroll
     for (int k = 0; k < E; ++k) {
         sg[k] = a.var[((size_t)t * E + k) * Bp + b];
@@ -313,47 +339,42 @@ __device__ __forceinline__ double state_cost_terms_t(const CostArgs &a, int b, i
 #pragma unroll
     for (int r = 0; r < E; ++r)
 #pragma unroll
-        for (int k = 0; k < E; ++k) {
-            M[r * E + k] = (r == k ? 1.0 : 0.0) + gamma * a.Q[r * E + k] * sg[k];     // I + gamma Q Sigma
-            Gm[r * E + k] = a.Qi[r * E + k] + (r == k ? gamma * sg[k] : 0.0);         // Q^-1 + gamma Sigma
-        }
-    const double det = lu_det_inv_t<E>(M, a.want_grad ? Minv : nullptr);
+        for (int k = 0; k < E; ++k) Gm[r * E + k] = a.Qi[r * E + k] + (r == k ? gamma * sg[k] : 0.0);      // Q^-1 + gamma Sigma
     lu_det_inv_t<E>(Gm, G);
-    double cost = (1.0 / gamma) * log(det);            // log of the determinant (NaN if det < 0), mpc.py:183
-    double Ge[E], Gte[E];
+    double quad = 0.0;
 #pragma unroll
     for (int r = 0; r < E; ++r) {
         double s1 = 0.0, s2 = 0.0;
 #pragma unroll
         for (int k = 0; k < E; ++k) { s1 += G[r * E + k] * e[k]; s2 += G[k * E + r] * e[k]; }
-        Ge[r] = s1; Gte[r] = s2;
+        quad += e[r] * s1;
+        if (a.want_grad) { dmu[r] = s1 + s2; gg[r] = gamma * s2 * s1; }
     }
-#pragma unroll
-    for (int k = 0; k < E; ++k) cost += e[k] * Ge[k];
-    if (a.want_grad) {
-#pragma unroll
-        for (int k = 0; k < E; ++k) {
-            double mq = 0.0;
-#pragma unroll
-            for (int r = 0; r < E; ++r) mq += Minv[k * E + r] * a.Q[r * E + k];
-            dmu[k] = Ge[k] + Gte[k];
-            dvar[k] = mq - gamma * Gte[k] * Ge[k];
-        }
-    }
-    return cost;
+    return quad;
 }
-__device__ __noinline__ double state_cost_terms(const CostArgs &a, int b, int t, double gamma, double *dmu, double *dvar)
-{
-    switch (a.d.E) {
-        case 1: return state_cost_terms_t<1>(a, b, t, gamma, dmu, dvar);
-        case 2: return state_cost_terms_t<2>(a, b, t, gamma, dmu, dvar);
-        case 3: return state_cost_terms_t<3>(a, b, t, gamma, dmu, dvar);
-        case 4: return state_cost_terms_t<4>(a, b, t, gamma, dmu, dvar);
-        case 5: return state_cost_terms_t<5>(a, b, t, gamma, dmu, dvar);
-        case 6: return state_cost_terms_t<6>(a, b, t, gamma, dmu, dvar);
-        case 7: return state_cost_terms_t<7>(a, b, t, gamma, dmu, dvar);
-        default: return state_cost_terms_t<8>(a, b, t, gamma, dmu, dvar);
+#define GPMPC_SWITCH_E(EXPR)                                                                                      \
+    switch (a.d.E) {                                                                                              \
+        case 1: { constexpr int EE = 1; return EXPR; } case 2: { constexpr int EE = 2; return EXPR; }             \
+        case 3: { constexpr int EE = 3; return EXPR; } case 4: { constexpr int EE = 4; return EXPR; }             \
+        case 5: { constexpr int EE = 5; return EXPR; } case 6: { constexpr int EE = 6; return EXPR; }             \
+        case 7: { constexpr int EE = 7; return EXPR; } default: { constexpr int EE = 8; return EXPR; }            \
     }
+__device__ __noinline__ double state_cost_det(const CostArgs &a, int b, int t, double gamma, double *mq)
+{
+    GPMPC_SWITCH_E(state_cost_det_t<EE>(a, b, t, gamma, mq))
+}
+__device__ __noinline__ double state_cost_quad(const CostArgs &a, int b, int t, double gamma, double *dmu, double *gg)
+{
+    GPMPC_SWITCH_E(state_cost_quad_t<EE>(a, b, t, gamma, dmu, gg))
+}
+#undef GPMPC_SWITCH_E
+__device__ __forceinline__ double state_cost_terms(const CostArgs &a, int b, int t, double gamma, double *dmu, double *dvar)
+{
+    double gg[kMaxE];
+    const double c = state_cost_det(a, b, t, gamma, dvar) + state_cost_quad(a, b, t, gamma, dmu, gg);
+    if (a.want_grad)
+        for (int k = 0; k < a.d.E; ++k) dvar[k] -= gg[k];
+    return c;
 }
 
 // Direct cost of action j (src/mpc.py:188-198): (u_j-u_ref)^T R (u_j-u_ref) + delta_j^T Rd delta_j, and the
@@ -432,77 +453,112 @@ __global__ void __launch_bounds__(128) cost_adjoint_kernel(const CostArgs a)
     if (a.gx0int) for (int k = 0; k < E; ++k) a.gx0int[(size_t)k * Bp + b] = mb[k];
 }
 
-// Few rollouts: one block per rollout.  Phase 1 evaluates the H+1 state-cost terms (and their partials) and the H
-// action terms in parallel over t; phase 2 is the sequential reverse sweep, with lane k of warp 0 owning input
-// dimension k (its 4E tape loads per step are independent, so the sweep costs ~one memory latency per step).
+// Few rollouts: one block of 128 threads per rollout.
+//   phase 1  the tape entries of this rollout go to shared memory as asynchronous 8-byte copies (all in flight at
+//            once); meanwhile the H+1 state-cost terms are evaluated in parallel over t, the determinant half and
+//            the quadratic half of a term in different warps, and the H action terms in the remaining warps;
+//   phase 2  warp 1 adds up the cost in the order of the one-thread kernel; warp 0 runs the sequential reverse
+//            sweep with lane (o mod 4, k) holding the partials of output o w.r.t. input dimension k in registers:
+//            per step two FMAs, a two-level shuffle reduction over o and one shuffle that hands the new adjoints
+//            back, with the partials of the next step already loaded -- ~100 cycles per horizon step.
+// Measured (n=4096, H=30, B=1, ncu): 57 us for the previous version (tape loads one latency per 128 entries, all
+// cost terms in one warp, sweep through shared memory with run-time loop bounds), see profiles/r02_summary.md.
+__device__ __forceinline__ void cp_async8(double *dst_smem, const double *src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+}
 __global__ void __launch_bounds__(128) cost_adjoint_small_kernel(const CostArgs a)
 {
     extern __shared__ double sm[];
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int E = a.d.E, D = a.d.D, m = a.d.m, H = a.H, Bp = a.d.Bpad;
     const int NT = 2 + 4 * D;
     double *seed_mu = sm;                          // [(H+1) * E]
     double *seed_var = seed_mu + (size_t)(H + 1) * E;
-    double *gact = seed_var + (size_t)(H + 1) * E; // [H * m]
-    double *cpart = gact + (size_t)H * (m > 0 ? m : 1);   // [2H + 1]
-    double *carry = cpart + 2 * H + 1;             // [2E]: mb, vb
-    double *tps = carry + 2 * E;                   // [H * E * 4D]: the partial derivatives of this rollout's tape
+    double *ggs = seed_var + (size_t)(H + 1) * E;  // [(H+1) * E]: gamma (G^T e)(G e), subtracted from seed_var after the barrier
+    double *gact = ggs + (size_t)(H + 1) * E;      // [H * m]
+    double *cpart = gact + (size_t)H * (m > 0 ? m : 1);   // [3H + 2]: determinant halves, quadratic halves, action terms
+    double *tps = cpart + 3 * H + 2;               // [H * E * 4D]: the partial derivatives of this rollout's tape
     const double gamma = (a.mode == 0) ? a.gamma[b] : 0.0;
-    if (a.want_grad)                               // all loads in flight at once instead of one latency per step
+    if (a.want_grad)
         for (int i = tid; i < H * E * 4 * D; i += blockDim.x) {
             const int e = i % (4 * D), to = i / (4 * D);
-            tps[i] = a.tape[((size_t)to * NT + 2 + e) * Bp + b];
+            cp_async8(tps + i, a.tape + ((size_t)to * NT + 2 + e) * Bp + b);
         }
-    for (int t = tid; t <= H; t += blockDim.x) {
-        double dmu[kMaxE], dvar[kMaxE];
-        for (int k = 0; k < E; ++k) dmu[k] = dvar[k] = 0.0;
-        double c = 0.0;
-        if (a.mode == 0) c = state_cost_terms(a, b, t, gamma, dmu, dvar);
-        else
-            for (int k = 0; k < E; ++k) {
-                if (a.seed_mu) dmu[k] = a.seed_mu[((size_t)t * E + k) * Bp + b];
-                if (a.seed_var) dvar[k] = a.seed_var[((size_t)t * E + k) * Bp + b];
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (a.mode == 0) {
+        if (warp < 2) {                            // warp 0: determinant halves, warp 1: quadratic halves, lane <-> t
+            for (int t = lane; t <= H; t += 32) {
+                double o1[kMaxE], o2[kMaxE];
+                if (warp == 0) {
+                    cpart[t] = state_cost_det(a, b, t, gamma, o1);
+                    if (a.want_grad) for (int k = 0; k < E; ++k) seed_var[t * E + k] = o1[k];
+                } else {
+                    cpart[H + 1 + t] = state_cost_quad(a, b, t, gamma, o1, o2);
+                    if (a.want_grad) for (int k = 0; k < E; ++k) { seed_mu[t * E + k] = o1[k]; ggs[t * E + k] = o2[k]; }
+                }
             }
-        cpart[t] = c;
-        for (int k = 0; k < E; ++k) { seed_mu[t * E + k] = dmu[k]; seed_var[t * E + k] = dvar[k]; }
+        } else {
+            for (int j = tid - 64; j < H; j += 64) {
+                double g[kMaxD];
+                cpart[2 * H + 2 + j] = action_cost_terms(a, b, j, g);
+                for (int k = 0; k < m; ++k) gact[j * m + k] = g[k];
+            }
+        }
+    } else {
+        for (int i = tid; i < (H + 1) * E; i += blockDim.x) {
+            seed_mu[i] = a.seed_mu ? a.seed_mu[(size_t)i * Bp + b] : 0.0;
+            seed_var[i] = a.seed_var ? a.seed_var[(size_t)i * Bp + b] : 0.0;
+            ggs[i] = 0.0;
+        }
+        for (int i = tid; i < H * m; i += blockDim.x) gact[i] = 0.0;
     }
-    for (int j = tid; j < H; j += blockDim.x) {
-        double g[kMaxD];
-        for (int k = 0; k < m; ++k) g[k] = 0.0;
-        double c = 0.0;
-        if (a.mode == 0) c = action_cost_terms(a, b, j, g);
-        cpart[H + 1 + j] = c;
-        for (int k = 0; k < m; ++k) gact[j * m + k] = g[k];
-    }
-    if (tid < 2 * E) carry[tid] = 0.0;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    if (tid >= 32) return;
-    if (tid == 0 && a.mode == 0) {
+    if (warp == 1 && lane == 0 && a.mode == 0) {
         // same order as the one-thread kernel: t = H..0, each state term followed by the action term of t-1
         double c = 0.0;
-        for (int t = H; t >= 0; --t) { c += cpart[t]; if (t > 0) c += cpart[H + t]; }
+        for (int t = H; t >= 0; --t) { c += cpart[t] + cpart[H + 1 + t]; if (t > 0) c += cpart[2 * H + 2 + t - 1]; }
         a.cost[b] = c;
     }
-    if (!a.want_grad) return;
-    const int k = tid;                             // lane k < D owns input dimension k
+    if (warp != 0 || !a.want_grad) return;
+    // ---- reverse sweep: lane = og * 8 + k, og = output mod 4, k = input dimension ----
+    const int og = lane >> 3, k = lane & 7;
+    const bool two = E > 4;                        // outputs og and og + 4
+    const bool act0 = k < D && og < E, act1 = k < D && og + 4 < E;
+    const unsigned full = 0xffffffffu;
+    double p0[4], p1[4], s0[2], s1[2];             // partials dm/du, dm/ds, dv/du, dv/ds and the two seeds of the current step
+    auto load = [&](int t, double *q0, double *q1, double *z0, double *z1) {
+        const double *tp0 = tps + ((size_t)(t - 1) * E + og) * 4 * D, *tp1 = tp0 + (size_t)4 * 4 * D;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { q0[i] = act0 ? tp0[i * D + k] : 0.0; q1[i] = act1 ? tp1[i * D + k] : 0.0; }
+        z0[0] = og < E ? seed_mu[t * E + og] : 0.0;       z0[1] = og < E ? seed_var[t * E + og] - ggs[t * E + og] : 0.0;
+        z1[0] = og + 4 < E ? seed_mu[t * E + og + 4] : 0.0; z1[1] = og + 4 < E ? seed_var[t * E + og + 4] - ggs[t * E + og + 4] : 0.0;
+    };
+    if (H >= 1) load(H, p0, p1, s0, s1);
+    double ub = 0.0, sb = 0.0;                     // adjoints of (u, s)_k entering step t (all lanes of a column hold the total)
     for (int t = H; t >= 1; --t) {
-        if (k < E) { carry[k] += seed_mu[t * E + k]; carry[E + k] += seed_var[t * E + k]; }
-        __syncwarp();
-        double ub = 0.0, sb = 0.0;
-        if (k < D) {
-            for (int o = 0; o < E; ++o) {
-                const double *tp = tps + ((size_t)(t - 1) * E + o) * 4 * D;    // dm/du, dm/ds, dv/du, dv/ds
-                const double mo = carry[o], vo = carry[E + o];
-                ub += mo * tp[k] + vo * tp[2 * D + k];
-                sb += mo * tp[D + k] + vo * tp[3 * D + k];
-            }
+        double n0[4] = {0, 0, 0, 0}, n1[4] = {0, 0, 0, 0}, z0[2] = {0, 0}, z1[2] = {0, 0};
+        if (t > 1) load(t - 1, n0, n1, z0, z1);
+        // adjoints of (mean_t, var_t) of my outputs: what the previous step handed back plus this step's seeds
+        double mo = __shfl_sync(full, ub, og) + s0[0], vo = __shfl_sync(full, sb, og) + s0[1];
+        if (!act0) mo = vo = 0.0;                  // idle lanes read an action column: keep its value out of 0 * x
+        double u = mo * p0[0] + vo * p0[2], v = mo * p0[1] + vo * p0[3];
+        if (two) {
+            mo = __shfl_sync(full, ub, og + 4) + s1[0]; vo = __shfl_sync(full, sb, og + 4) + s1[1];
+            if (!act1) mo = vo = 0.0;
+            u += mo * p1[0] + vo * p1[2]; v += mo * p1[1] + vo * p1[3];
         }
-        __syncwarp();
-        if (k < E) { carry[k] = ub; carry[E + k] = sb; }
-        else if (k < D) a.gradint[((size_t)(t - 1) * m + (k - E)) * Bp + b] = ub + gact[(t - 1) * m + (k - E)];
-        __syncwarp();
+        u += __shfl_xor_sync(full, u, 8);  v += __shfl_xor_sync(full, v, 8);
+        u += __shfl_xor_sync(full, u, 16); v += __shfl_xor_sync(full, v, 16);
+        ub = u; sb = v;
+        if (og == 0 && k >= E && k < D) a.gradint[((size_t)(t - 1) * m + (k - E)) * Bp + b] = ub + gact[(t - 1) * m + (k - E)];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { p0[i] = n0[i]; p1[i] = n1[i]; }
+        s0[0] = z0[0]; s0[1] = z0[1]; s1[0] = z1[0]; s1[1] = z1[1];
     }
-    if (a.gx0int && k < E) a.gx0int[(size_t)k * Bp + b] = carry[k] + seed_mu[k];
+    if (a.gx0int && og == 0 && k < E) a.gx0int[(size_t)k * Bp + b] = ub + seed_mu[k];
 }
 
 // =============================================================================================
@@ -511,7 +567,7 @@ __global__ void __launch_bounds__(128) cost_adjoint_small_kernel(const CostArgs 
 static void launch_cost_adjoint(gpmpc_ctx *h, const CostArgs &ca, int B, int H)
 {
     if (B < kSingleMaxB) {
-        const size_t smem = ((size_t)2 * (H + 1) * ca.d.E + (size_t)H * (ca.d.m > 0 ? ca.d.m : 1) + 2 * H + 1 + 2 * ca.d.E +
+        const size_t smem = ((size_t)3 * (H + 1) * ca.d.E + (size_t)H * (ca.d.m > 0 ? ca.d.m : 1) + 3 * H + 2 +
                              (size_t)H * ca.d.E * 4 * ca.d.D) * sizeof(double);
         if (smem <= 160 * 1024) {
             static bool configured[kMaxDevices] = {};

@@ -15,6 +15,7 @@ __device__ __forceinline__ double lu_det_inv_t(const double *Ain, double *inv)
 {
     double A[E][E];
     int piv[E];
+    double rinv[E];                                // reciprocals of the pivots (as in LAPACK's trtri), reused by the back substitution
     double det = 1.0;
 #pragma unroll
     for (int r = 0; r < E; ++r)
@@ -36,6 +37,7 @@ __device__ __forceinline__ double lu_det_inv_t(const double *Ain, double *inv)
         if (p != c) det = -det;
         det *= A[c][c];
         const double dinv = 1.0 / A[c][c];
+        rinv[c] = dinv;
 #pragma unroll
         for (int r = c + 1; r < E; ++r) {
             const double f = A[r][c] * dinv;
@@ -64,7 +66,7 @@ __device__ __forceinline__ double lu_det_inv_t(const double *Ain, double *inv)
             for (int r = E - 1; r >= 0; --r) {
 #pragma unroll
                 for (int k = r + 1; k < E; ++k) x[r] -= A[r][k] * x[k];
-                x[r] /= A[r][r];
+                x[r] *= rinv[r];
             }
 #pragma unroll
             for (int r = 0; r < E; ++r) inv[r * E + col] = x[r];
