@@ -66,6 +66,7 @@ extern "C" int gpmpc_destroy(gpmpc_handle h)
     }
     for (cudaStream_t st : h->aux_streams) cudaStreamDestroy(st);
     for (cudaEvent_t ev : h->aux_events) cudaEventDestroy(ev);
+    h->pin_in.release(); h->pin_out.release();
     gpmpc_split_disconnect(h);
     h->split_buf.release();
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);

@@ -46,6 +46,21 @@ struct DevBuf {                    // grow-only device buffer
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+struct HostBuf {                   // grow-only pinned host buffer
+    void *p = nullptr;
+    size_t bytes = 0;
+    cudaError_t reserve(size_t need) {
+        if (need <= bytes) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; bytes = 0;
+        cudaError_t e = cudaHostAlloc(&p, need, cudaHostAllocDefault);
+        if (e == cudaSuccess) bytes = need;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; bytes = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
 struct LookAhead {                 // side stream + events of one factorisation slot (fit.cu: cholesky_inplace)
     cudaStream_t side = nullptr;
     std::vector<cudaEvent_t> ev;
@@ -85,6 +100,7 @@ struct gpmpc_ctx {
 
     // rollout workspaces (grow-only)
     gpmpc::DevBuf mu, var, tape, cst, part, mpart, stage_in, stage_out, gbuf, tickets, dbg;
+    gpmpc::HostBuf pin_in, pin_out;   // small evaluations: all host inputs / outputs travel as ONE pinned copy each way
     int tape_B = 0, tape_H = 0;    // shape of the tape held from the last rollout
 
     // full-covariance rollout (fullcov.cu): cross-output weights (built lazily, rebuilt when Wt changes), the plan

@@ -84,6 +84,24 @@ constexpr int MEAN_THREADS = 128;
 //     a_k = 1/(lam_k/2 + s_k)  (uncertainty_prop.py:376),  b_k = 1/(s_k + lam_k)  (:331)
 // mu/var hold step t-1 as [(t-1)*E + a][Bpad]; actions come from Uint [(t-1)*m + k][Bpad].
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void prep_one(const StepDims &d, int b, int g, int k, double u, double s,
+                                         const double *__restrict__ lam_group, double *__restrict__ us, double *__restrict__ cst)
+{
+    if (g == 0) {
+        us[(size_t)k * d.Bpad + b] = u;
+        us[(size_t)(d.D + k) * d.Bpad + b] = s;
+    }
+    const double lam = lam_group[g * d.D + k];
+    const double a = 1.0 / (0.5 * lam + s);
+    const double bb = 1.0 / (s + lam);
+    const double c = sqrt(0.125 * a);
+    const double cm = sqrt(0.5 * bb);
+    double *cg = cst + (size_t)g * 4 * d.D * d.Bpad;
+    cg[(size_t)k * d.Bpad + b] = c;
+    cg[(size_t)(d.D + k) * d.Bpad + b] = c * u;
+    cg[(size_t)(2 * d.D + k) * d.Bpad + b] = cm;
+    cg[(size_t)(3 * d.D + k) * d.Bpad + b] = cm * u;
+}
 __global__ void prep_step_kernel(StepDims d, int t, const double *__restrict__ mu, const double *__restrict__ var,
                                  const double *__restrict__ Uint, const double *__restrict__ lam_group,
                                  double *__restrict__ us, double *__restrict__ cst, double act_var)
@@ -100,20 +118,31 @@ __global__ void prep_step_kernel(StepDims d, int t, const double *__restrict__ m
             u = Uint[((size_t)(t - 1) * d.m + (k - d.E)) * d.Bpad + b];
             s = act_var;
         }
-        if (g == 0) {
-            us[(size_t)k * d.Bpad + b] = u;
-            us[(size_t)(d.D + k) * d.Bpad + b] = s;
-        }
-        const double lam = lam_group[g * d.D + k];
-        const double a = 1.0 / (0.5 * lam + s);
-        const double bb = 1.0 / (s + lam);
-        const double c = sqrt(0.125 * a);
-        const double cm = sqrt(0.5 * bb);
-        double *cg = cst + (size_t)g * 4 * d.D * d.Bpad;
-        cg[(size_t)k * d.Bpad + b] = c;
-        cg[(size_t)(d.D + k) * d.Bpad + b] = c * u;
-        cg[(size_t)(2 * d.D + k) * d.Bpad + b] = cm;
-        cg[(size_t)(3 * d.D + k) * d.Bpad + b] = cm * u;
+        prep_one(d, b, g, k, u, s, lam_group, us, cst);
+    }
+}
+// Few rollouts: everything that precedes the first step in ONE launch -- both layout shuffles (x0 [B,E], U [B,H,m] ->
+// internal), the initial state (mean x0, variance var0) and the constants of step 1 for every lambda group.
+// Block (32 rollouts, 4 parts): part 0 does the state and the constants, all parts share the H*m actions.
+__global__ void begin_rollout_small_kernel(StepDims d, int H, const double *__restrict__ x0, const double *__restrict__ U,
+                                           double *__restrict__ x0int, double *__restrict__ Uint, double *__restrict__ mu,
+                                           double *__restrict__ var, double var0, const double *__restrict__ lam_group,
+                                           double *__restrict__ us, double *__restrict__ cst, double act_var)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= d.B) return;
+    const int hm = H * d.m;
+    for (int i = threadIdx.y; i < hm; i += blockDim.y) Uint[(size_t)i * d.Bpad + b] = U[(size_t)b * hm + i];
+    if (threadIdx.y != 0) return;
+    for (int k = 0; k < d.D; ++k) {
+        double u, s = act_var;
+        if (k < d.E) {
+            u = x0[(size_t)b * d.E + k]; s = var0;
+            x0int[(size_t)k * d.Bpad + b] = u; mu[(size_t)k * d.Bpad + b] = u; var[(size_t)k * d.Bpad + b] = var0;
+        } else if (H > 0) u = U[(size_t)b * hm + (k - d.E)];
+        else continue;
+        if (H > 0)
+            for (int g = 0; g < d.G; ++g) prep_one(d, b, g, k, u, s, lam_group, us, cst);
     }
 }
 
@@ -295,6 +324,7 @@ struct CostArgs {
     double *cost;                                // [B] (device, final layout)
     double *gradint;                             // [(t*m + k)][Bpad]
     double *gx0int;                              // [a][Bpad] or NULL
+    double *grad_ext;                            // few-rollouts kernel only: if set, the gradient goes here as [B, H, m] instead
 };
 
 // State cost of time t and its partials (src/mpc.py:179-185):
@@ -553,7 +583,11 @@ __global__ void __launch_bounds__(128) cost_adjoint_small_kernel(const CostArgs 
         u += __shfl_xor_sync(full, u, 8);  v += __shfl_xor_sync(full, v, 8);
         u += __shfl_xor_sync(full, u, 16); v += __shfl_xor_sync(full, v, 16);
         ub = u; sb = v;
-        if (og == 0 && k >= E && k < D) a.gradint[((size_t)(t - 1) * m + (k - E)) * Bp + b] = ub + gact[(t - 1) * m + (k - E)];
+        if (og == 0 && k >= E && k < D) {
+            const double gk = ub + gact[(t - 1) * m + (k - E)];
+            if (a.grad_ext) a.grad_ext[((size_t)b * H + (t - 1)) * m + (k - E)] = gk;
+            else a.gradint[((size_t)(t - 1) * m + (k - E)) * Bp + b] = gk;
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) { p0[i] = n0[i]; p1[i] = n1[i]; }
         s0[0] = z0[0]; s0[1] = z0[1]; s1[0] = z1[0]; s1[1] = z1[1];
@@ -564,7 +598,8 @@ __global__ void __launch_bounds__(128) cost_adjoint_small_kernel(const CostArgs 
 // =============================================================================================
 // Host orchestration
 // =============================================================================================
-static void launch_cost_adjoint(gpmpc_ctx *h, const CostArgs &ca, int B, int H)
+// returns true if the few-rollouts kernel ran (the one that honours CostArgs::grad_ext)
+static bool launch_cost_adjoint(gpmpc_ctx *h, const CostArgs &ca, int B, int H)
 {
     if (B < kSingleMaxB) {
         const size_t smem = ((size_t)3 * (H + 1) * ca.d.E + (size_t)H * (ca.d.m > 0 ? ca.d.m : 1) + 3 * H + 2 +
@@ -574,10 +609,11 @@ static void launch_cost_adjoint(gpmpc_ctx *h, const CostArgs &ca, int B, int H)
             if (first_use_on_device(configured))
                 cudaFuncSetAttribute(cost_adjoint_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
             cost_adjoint_small_kernel<<<B, 128, smem, h->stream>>>(ca);
-            return;
+            return true;
         }
     }
     cost_adjoint_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(ca);
+    return false;
 }
 
 static int check_ready(gpmpc_ctx *h, int B, int H)
@@ -838,25 +874,31 @@ static int forward(gpmpc_ctx *h, int B, int H, const double *x0_dev, const doubl
     if (rc) return rc;
     const StepDims &d = w.d;
     dim3 blk(128);
-    to_internal_kernel<<<dim3((B + 127) / 128, d.E), blk, 0, h->stream>>>(x0_dev, B, d.Bpad, d.E, w.x0int);
-    GP_LAUNCH_CHECK(h);
-    if (H > 0 && d.m > 0) {
-        to_internal_kernel<<<dim3((B + 127) / 128, H * d.m), blk, 0, h->stream>>>(U_dev, B, d.Bpad, H * d.m, w.Uint);
+    const double act_var = (double)1e-3f;          // fp32 eye in the action block, src/dynamics.py:162
+    const bool begun = B < kSingleMaxB;            // few rollouts: shuffles, initial state and the constants of step 1 in one launch
+    if (begun) {
+        begin_rollout_small_kernel<<<(B + 31) / 32, dim3(32, 4), 0, h->stream>>>(d, H, x0_dev, U_dev, w.x0int, w.Uint,
+                                                                                h->mu.as<double>(), h->var.as<double>(), 1e-3,
+                                                                                w.lamg, w.us, w.cst, act_var);
+        GP_LAUNCH_CHECK(h);
+    } else {
+        to_internal_kernel<<<dim3((B + 127) / 128, d.E), blk, 0, h->stream>>>(x0_dev, B, d.Bpad, d.E, w.x0int);
+        GP_LAUNCH_CHECK(h);
+        if (H > 0 && d.m > 0) {
+            to_internal_kernel<<<dim3((B + 127) / 128, H * d.m), blk, 0, h->stream>>>(U_dev, B, d.Bpad, H * d.m, w.Uint);
+            GP_LAUNCH_CHECK(h);
+        }
+        init_state_kernel<<<dim3((B + 127) / 128, d.E), blk, 0, h->stream>>>(w.x0int, B, d.Bpad, d.E, h->mu.as<double>(),
+                                                                               h->var.as<double>(), 1e-3);
         GP_LAUNCH_CHECK(h);
     }
-    init_state_kernel<<<dim3((B + 127) / 128, d.E), blk, 0, h->stream>>>(w.x0int, B, d.Bpad, d.E, h->mu.as<double>(),
-                                                                           h->var.as<double>(), 1e-3);
-    GP_LAUNCH_CHECK(h);
-    const double act_var = (double)1e-3f;          // fp32 eye in the action block, src/dynamics.py:162
     h->last_pair_ms = 0.0; h->last_pair_evals = 0;
     // few rollouts and one lambda group: the step kernel itself prepares the constants of the following step
     const bool fused_prep = B < kSingleMaxB && d.G == 1;
     // a single rollout: the whole horizon in one persistent cooperative launch
     static const bool no_persist = getenv("GPMPC_NO_PERSISTENT") != nullptr || getenv("GPMPC_STEP_DEBUG") != nullptr;
     if (fused_prep && B <= kPersistMaxB && H >= 2 && !no_persist && (h->opt_persistent || h->split_world > 1)) {
-        prep_step_kernel<<<dim3((B + 127) / 128, d.G), blk, 0, h->stream>>>(d, 1, h->mu.as<double>(), h->var.as<double>(),
-                                                                             w.Uint, w.lamg, w.us, w.cst, act_var);
-        GP_LAUNCH_CHECK(h);
+        // (the constants of step 1 are there: begin_rollout_small_kernel)
         const LambdaGroup &grp = h->groups[0];
         RolloutSingleArgs ra;
         for (int i = 0; i < kGroupMax; ++i) {
@@ -921,7 +963,7 @@ static int forward(gpmpc_ctx *h, int B, int H, const double *x0_dev, const doubl
         cudaGetLastError();                            // the grid does not fit: one launch per step instead
     }
     for (int t = 1; t <= H; ++t) {
-        if (!fused_prep || t == 1) {
+        if (!(begun && t == 1) && (!fused_prep || t == 1)) {
             prep_step_kernel<<<dim3((B + 127) / 128, d.G), blk, 0, h->stream>>>(d, t, h->mu.as<double>(), h->var.as<double>(),
                                                                                  w.Uint, w.lamg, w.us, w.cst, act_var);
             GP_LAUNCH_CHECK(h);
@@ -1051,16 +1093,36 @@ extern "C" int gpmpc_rollout_cost_grad(gpmpc_handle h, int B, int H, const doubl
     if (Rdelta && !last_u) return fail(h, GPMPC_ERR_INVALID, "gpmpc_rollout_cost_grad: Rdelta needs last_u");
     GP_CUDA(h, cudaSetDevice(h->device));
     const int E = h->E, m = h->m;
-    const size_t need = ((size_t)B * E + (size_t)B * H * m + (size_t)B + (size_t)B * m) * sizeof(double) + 2048;
+    const size_t n_x0 = (size_t)B * E, n_U = (H > 0 && m > 0) ? (size_t)B * H * m : 0, n_lu = Rdelta ? (size_t)B * m : 0;
+    const size_t need = (n_x0 + n_U + (size_t)B + n_lu) * sizeof(double) + 2048;
     GP_CUDA(h, h->stage_in.reserve(need));
-    size_t off = 0;
-    const double *x0d, *Ud = nullptr, *gd, *lud = nullptr;
-    if ((rc = stage_in(h, h->stage_in, off, x0, (size_t)B * E, &x0d))) return rc;
-    if (H > 0 && m > 0 && (rc = stage_in(h, h->stage_in, off, U, (size_t)B * H * m, &Ud))) return rc;
-    if ((rc = stage_in(h, h->stage_in, off, gamma, (size_t)B, &gd))) return rc;
-    if (Rdelta && (rc = stage_in(h, h->stage_in, off, last_u, (size_t)B * m, &lud))) return rc;
-
     const bool want_grad = grad != nullptr;
+    const bool cost_host = !is_device_ptr(cost);
+    const bool ghost = want_grad && !is_device_ptr(grad);
+    const double *x0d, *Ud = nullptr, *gd, *lud = nullptr;
+    // Few rollouts with host buffers (the solver-callback pattern): every input goes through ONE pinned copy, and
+    // cost + gradient come back as one (a pageable cudaMemcpyAsync costs ~5 us of driver time per call).  The pinned
+    // buffers are reused by the next call, so this path is taken only when this call ends with a synchronize.
+    const bool few = B < kSingleMaxB;
+    const bool packed_in = few && cost_host && !is_device_ptr(x0) && (!n_U || !is_device_ptr(U)) && !is_device_ptr(gamma) &&
+                           (!n_lu || !is_device_ptr(last_u));
+    if (packed_in) {
+        const size_t total = n_x0 + n_U + (size_t)B + n_lu;
+        GP_CUDA(h, h->pin_in.reserve(total * sizeof(double)));
+        double *hp = h->pin_in.as<double>(), *dp = h->stage_in.as<double>();
+        std::memcpy(hp, x0, n_x0 * sizeof(double));                                  x0d = dp;
+        if (n_U) std::memcpy(hp + n_x0, U, n_U * sizeof(double));                    Ud = n_U ? dp + n_x0 : nullptr;
+        std::memcpy(hp + n_x0 + n_U, gamma, (size_t)B * sizeof(double));             gd = dp + n_x0 + n_U;
+        if (n_lu) std::memcpy(hp + n_x0 + n_U + B, last_u, n_lu * sizeof(double));   lud = n_lu ? dp + n_x0 + n_U + B : nullptr;
+        GP_CUDA(h, cudaMemcpyAsync(dp, hp, total * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    } else {
+        size_t off = 0;
+        if ((rc = stage_in(h, h->stage_in, off, x0, n_x0, &x0d))) return rc;
+        if (n_U && (rc = stage_in(h, h->stage_in, off, U, n_U, &Ud))) return rc;
+        if ((rc = stage_in(h, h->stage_in, off, gamma, (size_t)B, &gd))) return rc;
+        if (n_lu && (rc = stage_in(h, h->stage_in, off, last_u, n_lu, &lud))) return rc;
+    }
+
     RolloutWork w;
     if ((rc = forward(h, B, H, x0d, Ud, want_grad, false, w))) return rc;
     const StepDims &d = w.d;
@@ -1071,7 +1133,7 @@ extern "C" int gpmpc_rollout_cost_grad(gpmpc_handle h, int B, int H, const doubl
     ca.d = d; ca.H = H; ca.mode = 0; ca.has_rd = Rdelta ? 1 : 0; ca.want_grad = want_grad ? 1 : 0;
     ca.mu = h->mu.as<double>(); ca.var = h->var.as<double>(); ca.tape = h->tape.as<double>(); ca.Uint = w.Uint;
     ca.gamma = gd;
-    // gbuf: last_u internal [m][Bp] | grad internal [H*m][Bp] | cost [B] | grad external [B*H*m]
+    // gbuf: last_u internal [m][Bp] | grad internal [H*m][Bp] | cost [Bp] | grad external [B*H*m]
     const size_t Bp = d.Bpad;
     const size_t gcount = (size_t)m * Bp + (size_t)H * m * Bp + Bp + (size_t)B * H * m + 64;
     GP_CUDA(h, h->gbuf.reserve(gcount * sizeof(double)));
@@ -1085,22 +1147,33 @@ extern "C" int gpmpc_rollout_cost_grad(gpmpc_handle h, int B, int H, const doubl
         GP_LAUNCH_CHECK(h);
     }
     ca.last_u = lu_int;
-    const bool cost_host = !is_device_ptr(cost);
     ca.cost = cost_host ? cost_dev : cost;
     ca.gradint = grad_int;
     ca.gx0int = nullptr;
-    launch_cost_adjoint(h, ca, B, H);
+    const bool has_grad = want_grad && H > 0 && m > 0;
+    double *gdev = ghost ? grad_ext : grad;
+    ca.grad_ext = has_grad ? gdev : nullptr;
+    const bool direct = launch_cost_adjoint(h, ca, B, H);
     GP_LAUNCH_CHECK(h);
-    if (want_grad && H > 0 && m > 0) {
-        const bool ghost = !is_device_ptr(grad);
-        double *gdev = ghost ? grad_ext : grad;
+    if (has_grad && !direct) {
         to_external_kernel<<<dim3((B + 127) / 128, H * m), 128, 0, h->stream>>>(grad_int, B, d.Bpad, H * m, gdev);
         GP_LAUNCH_CHECK(h);
-        if (ghost) GP_CUDA(h, cudaMemcpyAsync(grad, gdev, (size_t)B * H * m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     }
-    if (cost_host) GP_CUDA(h, cudaMemcpyAsync(cost, cost_dev, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    const size_t n_grad = has_grad ? (size_t)B * H * m : 0;
+    const bool packed_out = few && cost_host && (!has_grad || ghost);
+    if (packed_out) {                              // cost [Bp] and the external gradient are adjacent in gbuf
+        GP_CUDA(h, h->pin_out.reserve((Bp + n_grad) * sizeof(double)));
+        GP_CUDA(h, cudaMemcpyAsync(h->pin_out.p, cost_dev, (Bp + n_grad) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        if (has_grad && ghost) GP_CUDA(h, cudaMemcpyAsync(grad, gdev, n_grad * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (cost_host) GP_CUDA(h, cudaMemcpyAsync(cost, cost_dev, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
     if (means || vars) { if ((rc = export_traj(h, d, H, means, vars))) return rc; }
-    if (cost_host || (want_grad && !is_device_ptr(grad))) GP_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (cost_host || ghost) GP_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (packed_out) {
+        std::memcpy(cost, h->pin_out.as<double>(), (size_t)B * sizeof(double));
+        if (n_grad) std::memcpy(grad, h->pin_out.as<double>() + Bp, n_grad * sizeof(double));
+    }
     return GPMPC_OK;
 }
 
