@@ -66,7 +66,7 @@ extern "C" int gpmpc_destroy(gpmpc_handle h)
     }
     for (cudaStream_t st : h->aux_streams) cudaStreamDestroy(st);
     for (cudaEvent_t ev : h->aux_events) cudaEventDestroy(ev);
-    h->pin_in.release(); h->pin_out.release();
+    h->pin_in.release(); h->pin_out.release(); h->claim.release();
     gpmpc_split_disconnect(h);
     h->split_buf.release();
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -95,6 +95,10 @@ extern "C" int gpmpc_set_option(gpmpc_handle h, const char *name, int value)
 {
     if (!h || !name) return GPMPC_ERR_INVALID;
     if (std::strcmp(name, "persistent_single") == 0) { h->opt_persistent = value != 0; return GPMPC_OK; }
+    if (std::strcmp(name, "single_big_share") == 0) {       // per mille, 500..900
+        if (value < 500 || value > 900) return fail(h, GPMPC_ERR_INVALID, "single_big_share: 500..900 per mille");
+        h->opt_single_big = value; return GPMPC_OK;
+    }
     if (std::strcmp(name, "split_timeline") == 0) { h->opt_split_timeline = value != 0; return GPMPC_OK; }
     if (std::strcmp(name, "l2_persist") == 0) {
         h->opt_l2_persist = value != 0;

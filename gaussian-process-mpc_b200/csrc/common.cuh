@@ -100,6 +100,11 @@ struct gpmpc_ctx {
 
     // rollout workspaces (grow-only)
     gpmpc::DevBuf mu, var, tape, cst, part, mpart, stage_in, stage_out, gbuf, tickets, dbg;
+    gpmpc::DevBuf claim;              // mm_step_single: per-step slice-claim counters [H][kClaimStride] ints
+    // per mille of the tiles that go to the first-arrived CTA of each SM (500 = equal static slices).  Measured on B200
+    // (B = 1 objective+gradient, us): n=4096, H=30: 500 -> 2050, 570 -> 1995, 630 -> 1980, 660 -> 1953..1974, 700 -> 2021,
+    // 740 -> 2088; n=16384, H=20: 500 -> 18919, 600 -> 18466, 660 -> 17653, 700 -> 17961, 740 -> 18519
+    int opt_single_big = 660;
     gpmpc::HostBuf pin_in, pin_out;   // small evaluations: all host inputs / outputs travel as ONE pinned copy each way
     int tape_B = 0, tape_H = 0;    // shape of the tape held from the last rollout
 
@@ -181,6 +186,7 @@ inline cudaError_t to_device(gpmpc_ctx *h, void *dst, const void *src, size_t by
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // cudaFuncSetAttribute is per device: `done` is a per-call-site table indexed by the current device
+constexpr int kClaimStride = 260;   // 256 per-SM arrival counters + big / small slice counters
 constexpr int kMaxDevices = 64;
 inline bool first_use_on_device(bool (&done)[kMaxDevices]) {
     int dev = 0;

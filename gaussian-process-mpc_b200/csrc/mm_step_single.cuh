@@ -64,6 +64,14 @@ struct SingleStepArgs {
     double *us_w, *cst_w;
     double act_var;
     unsigned long long *dbg;       // optional [B*P][6] globaltimer stamps (GPMPC_STEP_DEBUG=1), else NULL
+    // Unequal shares for the two CTAs of an SM (B = 1, grid = 2 x SMs only; else NULL).  The warp scheduler favours the
+    // CTA that arrived first: with equal tile ranges it finishes after 46 us, its neighbour after 60 us
+    // (profiles/r01c_step_single_cta_timeline.csv).  Every CTA therefore CLAIMS its slice: the first arrival on an SM
+    // takes one of the P/2 big slices (tiles_big tiles in total), the second a small one.  claim = this step's counters:
+    // [smid % 256] arrivals per SM, [256] big slices handed out, [257] small ones (zeroed once per rollout).  A pool that
+    // runs dry (an SM that got one or three CTAs) overflows into the other, so the slices are always a bijection; the
+    // partial sums are stored per slice and summed in slice order, i.e. the result does not depend on who took what.
+    int *claim; int tiles_big;
     // host side only (launch attribute, not read by the kernel): L2 access-policy window over the weights.  Every step
     // streams the same Wt; a plain LRU keeps none of a working set larger than L2 across steps, a persisting fraction
     // that fits stays resident
@@ -76,7 +84,7 @@ __device__ __forceinline__ unsigned long long gtime()
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-#define GP_STAMP(i) do { if (a.dbg && tid == 0) a.dbg[((size_t)b * P + bx) * 6 + (i)] = gtime(); } while (0)
+#define GP_STAMP(i) do { if (a.dbg && tid == 0) a.dbg[((size_t)b * P + cta) * 6 + (i)] = gtime(); } while (0)
 
 template <int D, int EG>
 __host__ __device__ constexpr size_t single_stage_doubles() { return (size_t)EG * PT * PT + PT * D; }
@@ -106,13 +114,13 @@ mm_step_single(const SingleStepArgs a)
     __shared__ double red[SINGLE_WARPS][EG * NA];
     __shared__ double fin[NV];
     __shared__ __align__(8) unsigned long long full[SINGLE_STAGES], empty[SINGLE_STAGES];
-    __shared__ int s_last;
+    __shared__ int s_last, s_slice;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     // grid (B, P): the rollout index is the FAST block index, so the CTAs that are resident together work on the
     // same tile ranges for different rollouts and share the Wt tiles through L2 (2 <= B < 64)
     const int b = blockIdx.x;                            // rollout
     const int P = gridDim.y;
-    const int bx = blockIdx.y;                           // this CTA's slice of the tile list / training set
+    const int cta = blockIdx.y;
     // Programmatic dependent launch: the next step's grid may be scheduled while this one drains; everything up
     // to griddepcontrol.wait touches only data no step kernel writes (the exp table, Wt, X).
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
@@ -122,8 +130,23 @@ mm_step_single(const SingleStepArgs a)
 #pragma unroll
         for (int s = 0; s < SINGLE_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], SINGLE_WARPS); }
         mbar_fence_init();
+        int slice = cta;
+        if (a.claim) {                                   // (counters of THIS step: nothing the preceding grid writes)
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            const int half = P >> 1;
+            if (atomicAdd(&a.claim[smid & 255], 1) == 0) {
+                const int k = atomicAdd(&a.claim[256], 1);
+                slice = k < half ? k : half + atomicAdd(&a.claim[257], 1);
+            } else {
+                const int j = atomicAdd(&a.claim[257], 1);
+                slice = j < half ? half + j : atomicAdd(&a.claim[256], 1);
+            }
+        }
+        s_slice = slice;
     }
     __syncthreads();
+    const int bx = s_slice;                              // this CTA's slice of the tile list / training set
 
     double accT[EG], acc1[GRAD ? EG : 1][D], acc2[GRAD ? EG : 1][D];
 #pragma unroll
@@ -135,8 +158,14 @@ mm_step_single(const SingleStepArgs a)
             for (int k = 0; k < D; ++k) acc1[g][k] = acc2[g][k] = 0.0;
     }
 
-    const int t_begin = (int)((long long)a.total_tiles * bx / P);
-    const int t_end = (int)((long long)a.total_tiles * (bx + 1) / P);
+    int t_begin = (int)((long long)a.total_tiles * bx / P);
+    int t_end = (int)((long long)a.total_tiles * (bx + 1) / P);
+    if (a.claim) {
+        const int half = P >> 1, sm = bx < half ? bx : bx - half;
+        const long long base = bx < half ? 0 : a.tiles_big, cnt = bx < half ? a.tiles_big : a.total_tiles - a.tiles_big;
+        t_begin = (int)(base + cnt * sm / half);
+        t_end = (int)(base + cnt * (sm + 1) / half);
+    }
     int I = 0, J = 0;                                    // tile being consumed
     {
         int rem = t_begin, row = 0;

@@ -685,7 +685,8 @@ struct NextPrep { bool on = false; const double *Uint = nullptr; const double *l
 // grad_mode: 0 forward values only, 1 all moments the adjoint reads, 2 first step of a rollout whose d/dx0 is not
 // requested (mm_pairs.cuh).
 static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int ctas, int P, long long total_tiles, int grad_mode,
-                    double *us, double *cst, double *mu, double *var, double *tape, const NextPrep &next = NextPrep())
+                    double *us, double *cst, double *mu, double *var, double *tape, const NextPrep &next = NextPrep(),
+                    int *claim_row = nullptr)
 {
     const bool want_grad = grad_mode != 0;
     const size_t mat = (size_t)h->ld * h->ld;
@@ -712,6 +713,8 @@ static int run_step(gpmpc_ctx *h, const StepDims &d, int t, int ctas, int P, lon
             sa.prep_next = (next.on && d.G == 1) ? 1 : 0;
             sa.Uint = next.Uint; sa.lam_group = next.lam_group; sa.us_w = us; sa.cst_w = cst; sa.act_var = next.act_var;
             sa.dbg = nullptr;
+            sa.claim = nullptr; sa.tiles_big = 0;
+            if (claim_row) { sa.claim = claim_row + (size_t)g * kClaimStride; sa.tiles_big = (int)(total_tiles * h->opt_single_big / 1000); }
             sa.l2_base = nullptr; sa.l2_bytes = 0; sa.l2_hit = 0.f;
             if (h->opt_l2_persist) {
                 if (h->l2_persist_max < 0) {                 // first use: device limits, carve out the persisting part of L2
@@ -962,6 +965,18 @@ static int forward(gpmpc_ctx *h, int B, int H, const double *x0_dev, const doubl
             return fail(h, GPMPC_ERR_CUDA, std::string("mm_rollout_single: ") + cudaGetErrorString(e));
         cudaGetLastError();                            // the grid does not fit: one launch per step instead
     }
+    // one rollout on a grid of exactly two CTAs per SM: the CTAs claim unequal slices (mm_step_single.cuh)
+    int *claim = nullptr;
+    {
+        int sms = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+        if (B == 1 && H > 0 && h->opt_single_big > 500 && w.ctas == SINGLE_CTAS_PER_SM * sms && SINGLE_CTAS_PER_SM == 2 && sms <= 256) {
+            const size_t bytes = (size_t)H * d.G * kClaimStride * sizeof(int);
+            GP_CUDA(h, h->claim.reserve(bytes));
+            GP_CUDA(h, cudaMemsetAsync(h->claim.p, 0, bytes, h->stream));
+            claim = h->claim.as<int>();
+        }
+    }
     for (int t = 1; t <= H; ++t) {
         if (!(begun && t == 1) && (!fused_prep || t == 1)) {
             prep_step_kernel<<<dim3((B + 127) / 128, d.G), blk, 0, h->stream>>>(d, t, h->mu.as<double>(), h->var.as<double>(),
@@ -972,7 +987,8 @@ static int forward(gpmpc_ctx *h, int B, int H, const double *x0_dev, const doubl
         next.on = fused_prep && t < H; next.Uint = w.Uint; next.lam_group = w.lamg; next.act_var = act_var;
         const int grad_mode = !want_grad ? 0 : ((t == 1 && !need_gx0) ? 2 : 1);
         rc = run_step(h, d, t, w.ctas, w.P, w.total_tiles, grad_mode, w.us, w.cst, h->mu.as<double>(),
-                      h->var.as<double>(), h->tape.as<double>(), next);
+                      h->var.as<double>(), h->tape.as<double>(), next,
+                      claim ? claim + (size_t)(t - 1) * d.G * kClaimStride : nullptr);
         if (rc) return rc;
         if (h->time_pairs) {
             GP_CUDA(h, cudaEventSynchronize(h->ev1));

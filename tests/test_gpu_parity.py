@@ -1263,6 +1263,41 @@ def test_persistent_single_rollout_matches_stepwise_path(gp):
         norm_close(xt.grad.cpu().numpy(), xt2.grad.cpu().numpy(), 1e-8)
 
 
+def test_single_rollout_unequal_slices_match_equal_slices(gp):
+    """B = 1 on a grid of two CTAs per SM: the CTAs claim unequal slices of the tile list (the first arrival on an SM
+    the big one).  Whatever the share, the slices partition the tiles and the partial sums are added in slice order:
+    same result up to summation order, identical from call to call, and equal to the C oracle."""
+    from oracle import oracle as orc
+    for n, E, m, H in ((1000, 4, 1, 5), (4096, 4, 1, 30)):
+        dyn, S, A, nxt, rng = _synth_dynamics(gp, n, E, m, seed=21)
+        Q = 2 * np.eye(E); R = 0.01 * np.eye(m)
+        br = gp.BatchedRollouts(dyn, Q, R)
+        x0 = rng.uniform(-0.5, 0.5, E); U = rng.uniform(-0.3, 0.3, (1, H, m))
+        br.cost_and_grad(x0, U, -1.0, host_out=True)                      # fit
+        res = {}
+        try:
+            for share in (500, 660, 850):
+                dyn._bundle.set_option("single_big_share", share)
+                c1, g1 = br.cost_and_grad(x0, U, -1.0, host_out=True)
+                c2, g2 = br.cost_and_grad(x0, U, -1.0, host_out=True)
+                assert np.array_equal(c1, c2) and np.array_equal(g1, g2)  # deterministic: no dependence on who claimed what
+                res[share] = (c1, g1)
+        finally:
+            dyn._bundle.set_option("single_big_share", 660)
+        for share in (660, 850):
+            close(res[share][0], res[500][0], 1e-8); norm_close(res[share][1], res[500][1], 1e-8)
+        if n <= 1000:
+            X = np.concatenate([S, A], 1)
+            lam = np.full((E, E + m), 2.0)
+            fits = [orc.fit(X, nxt[:, a], lam[a], 1.0, float(np.float32(0.1 ** 2)) ** 0.5) for a in range(E)]
+            c, gr, _, _ = orc.c_rollout_cost_grad(X, [f["Ky_inv"] for f in fits], [f["beta"] for f in fits], lam, np.ones(E),
+                                                  x0, U[0], -1.0, Q, R)
+            for share in res:
+                close(res[share][0][0], c, RTOL); norm_close(res[share][1][0], gr, RTOL)
+    with pytest.raises(Exception):
+        dyn._bundle.set_option("single_big_share", 100)
+
+
 def test_monte_carlo_checkers_agree_with_the_exact_moments(gp):
     """The reference's own test strategy (src/test/tools/test_uncertainty_prop.py:62-69,113-120,173-180): the analytic
     mean / variance / covariance against the Monte-Carlo checkers (T = 10 000), within its 2 % / 5 % / 2 %-style bands

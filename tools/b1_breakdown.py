@@ -17,6 +17,10 @@ for a in range(E):
 dyn.append_train_data(S, A, nxt)
 dyn._sync_propagation_hypers()
 bundle = dyn._bundle
+if os.environ.get('BIG'):
+    bundle.set_option('single_big_share', int(os.environ['BIG'])); print('single_big_share', os.environ['BIG'])
+if os.environ.get('PERSIST'):
+    bundle.set_option('persistent_single', 1); print('persistent whole-horizon kernel ON')
 Q = 2 * np.eye(E); R = 0.01 * np.eye(m)
 x0 = np.zeros((1, E)); U = rng.uniform(-0.3, 0.3, (1, H, m)); g = np.full(1, -1.0)
 dev = bundle.device
@@ -33,7 +37,8 @@ def med(f):
 def dev_call(want_grad=True):
     bundle.cost_grad(x0d, Ud, gd, Q, R, want_grad=want_grad, host_out=False); torch.cuda.synchronize()
 
-print(f"n={n} H={H}  us per evaluation (median of {reps})")
+c0, g0, _, _ = bundle.cost_grad(x0, U, g, Q, R)
+print(f"n={n} H={H}  cost {c0[0]:.15g} |grad| {float(np.linalg.norm(g0)):.15g}  us per evaluation (median of {reps})")
 print("  host in/out, cost+grad      ", round(med(lambda: bundle.cost_grad(x0, U, g, Q, R)), 1))
 print("  host in/out, cost only      ", round(med(lambda: bundle.cost_grad(x0, U, g, Q, R, want_grad=False)), 1))
 print("  device in/out + sync, +grad ", round(med(dev_call), 1))
