@@ -394,12 +394,24 @@ def run_ours(args):
         bundle.cost_grad(x1, U1, g1, Q, R, want_grad=True, host_out=False); torch.cuda.synchronize()
         single_ms, _ = bundle.pair_kernel_timing()
         bundle.set_pair_timing(False)
+        # the same evaluation un-instrumented (consecutive steps overlap through programmatic dependent launch): whole
+        # evaluation, device buffers, adjoint and prologue included -- a lower bound of the step kernels' bandwidth
+        ev = []
+        for _ in range(12):
+            torch.cuda.synchronize(); t1 = time.perf_counter()
+            bundle.cost_grad(x1, U1, g1, Q, R, want_grad=True, host_out=False); torch.cuda.synchronize()
+            ev.append(time.perf_counter() - t1)
+        eval_s = float(np.median(ev[2:]))
         line["roofline_single"] = {
             "bound": "hbm", "kernel": "mm_step_single<5,4,grad> (B=1: one fused launch per horizon step)",
             "achieved": bytes_algo / (single_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": bytes_algo / (single_ms * 1e-3) / 1e9 / hbm_peak,
             "traffic": ncu_traffic("mm_step_single")[0], "traffic_source": ncu_traffic("mm_step_single")[1],
             "ms_per_launch": single_ms / H,
+            "in_evaluation": {"ms_per_evaluation": 1e3 * eval_s, "achieved": bytes_algo / eval_s / 1e9,
+                              "frac": bytes_algo / eval_s / 1e9 / hbm_peak,
+                              "note": "algorithmic bytes of the H steps / wall time of one whole un-instrumented B=1 "
+                                      "evaluation (device buffers, prologue and adjoint included)"},
             "note": "algorithmic bytes = H*E*n(n+1)/2*8 (Wt upper triangle once per step) / CUDA-event time of the H "
                     "launches of one B=1 evaluation (events on the library stream, programmatic dependent launch off "
                     "between timed launches)"}
