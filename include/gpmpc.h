@@ -61,7 +61,10 @@ int gpmpc_synchronize(gpmpc_handle h);
  *   "split_timeline" (0):    stamp the inter-GPU exchange of every step (see gpmpc_split_last_exchange_us).
  *   "l2_persist" (0):        1 = few-rollouts kernels launch with an L2 access-policy window over the weights so that the
  *                            part of Wt that fits the persisting L2 carve-out stays resident from one horizon step to the
- *                            next (measured: no effect on B200, the kernel is not bound by the stream alone).            */
+ *                            next (measured: no effect on B200, the kernel is not bound by the stream alone).
+ *   "single_big_share" (660): per mille (500..900) of the tiles of a single rollout that go to the CTA that arrived first on
+ *                            each SM (the warp scheduler favours it); 500 = equal static slices.  The result does not
+ *                            depend on which CTA claimed which slice.                                                    */
 int gpmpc_set_option(gpmpc_handle h, const char *name, int value);
 int gpmpc_num_train(gpmpc_handle h);
 
