@@ -127,6 +127,8 @@ def run_ref_runner(device, n, Hs, steps, warmup, timeout=1500):
     cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_runner.py"), "--device", device, "--n", str(n),
            "--H", ",".join(str(h) for h in Hs), "--steps", str(steps), "--warmup", str(warmup)]
     env = dict(os.environ)
+    if int(env.get("WORLD_SIZE", "1")) > 1:
+        env.pop("OMP_NUM_THREADS", None)          # torchrun pins it to 1 per rank; the reference arm gets all host cores
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
         env.pop(k, None)
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
