@@ -306,3 +306,63 @@ def test_batched_simulator_closed_loop_on_a_fake_plant():
     assert np.all(np.abs(out["states"][-1]) < 1e-2) and np.all(np.abs(out["actions"]) <= 1.0 + 1e-12)
     far = np.abs(x0[:, 0]) > 0.1
     assert np.all(np.abs(out["states"][3, far, 0]) < 0.5 * np.abs(x0[far, 0]))                    # the controller, not the plant's 0.9
+
+
+def _claim_slices(arrivals, P):
+    """Mirror of the slice claim in csrc/mm_step_single.cuh: `arrivals` lists the SM of every CTA in the order their
+    atomics are served.  Returns the slice each CTA ends up with."""
+    half = P // 2
+    per_sm, nbig, nsmall, out = {}, 0, 0, []
+    for sm in arrivals:
+        first = per_sm.get(sm, 0) == 0
+        per_sm[sm] = per_sm.get(sm, 0) + 1
+        if first:
+            k = nbig; nbig += 1
+            if k < half:
+                out.append(k)
+            else:
+                out.append(half + nsmall); nsmall += 1
+        else:
+            j = nsmall; nsmall += 1
+            if j < half:
+                out.append(half + j)
+            else:
+                out.append(nbig); nbig += 1
+    return out
+
+
+def _slice_range(s, P, total, tiles_big):
+    half = P // 2
+    sm = s if s < half else s - half
+    base, cnt = (0, tiles_big) if s < half else (tiles_big, total - tiles_big)
+    return base + cnt * sm // half, base + cnt * (sm + 1) // half
+
+
+def test_single_rollout_slice_claim_is_always_a_bijection():
+    """The CTAs of the single-rollout step kernel claim their tile slices (first arrival on an SM: a big one).  Whatever
+    the arrival order and however unevenly the hardware spreads the CTAs over the SMs, every slice is taken exactly
+    once, and the slices partition the tile list."""
+    rng = np.random.default_rng(5)
+    sms = 148
+    P = 2 * sms
+    cases = [np.repeat(np.arange(sms), 2)]                                  # two per SM, in order
+    cases.append(np.concatenate([np.arange(sms), np.arange(sms)]))          # all first arrivals, then all second ones
+    for _ in range(40):
+        a = np.repeat(np.arange(sms), 2); rng.shuffle(a); cases.append(a)   # two per SM, any order
+    for _ in range(40):
+        cases.append(rng.integers(0, sms, P))                               # 0..k CTAs per SM
+    cases.append(np.zeros(P, dtype=int))                                    # everything on one SM
+    cases.append(np.arange(P) % (P // 4))                                   # four per SM on a quarter of the SMs
+    for a in cases:
+        got = _claim_slices(list(a), P)
+        assert sorted(got) == list(range(P))
+    a = np.repeat(np.arange(sms), 2)
+    got = _claim_slices(list(a), P)
+    assert all(s < sms for s in got[0::2]) and all(s >= sms for s in got[1::2])   # first arrival big, second small
+    for total in (296, 297, 528, 8256, 131328):
+        for share in (500, 660, 900):
+            tiles_big = total * share // 1000
+            edges = sorted(_slice_range(s, P, total, tiles_big) for s in range(P))
+            assert edges[0][0] == 0 and edges[-1][1] == total
+            assert all(edges[i][1] == edges[i + 1][0] for i in range(P - 1))
+            assert all(lo <= hi for lo, hi in edges)
